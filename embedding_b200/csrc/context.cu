@@ -1,0 +1,79 @@
+// context.cu -- ctx lifecycle, error text, pinned host memory, phase timings.
+#include "dge_internal.cuh"
+
+static thread_local std::string g_tls_error;
+
+void dge_set_error(dge_ctx *ctx, const std::string &msg) {
+    g_tls_error = msg;
+    if (ctx) ctx->err = msg;
+}
+int dge_fail(dge_ctx *ctx, int code, const std::string &msg) {
+    dge_set_error(ctx, msg);
+    return code;
+}
+
+extern "C" {
+
+int dge_version(void) { return 100; }
+
+int dge_create(int device, dge_ctx **out) {
+    if (!out) return dge_fail(nullptr, DGE_E_INVALID, "dge_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return dge_fail(nullptr, DGE_E_NO_DEVICE,
+                        std::string("dge_create: no CUDA device (") + cudaGetErrorString(e) +
+                            "); libdge has no CPU fallback");
+    if (device < 0 || device >= n)
+        return dge_fail(nullptr, DGE_E_INVALID, "dge_create: device ordinal out of range");
+    cudaDeviceProp prop;
+    DGE_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return dge_fail(nullptr, DGE_E_NO_DEVICE,
+                        std::string("dge_create: device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                            std::to_string(prop.minor) + "; libdge is built for sm_100a (B200) only");
+    DGE_CUDA(nullptr, cudaSetDevice(device));
+    dge_ctx *ctx = new dge_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return dge_fail(nullptr, DGE_E_CUDA, "dge_create: stream/event creation failed");
+    }
+    *out = ctx;
+    return DGE_OK;
+}
+
+void dge_destroy(dge_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    delete ctx;
+}
+
+const char *dge_last_error(const dge_ctx *ctx) { return ctx ? ctx->err.c_str() : g_tls_error.c_str(); }
+
+void *dge_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void dge_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int dge_phase_ms(const dge_ctx *ctx, const char *phase, float *ms) {
+    if (!ctx || !phase || !ms) return DGE_E_INVALID;
+    auto it = ctx->phase_ms.find(phase);
+    if (it == ctx->phase_ms.end()) return DGE_E_INVALID;
+    *ms = it->second;
+    return DGE_OK;
+}
+
+int64_t dge_kernel_launches(const dge_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+} // extern "C"

@@ -1,0 +1,130 @@
+// dge_internal.cuh -- shared internals of libdge.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/dge.h"
+
+#define DGE_WARP 32
+
+struct dge_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    std::map<std::string, float> phase_ms;
+    int64_t launches = 0;
+};
+
+// One 32-byte sector per edge: a walk step is ONE dependent random load.  The record carries the
+// chosen column's and the alias column's destination together with their CSR row (start, degree),
+// so the next step needs no row_ptr lookup.
+struct __align__(32) dge_edge_rec {
+    double prob;      // alias-table acceptance threshold of this column
+    int32_t dst;      // col[i]
+    int32_t adst;     // col[alias[i]]  (alias == -1  =>  dst)
+    uint32_t start0;  // row_ptr[dst]
+    uint32_t deg0;    // degree(dst)
+    uint32_t start1;  // row_ptr[adst]
+    uint32_t deg1;    // degree(adst)
+};
+static_assert(sizeof(dge_edge_rec) == 32, "edge record must be one 32 B sector");
+
+struct dge_graph {
+    dge_ctx *ctx = nullptr;
+    int32_t nv = 0, ns = 0;
+    int64_t ne = 0;
+    int64_t *row_ptr = nullptr;   // [nv+1]
+    int32_t *col = nullptr;       // [ne]
+    double *w = nullptr;          // [ne]
+    double *prob = nullptr;       // [ne]
+    int32_t *alias = nullptr;     // [ne]
+    double *out_degree = nullptr; // [nv]
+    int32_t *sources = nullptr;   // [ns]
+    double *src_w = nullptr;      // [ns] out_degree of each source
+    double *src_prob = nullptr;   // [ns]
+    int32_t *src_alias = nullptr; // [ns]
+    double *sws = nullptr;        // [1] device copy of sourceWeightSum
+    double source_weight_sum = 0;
+    dge_edge_rec *rec = nullptr;  // [ne]
+    dge_edge_rec *srec = nullptr; // [ns]
+};
+
+struct dge_corpus {
+    dge_ctx *ctx = nullptr;
+    int64_t n = 0;          // walks
+    int32_t L = 0;          // positions
+    int32_t n_ids = 0;      // id space (graph vertices)
+    int32_t *tok = nullptr; // POSITION-major [L][n]: the walk kernel's stores are coalesced
+};
+
+struct dge_model {
+    dge_ctx *ctx = nullptr;
+    int32_t V = 0, dim = 0, stride = 0; // stride = dim rounded up to 4 floats (zero padded)
+    int64_t pairs = 0;
+    float *syn0 = nullptr, *syn1neg = nullptr; // device [V*stride]
+    int32_t *id_of_word = nullptr;             // device [V]
+};
+
+// ---- error plumbing
+void dge_set_error(dge_ctx *ctx, const std::string &msg);
+int dge_fail(dge_ctx *ctx, int code, const std::string &msg);
+#define DGE_CUDA(ctx, expr)                                                                       \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return dge_fail((ctx), DGE_E_CUDA,                                                    \
+                            std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                                ":" + std::to_string(__LINE__) + ")");                            \
+    } while (0)
+#define DGE_LAUNCH_CHECK(ctx)                 \
+    do {                                      \
+        (ctx)->launches++;                    \
+        DGE_CUDA((ctx), cudaGetLastError());  \
+    } while (0)
+
+// phase timing with CUDA events on ctx->stream
+struct dge_phase_timer {
+    dge_ctx *ctx;
+    const char *name;
+    dge_phase_timer(dge_ctx *c, const char *n) : ctx(c), name(n) { cudaEventRecord(ctx->ev0, ctx->stream); }
+    void stop() {
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaEventSynchronize(ctx->ev1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        ctx->phase_ms[name] = ms;
+    }
+};
+
+template <typename T>
+static inline cudaError_t dge_malloc(T **p, size_t n) {
+    return cudaMalloc((void **)p, (n ? n : 1) * sizeof(T));
+}
+
+// ---- Philox4x32-10 (Salmon et al., SC'11).  Same stream definition as oracle/dge_oracle.c.
+__host__ __device__ static inline void dge_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                         uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        if (r) { k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// 53-bit uniform on the java.util.Random.nextDouble() grid: (bits >> 11) * 2^-53
+__host__ __device__ static inline double dge_u53(uint32_t lo, uint32_t hi) {
+    uint64_t bits = ((uint64_t)hi << 32) | lo;
+    return (double)(bits >> 11) * 0x1.0p-53;
+}

@@ -1,0 +1,70 @@
+"""Synthetic inputs of the named shapes (BASELINE.json configs).
+
+The reference ships no flow data, so every config runs on seeded synthetic flows:
+  * `flow_tensor(n, seed, density)`            F[src, hour(24), dst] int32 trip counts (CA 77 / tract 801)
+  * `powerlaw_flow_graph(n_regions, L, seed)`  COO of a time-sliced graph with Zipf out-degrees and
+                                               Pareto integer weights (100K / 1M regions x 24 slices)
+  * `spatial_weights(n, seed)`                 exp(-100 d) over random centroids (SpatialGraph.java:43-48)
+numpy only; used by tests, bench.py and the host mirror.
+"""
+import json
+import os
+
+import numpy as np
+
+_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def tract_ids():
+    """The 801 real Chicago tract ids (fixture extracted from the reference's miscs/POI_tract.pickle)."""
+    with open(os.path.join(_GOLDEN, "poi_tract.json")) as f:
+        return np.array(json.load(f)["tract_ids"], np.int32)
+
+
+def ca_ids():
+    return np.arange(1, 78, dtype=np.int32)  # community areas are numbered 1..77 (CommunityAreas.java:210)
+
+
+def flow_tensor(n, seed=2013, density=0.6, alpha=1.2, scale=3.0):
+    """F[src, hour, dst] int32: floor(Pareto(alpha) * scale) masked to `density`, heavier in daytime hours."""
+    rng = np.random.default_rng(seed)
+    F = np.floor(rng.pareto(alpha, size=(n, 24, n)) * scale).astype(np.int64)
+    mask = rng.random((n, 24, n)) < density
+    hour_profile = 0.35 + 0.65 * np.sin(np.linspace(0, np.pi, 24)) ** 2
+    F = np.floor(F * mask * hour_profile[None, :, None]).astype(np.int64)
+    return np.minimum(F, 2 ** 20).astype(np.int32)
+
+
+def spatial_weights(n, seed=2013, extent=0.25):
+    """w = exp(-100 * centroid distance) over `n` random 2-D centroids (degrees, like the shapefile's)."""
+    rng = np.random.default_rng(seed)
+    xy = rng.random((n, 2)) * extent
+    d = np.sqrt(((xy[:, None, :] - xy[None, :, :]) ** 2).sum(-1))
+    return np.exp(-d * 100.0)
+
+
+def powerlaw_flow_graph(n_regions, L=24, seed=100000, mean_degree=42, cap=4096, zipf_a=1.6):
+    """Time-sliced synthetic flow graph: node (h, r) has id h*n_regions + r (first-appearance order of a
+    host that walks layers then regions), edges (h, r) -> ((h+1)%L, r') grouped by source.
+
+    out-degree ~ Zipf(zipf_a) rescaled to `mean_degree`, capped at `cap`; destinations by preferential
+    attachment over regions (popularity ~ Zipf); weights floor(Pareto(1.2)) + 1.
+    Returns dict(n_vertices, src, dst, w, sources, v_layer, v_region)."""
+    rng = np.random.default_rng(seed)
+    nv = n_regions * L
+    raw = rng.zipf(zipf_a, size=nv).astype(np.float64)
+    raw = np.minimum(raw, cap * 4.0)
+    deg = np.maximum(1, np.minimum(cap, np.round(raw * (mean_degree / raw.mean())))).astype(np.int64)
+    deg = np.minimum(deg, n_regions)
+    ne = int(deg.sum())
+    src = np.repeat(np.arange(nv, dtype=np.int32), deg)
+    pop = rng.zipf(1.3, size=n_regions).astype(np.float64)
+    cdf = np.cumsum(pop / pop.sum())
+    dst_region = np.searchsorted(cdf, rng.random(ne)).astype(np.int64)
+    np.minimum(dst_region, n_regions - 1, out=dst_region)
+    layer = (src // n_regions).astype(np.int64)
+    dst = (((layer + 1) % L) * n_regions + dst_region).astype(np.int32)
+    w = (np.floor(rng.pareto(1.2, size=ne)) + 1.0).astype(np.float64)
+    v = np.arange(nv, dtype=np.int32)
+    return dict(n_vertices=nv, src=src, dst=dst, w=w, sources=np.arange(n_regions, dtype=np.int32),
+                v_layer=(v // n_regions).astype(np.int32), v_region=(v % n_regions).astype(np.int32))

@@ -1,0 +1,154 @@
+/*
+ * dge.h -- C ABI of libdge.so: the B200-native (sm_100a) replacement of the region-embedding
+ * hot path of thekingofkings/embedding:
+ *     stage 1  weighted random walks over the time-sliced mobility-flow graph
+ *     stage 2  skip-gram negative-sampling SGD over the walk corpus
+ *
+ * The reference is pure Java and has no FFI of its own.  Each entry point below names the Java
+ * symbol it stands under (paths relative to embedding/src/main/java/embedding/ of the reference);
+ * INTEGRATION.md shows the JNI / Panama stubs a maintainer adds to the unchanged Java classes.
+ *
+ * Conventions
+ *   - plain C types only; every buffer in a signature is HOST memory owned by the caller
+ *     (device memory never crosses the ABI);
+ *   - opaque handles are library-owned and released only by the matching *_free;
+ *   - every call is blocking; a ctx (one per GPU / process) is used by one thread at a time;
+ *   - return 0 on success, a negative dge_status otherwise; dge_last_error() has the text;
+ *   - there is NO CPU fallback: without a usable sm_100 device dge_create fails with DGE_E_NO_DEVICE.
+ */
+#ifndef DGE_H
+#define DGE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dge_ctx dge_ctx;
+typedef struct dge_graph dge_graph;
+typedef struct dge_corpus dge_corpus;
+typedef struct dge_model dge_model;
+
+typedef enum {
+    DGE_OK = 0,
+    DGE_E_INVALID = -1,   /* bad argument (null pointer, out-of-range id, size) */
+    DGE_E_NO_DEVICE = -2, /* no CUDA device / not sm_100 */
+    DGE_E_CUDA = -3,      /* CUDA runtime error */
+    DGE_E_IO = -4,        /* file error */
+    DGE_E_LIMIT = -5,     /* documented size limit exceeded */
+    DGE_E_COMM = -6       /* NCCL / multi-GPU error */
+} dge_status;
+
+enum { DGE_SAMPLER_ALIAS = 0, /* LayeredGraph.sampleVertexSequence()    :232-252 */
+       DGE_SAMPLER_CDF = 1 }; /* LayeredGraph.sampleVertexSequence_OV() :260-279 */
+
+/* ------------------------------------------------------------------ context */
+int dge_version(void);
+/* device: CUDA ordinal (one process per GPU uses LOCAL_RANK). */
+int dge_create(int device, dge_ctx **out);
+void dge_destroy(dge_ctx *ctx);
+/* ctx may be NULL: returns the calling thread's last error (e.g. from a failed dge_create). */
+const char *dge_last_error(const dge_ctx *ctx);
+/* Pinned host buffers (optional; any host pointer is accepted everywhere, pinned ones copy faster). */
+void *dge_host_alloc(size_t bytes);
+void dge_host_free(void *p);
+/* Device time in ms of the most recent run of a named internal phase, measured with CUDA events on
+ * the launching stream ("csr", "alias", "pack", "walk", "vocab", "sgns", "tokens_d2h", ...).
+ * Returns DGE_E_INVALID for an unknown name. */
+int dge_phase_ms(const dge_ctx *ctx, const char *phase, float *ms);
+/* Number of library kernels launched since dge_create (for bench.py's gpu_launches). */
+int64_t dge_kernel_launches(const dge_ctx *ctx);
+
+/* ------------------------------------------------------------------ stage 1a: graph + alias tables
+ * Stands under LayeredGraph.addEdge :157-174, addSourceVertex :180-189, initiateAliasTables :195-226
+ * (row tables: Vertex.initiateAliasTable :54-82).  The Java host owns names and order: it passes
+ * vertex ids in first-appearance order, COO edges in insertion order, the source list in order.
+ * CSR rows keep insertion order; out_degree is the left-to-right double sum of the row
+ * (Vertex.addOutEdge :46-49) unless out_degree != NULL (host-owned values, e.g. after
+ * SpatialGraph.keepNearestKVertices :29-35); source_weight_sum likewise (:188 / SpatialGraph.java:57).
+ * prob/alias tables are bit-identical to the Java ones (IEEE double, same operation order).
+ * Limits: n_edges < 2^31, a single row (or the source list) <= 2^25 entries. */
+int dge_graph_build(dge_ctx *ctx, int32_t n_vertices, int64_t n_edges, const int32_t *src, const int32_t *dst,
+                    const double *w, int32_t n_sources, const int32_t *sources, const double *out_degree,
+                    const double *source_weight_sum, dge_graph **out);
+int dge_graph_sizes(const dge_graph *g, int32_t *n_vertices, int64_t *n_edges, int32_t *n_sources);
+/* Read-back (Vertex.probTable / aliasTable / outDegree, LayeredGraph.probTable / aliasTable); any
+ * pointer may be NULL.  row_ptr[nv+1], col/w/prob/alias[ne] in CSR order, out_degree[nv],
+ * src_prob/src_alias[ns], source_weight_sum[1].  alias == -1 means "no alias" as in Java. */
+int dge_graph_tables(const dge_graph *g, int64_t *row_ptr, int32_t *col, double *w, double *prob,
+                     int32_t *alias, double *out_degree, double *src_prob, int32_t *src_alias,
+                     double *source_weight_sum);
+/* Batched Vertex.sampleNextVertex(double x) :123-132 (sampler ALIAS) / sampleNextVertex_OV :89-98 with the
+ * uniform supplied (sampler CDF): out[i] = next vertex of v[i] for uniform x[i], -1 if v[i] has no
+ * out-edge.  v[i] == -1 draws a source vertex instead (sampleVertexSequence :233-242). */
+int dge_graph_sample_next(const dge_graph *g, int64_t n, const int32_t *v, const double *x, int sampler,
+                          int32_t *out);
+void dge_graph_free(dge_graph *g);
+
+/* ------------------------------------------------------------------ stage 1b: walks
+ * Stands under the loop of CrossTimeGraph.sampleSequenceHelper :134-140 / SpatialGraph.outputSampleSequence
+ * :103-110 calling LayeredGraph.sampleVertexSequence() :232-252.  Walk i uses the counter-based stream
+ * Philox4x32-10(key = seed, counter = (first_walk_id + i, draw/2)): draw 0 picks the source, draw t the
+ * t-th step; results do not depend on how walks are split over calls or GPUs.  (The reference's
+ * java.util.Random is unseeded, LayeredGraph.java:14, so its walks are not reproducible.) */
+int dge_walk(const dge_graph *g, int64_t n_walks, int64_t first_walk_id, int32_t num_layer, uint64_t seed,
+             int sampler, dge_corpus **out);
+/* Corpus from host tokens [n_walks, L] (int32 ids in [0,n_ids), -1 = padding). */
+int dge_corpus_from_tokens(dge_ctx *ctx, const int32_t *tokens, int64_t n_walks, int32_t L, int32_t n_ids,
+                           dge_corpus **out);
+int dge_corpus_shape(const dge_corpus *c, int64_t *n_walks, int32_t *L, int32_t *n_ids);
+/* tokens[n_walks * L] walk-major, -1 padded after a dead end (Java: sampleNextVertex() == null). */
+int dge_corpus_tokens(const dge_corpus *c, int32_t *tokens);
+/* In-place change of id space: token t at walk position j becomes id_map[t] + j * position_stride; the
+ * corpus then reports new_n_ids.  This is how the host puts both corpora of the "usespatial" run into ONE
+ * vocabulary, exactly as the token strings do in the reference: a cross-time token "<h>-<region>"
+ * (CrossTimeGraph.java:80-82) and a spatial token "<j>-<region>" (SpatialGraph.java:105-108) are the same
+ * word when h == j.  id_map has the corpus' current n_ids entries, all results must lie in [0, new_n_ids). */
+int dge_corpus_relabel(dge_corpus *c, const int32_t *id_map, int32_t new_n_ids, int32_t position_stride);
+/* Number of tokens != -1 (walk steps taken, counting the source draw). */
+int dge_corpus_count_tokens(const dge_corpus *c, int64_t *n_tokens);
+/* `.seq` text (CrossTimeGraph.java:136-137, SpatialGraph.java:105-110): one walk per line, tokens
+ * "<layer>-<region>" joined by one space, '\n' terminated, no header.  label_layer / label_region are
+ * per vertex id; position_prefix != 0 writes "<j>-<region>" with j the position in the walk (spatial
+ * mode) and ignores label_layer.  append != 0 appends to an existing file. */
+int dge_corpus_write_seq(const dge_corpus *c, const int32_t *label_layer, const int32_t *label_region,
+                         int position_prefix, const char *path, int append);
+void dge_corpus_free(dge_corpus *c);
+
+/* ------------------------------------------------------------------ stage 2: skip-gram
+ * Stands under DeepWalk.learnEmbedding :32-83: Word2Vec.Builder()...build() :73-76 and w2v.fit() :79
+ * (DL4J 0.7.2, external) and WordVectorSerializer.writeWordVectors :82. */
+typedef struct {
+    int32_t dim;            /* layerSize(...)         DeepWalk.java:62-66,74 */
+    int32_t window;         /* windowSize(numLayer)   :74 */
+    int32_t negative;       /* negativeSample(5)      :75 */
+    int32_t min_count;      /* minWordFrequency(2)    :73 */
+    int32_t epochs;         /* iterations(1) x epochs(1) */
+    int32_t neg_table_size; /* DL4J: 100000 */
+    int32_t exp_table_size; /* sigmoid lookup table entries (1000) */
+    int32_t concurrency;    /* sentences in flight: 0 = fill the GPU; 1 = sequential (parity tests);
+                               the analogue of workers(8), :75 */
+    float lr;               /* 0.025 */
+    float min_lr;           /* 1e-4 */
+    uint64_t seed;
+} dge_sgns_params;
+void dge_sgns_default_params(dge_sgns_params *p);
+/* Trains on the concatenation of n corpora (FileSentenceIterator over both .seq files, :48-50). All
+ * corpora must share one id space (n_ids).  Vocabulary: ids with count >= min_count, indexed by
+ * descending count (ties: ascending id). */
+int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_corpora,
+                   const dge_sgns_params *params, dge_model **out);
+int dge_model_shape(const dge_model *m, int32_t *vocab_size, int32_t *dim, int64_t *pairs_trained);
+/* syn0 / syn1neg [V*dim] row-major by vocabulary index; id_of_word[V] maps back to corpus ids. NULLs ok. */
+int dge_model_vectors(const dge_model *m, float *syn0, float *syn1neg, int32_t *id_of_word);
+/* `.vec` text (writeWordVectors, consumers python/embeddingEvaluation_tract.py:139-166): no header, one line
+ * per vocabulary word "<layer>-<region> v1 ... vD".  label arrays are indexed by corpus id. */
+int dge_model_write_vec(const dge_model *m, const int32_t *label_layer, const int32_t *label_region,
+                        const char *path);
+void dge_model_free(dge_model *m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

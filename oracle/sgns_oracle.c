@@ -1,0 +1,337 @@
+/*
+ * sgns_oracle.c -- CPU ORACLE for stage 2.  TEST INFRASTRUCTURE ONLY (see sgns_oracle.h).
+ * PARITY UNPINNED: restates the published word2vec skip-gram algorithm with the DL4J 0.7.2
+ * parameterisation of SURVEY.md 8(a) A14; the DL4J sources are not under /root/reference.
+ * Call sites it stands in for: DeepWalk.java:73-76 (builder), :79 (fit).
+ */
+#include "sgns_oracle.h"
+#include "dge_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <pthread.h>
+
+#define MAX_EXP 6.0f
+#define LCG_MUL 25214903917ULL
+#define LCG_ADD 11ULL
+
+struct ora_vocab {
+    int32_t n_ids, V;
+    int64_t total;
+    int32_t *word_of_id; /* n_ids */
+    int32_t *id_of_word; /* V */
+    int64_t *count;      /* V */
+};
+
+typedef struct { int64_t c; int32_t id; } cnt_id;
+static int cmp_cnt_desc(const void *a, const void *b) {
+    const cnt_id *x = (const cnt_id *)a, *y = (const cnt_id *)b;
+    if (x->c != y->c) return x->c > y->c ? -1 : 1;
+    return x->id < y->id ? -1 : (x->id > y->id);
+}
+
+ora_vocab *ora_vocab_build(const int32_t *tokens, int64_t n_tokens, int32_t n_ids, int32_t min_count) {
+    ora_vocab *v = (ora_vocab *)calloc(1, sizeof(*v));
+    v->n_ids = n_ids;
+    int64_t *cnt = (int64_t *)calloc((size_t)(n_ids ? n_ids : 1), sizeof(int64_t));
+    for (int64_t i = 0; i < n_tokens; i++)
+        if (tokens[i] >= 0) cnt[tokens[i]]++;
+    cnt_id *arr = (cnt_id *)malloc(sizeof(cnt_id) * (size_t)(n_ids ? n_ids : 1));
+    int32_t V = 0;
+    for (int32_t i = 0; i < n_ids; i++)
+        if (cnt[i] >= min_count && cnt[i] > 0) { arr[V].c = cnt[i]; arr[V].id = i; V++; }
+    qsort(arr, (size_t)V, sizeof(cnt_id), cmp_cnt_desc);
+    v->V = V;
+    v->word_of_id = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_ids ? n_ids : 1));
+    v->id_of_word = (int32_t *)malloc(sizeof(int32_t) * (size_t)(V ? V : 1));
+    v->count = (int64_t *)malloc(sizeof(int64_t) * (size_t)(V ? V : 1));
+    for (int32_t i = 0; i < n_ids; i++) v->word_of_id[i] = -1;
+    for (int32_t w = 0; w < V; w++) {
+        v->word_of_id[arr[w].id] = w;
+        v->id_of_word[w] = arr[w].id;
+        v->count[w] = arr[w].c;
+        v->total += arr[w].c;
+    }
+    free(arr); free(cnt);
+    return v;
+}
+void ora_vocab_free(ora_vocab *v) {
+    if (!v) return;
+    free(v->word_of_id); free(v->id_of_word); free(v->count); free(v);
+}
+int32_t ora_vocab_size(const ora_vocab *v) { return v->V; }
+int64_t ora_vocab_total_words(const ora_vocab *v) { return v->total; }
+void ora_vocab_tables(const ora_vocab *v, int32_t *word_of_id, int32_t *id_of_word, int64_t *count) {
+    if (word_of_id) memcpy(word_of_id, v->word_of_id, sizeof(int32_t) * (size_t)v->n_ids);
+    if (id_of_word) memcpy(id_of_word, v->id_of_word, sizeof(int32_t) * (size_t)v->V);
+    if (count) memcpy(count, v->count, sizeof(int64_t) * (size_t)v->V);
+}
+
+/* unigram^0.75 cumulative table (word2vec.c InitUnigramTable; DL4J makeTable). */
+void ora_neg_table(const ora_vocab *v, int32_t table_size, int32_t *table) {
+    int32_t V = v->V;
+    if (V == 0) { for (int32_t i = 0; i < table_size; i++) table[i] = 0; return; }
+    double pow_sum = 0;
+    for (int32_t w = 0; w < V; w++) pow_sum += pow((double)v->count[w], 0.75);
+    int32_t wi = 0;
+    double d1 = pow((double)v->count[0], 0.75) / pow_sum;
+    for (int32_t i = 0; i < table_size; i++) {
+        table[i] = wi;
+        if ((double)i / (double)table_size > d1) {
+            if (wi < V - 1) wi++;
+            d1 += pow((double)v->count[wi], 0.75) / pow_sum;
+        }
+    }
+}
+
+void ora_init_syn0(int32_t V, int32_t dim, uint64_t seed, float *syn0) {
+    /* (U[0,1) - 0.5) / dim ; element e = row*dim + col is draw e of a Philox stream. */
+    for (int64_t e = 0; e < (int64_t)V * dim; e++) {
+        uint32_t ctr[4] = {(uint32_t)(e >> 2), (uint32_t)((uint64_t)(e >> 2) >> 32), 0x5347u, 0u};
+        uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+        uint32_t r[4];
+        ora_philox4x32_10(ctr, key, r);
+        float u = (float)(r[e & 3] >> 8) * 0x1.0p-24f;
+        syn0[e] = (u - 0.5f) / (float)dim;
+    }
+}
+
+uint64_t ora_sentence_rng(uint64_t seed, int32_t epoch, int64_t sentence) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(sentence + 1) + 0xD1B54A32D192ED03ULL * (uint64_t)epoch;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return z & 0x7FFFFFFFFFFFFFFFULL;
+}
+
+float ora_alpha(const ora_sgns_params *p, int32_t epoch, int64_t sentence, int64_t n_sent) {
+    double progress = (double)((int64_t)epoch * n_sent + sentence) / (double)((int64_t)p->epochs * n_sent);
+    float a = p->lr * (float)(1.0 - progress);
+    return a < p->min_lr ? p->min_lr : a;
+}
+
+static inline uint64_t lcg_abs(uint64_t r) { /* Math.abs(r * 25214903917L + 11) on a Java long */
+    int64_t x = (int64_t)(r * LCG_MUL + LCG_ADD);
+    return (uint64_t)(x < 0 ? -(uint64_t)x : (uint64_t)x);
+}
+
+/* Huffman tree (word2vec.c CreateBinaryTree): codes/points per word, for the optional HS rounds. */
+typedef struct { int32_t *points; int8_t *codes; int32_t *len; int32_t max_len; } huff;
+static void huff_build(const int64_t *count, int32_t V, huff *h) {
+    h->max_len = 40;
+    h->points = (int32_t *)calloc((size_t)V * 40, sizeof(int32_t));
+    h->codes = (int8_t *)calloc((size_t)V * 40, 1);
+    h->len = (int32_t *)calloc((size_t)V, sizeof(int32_t));
+    if (V < 2) return;
+    int64_t *cnt = (int64_t *)malloc(sizeof(int64_t) * (size_t)(2 * V + 1));
+    int8_t *bin = (int8_t *)calloc((size_t)(2 * V + 1), 1);
+    int32_t *parent = (int32_t *)calloc((size_t)(2 * V + 1), sizeof(int32_t));
+    for (int32_t a = 0; a < V; a++) cnt[a] = count[a];
+    for (int32_t a = V; a < 2 * V; a++) cnt[a] = (int64_t)1e15;
+    int32_t pos1 = V - 1, pos2 = V;
+    for (int32_t a = 0; a < V - 1; a++) {
+        int32_t m1, m2;
+        if (pos1 >= 0 && cnt[pos1] < cnt[pos2]) m1 = pos1--; else m1 = pos2++;
+        if (pos1 >= 0 && cnt[pos1] < cnt[pos2]) m2 = pos1--; else m2 = pos2++;
+        cnt[V + a] = cnt[m1] + cnt[m2];
+        parent[m1] = V + a; parent[m2] = V + a;
+        bin[m2] = 1;
+    }
+    for (int32_t a = 0; a < V; a++) {
+        int8_t code[40]; int32_t point[40];
+        int32_t b = a, i = 0;
+        while (1) {
+            code[i] = bin[b]; point[i] = b; i++;
+            b = parent[b];
+            if (b == V * 2 - 2) break;
+        }
+        h->len[a] = i;
+        h->points[(int64_t)a * 40] = V - 2;
+        for (b = 0; b < i; b++) {
+            h->codes[(int64_t)a * 40 + i - b - 1] = code[b];
+            h->points[(int64_t)a * 40 + i - b] = point[b] - V;
+        }
+    }
+    free(cnt); free(bin); free(parent);
+}
+static void huff_free(huff *h) { free(h->points); free(h->codes); free(h->len); }
+
+struct ora_model {
+    int32_t V, dim;
+    float *syn0, *syn1neg, *syn1;
+    int32_t *id_of_word;
+};
+
+typedef struct {
+    const int32_t *tokens; int64_t n_sent; int32_t L;
+    const ora_sgns_params *p;
+    const ora_vocab *vocab;
+    const int32_t *table; const float *exp_table;
+    const huff *hf;
+    ora_model *m;
+    int tid, nthreads;
+    int count_only;
+    int64_t pairs;
+} worker;
+
+static void *worker_run(void *arg) {
+    worker *w = (worker *)arg;
+    const ora_sgns_params *p = w->p;
+    const int32_t D = p->dim, V = w->vocab->V, E = p->exp_table_size, T = p->neg_table_size;
+    const int32_t win = p->window;
+    float *neu1e = (float *)malloc(sizeof(float) * (size_t)(D ? D : 1));
+    int32_t *sent = (int32_t *)malloc(sizeof(int32_t) * (size_t)(w->L ? w->L : 1));
+    float *syn0 = w->m ? w->m->syn0 : NULL, *syn1neg = w->m ? w->m->syn1neg : NULL, *syn1 = w->m ? w->m->syn1 : NULL;
+    const float idx_scale = (float)E / MAX_EXP / 2.0f;
+    int64_t pairs = 0;
+    for (int32_t ep = 0; ep < p->epochs; ep++) {
+        for (int64_t s = w->tid; s < w->n_sent; s += w->nthreads) {
+            int32_t n = 0;
+            for (int32_t j = 0; j < w->L; j++) {
+                int32_t id = w->tokens[s * w->L + j];
+                if (id < 0) continue;
+                int32_t wd = w->vocab->word_of_id[id];
+                if (wd >= 0) sent[n++] = wd;
+            }
+            float alpha = ora_alpha(p, ep, s, w->n_sent);
+            uint64_t r = ora_sentence_rng(p->seed, ep, s);
+            for (int32_t i = 0; i < n; i++) {
+                r = lcg_abs(r);
+                int32_t b = (int32_t)(uint32_t)r % win; /* ((int) nextRandom) % window, may be negative */
+                int32_t w1 = sent[i];
+                int32_t end = win * 2 + 1 - b;
+                for (int32_t a = b; a < end; a++) {
+                    if (a == win) continue;
+                    int32_t c = i - win + a;
+                    if (c < 0 || c >= n) continue;
+                    int32_t last = sent[c];
+                    if (last == w1) continue;
+                    uint64_t ns = r;
+                    r = lcg_abs(r);
+                    pairs++;
+                    if (w->count_only) continue;
+                    float *v0 = syn0 + (int64_t)last * D;
+                    for (int32_t d = 0; d < D; d++) neu1e[d] = 0;
+                    if (p->use_hs) {
+                        for (int32_t q = 0; q < w->hf->len[w1]; q++) {
+                            int32_t pt = w->hf->points[(int64_t)w1 * 40 + q];
+                            int32_t code = w->hf->codes[(int64_t)w1 * 40 + q];
+                            if (pt < 0 || pt >= V) continue;
+                            float *v1 = syn1 + (int64_t)pt * D;
+                            float dot = 0;
+                            for (int32_t d = 0; d < D; d++) dot += v0[d] * v1[d];
+                            if (dot < -MAX_EXP || dot >= MAX_EXP) continue;
+                            int32_t idx = (int32_t)((dot + MAX_EXP) * idx_scale);
+                            if (idx < 0 || idx >= E) continue;
+                            float g = (1.0f - (float)code - w->exp_table[idx]) * alpha;
+                            for (int32_t d = 0; d < D; d++) neu1e[d] += g * v1[d];
+                            for (int32_t d = 0; d < D; d++) v1[d] += g * v0[d];
+                        }
+                    }
+                    for (int32_t k = 0; k < p->negative + 1; k++) {
+                        int32_t target, label;
+                        if (k == 0) { target = w1; label = 1; }
+                        else {
+                            if (V < 2) break;
+                            ns = ns * LCG_MUL + LCG_ADD;
+                            target = w->table[(ns >> 16) % (uint64_t)T];
+                            if (target <= 0 || target >= V) target = (int32_t)(ns % (uint64_t)(V - 1)) + 1;
+                            if (target == w1) continue;
+                            label = 0;
+                        }
+                        float *v1 = syn1neg + (int64_t)target * D;
+                        float dot = 0;
+                        for (int32_t d = 0; d < D; d++) dot += v0[d] * v1[d];
+                        float g;
+                        if (dot > MAX_EXP) g = ((float)label - 1.0f) * alpha;
+                        else if (dot < -MAX_EXP) g = ((float)label - 0.0f) * alpha;
+                        else {
+                            int32_t idx = (int32_t)((dot + MAX_EXP) * idx_scale);
+                            if (idx < 0 || idx >= E) continue;
+                            g = ((float)label - w->exp_table[idx]) * alpha;
+                        }
+                        for (int32_t d = 0; d < D; d++) neu1e[d] += g * v1[d];
+                        for (int32_t d = 0; d < D; d++) v1[d] += g * v0[d];
+                    }
+                    for (int32_t d = 0; d < D; d++) v0[d] += neu1e[d];
+                }
+            }
+        }
+    }
+    w->pairs = pairs;
+    free(neu1e); free(sent);
+    return NULL;
+}
+
+static int64_t run_workers(const int32_t *tokens, int64_t n_sent, int32_t L, const ora_sgns_params *p,
+                           const ora_vocab *vocab, const int32_t *table, const float *exp_table,
+                           const huff *hf, ora_model *m, int count_only) {
+    int nt = p->threads > 0 ? p->threads : 1;
+    if (nt > 256) nt = 256;
+    worker *ws = (worker *)calloc((size_t)nt, sizeof(worker));
+    pthread_t *th = (pthread_t *)calloc((size_t)nt, sizeof(pthread_t));
+    for (int t = 0; t < nt; t++) {
+        ws[t].tokens = tokens; ws[t].n_sent = n_sent; ws[t].L = L; ws[t].p = p; ws[t].vocab = vocab;
+        ws[t].table = table; ws[t].exp_table = exp_table; ws[t].hf = hf; ws[t].m = m;
+        ws[t].tid = t; ws[t].nthreads = nt; ws[t].count_only = count_only;
+    }
+    if (nt == 1) worker_run(&ws[0]);
+    else {
+        for (int t = 0; t < nt; t++) pthread_create(&th[t], NULL, worker_run, &ws[t]);
+        for (int t = 0; t < nt; t++) pthread_join(th[t], NULL);
+    }
+    int64_t pairs = 0;
+    for (int t = 0; t < nt; t++) pairs += ws[t].pairs;
+    free(ws); free(th);
+    return pairs;
+}
+
+ora_model *ora_sgns_train(const int32_t *tokens, int64_t n_sent, int32_t L, int32_t n_ids,
+                          const ora_sgns_params *p, int64_t *pairs_out) {
+    ora_vocab *vocab = ora_vocab_build(tokens, n_sent * L, n_ids, p->min_count);
+    int32_t V = vocab->V, D = p->dim;
+    ora_model *m = (ora_model *)calloc(1, sizeof(*m));
+    m->V = V; m->dim = D;
+    size_t n = (size_t)(V ? V : 1) * (size_t)D;
+    m->syn0 = (float *)malloc(sizeof(float) * n);
+    m->syn1neg = (float *)calloc(n, sizeof(float));
+    m->syn1 = p->use_hs ? (float *)calloc(n, sizeof(float)) : NULL;
+    m->id_of_word = (int32_t *)malloc(sizeof(int32_t) * (size_t)(V ? V : 1));
+    memcpy(m->id_of_word, vocab->id_of_word, sizeof(int32_t) * (size_t)V);
+    ora_init_syn0(V, D, p->seed, m->syn0);
+    int32_t *table = (int32_t *)malloc(sizeof(int32_t) * (size_t)p->neg_table_size);
+    ora_neg_table(vocab, p->neg_table_size, table);
+    float *exp_table = (float *)malloc(sizeof(float) * (size_t)p->exp_table_size);
+    for (int32_t i = 0; i < p->exp_table_size; i++) {
+        double e = exp(((double)i / (double)p->exp_table_size * 2.0 - 1.0) * (double)MAX_EXP);
+        exp_table[i] = (float)(e / (e + 1.0));
+    }
+    huff hf; memset(&hf, 0, sizeof(hf));
+    if (p->use_hs) huff_build(vocab->count, V, &hf);
+    int64_t pairs = run_workers(tokens, n_sent, L, p, vocab, table, exp_table, &hf, m, 0);
+    if (pairs_out) *pairs_out = pairs;
+    if (p->use_hs) huff_free(&hf);
+    free(table); free(exp_table);
+    ora_vocab_free(vocab);
+    return m;
+}
+
+int64_t ora_sgns_count_pairs(const int32_t *tokens, int64_t n_sent, int32_t L, int32_t n_ids,
+                             const ora_sgns_params *p) {
+    ora_vocab *vocab = ora_vocab_build(tokens, n_sent * L, n_ids, p->min_count);
+    int64_t pairs = run_workers(tokens, n_sent, L, p, vocab, NULL, NULL, NULL, NULL, 1);
+    ora_vocab_free(vocab);
+    return pairs;
+}
+
+void ora_model_free(ora_model *m) {
+    if (!m) return;
+    free(m->syn0); free(m->syn1neg); free(m->syn1); free(m->id_of_word); free(m);
+}
+int32_t ora_model_vocab_size(const ora_model *m) { return m->V; }
+void ora_model_get(const ora_model *m, float *syn0, float *syn1neg, int32_t *id_of_word) {
+    size_t n = (size_t)m->V * (size_t)m->dim;
+    if (syn0) memcpy(syn0, m->syn0, sizeof(float) * n);
+    if (syn1neg) memcpy(syn1neg, m->syn1neg, sizeof(float) * n);
+    if (id_of_word) memcpy(id_of_word, m->id_of_word, sizeof(int32_t) * (size_t)m->V);
+}

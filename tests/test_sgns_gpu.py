@@ -1,0 +1,122 @@
+"""GPU parity, stage 2: skip-gram negative sampling.  Parity is UNPINNED against DL4J (sources absent, see
+oracle/sgns_oracle.h); what is checked: (i) identical vocabulary / pair / negative enumeration and fp32-
+tolerance agreement with the CPU oracle in a sequential schedule, (ii) the parallel Hogwild schedule reaches
+the same embedding quality."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+# fp32, ~1e4 dependent updates, GPU uses FMA + tree-reduced dots, the oracle sequential non-fused adds
+SEQ_ATOL = 2e-4
+
+
+def community_corpus(n=3000, L=8, seed=1):
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 10, size=(n, L))
+    b = rng.integers(10, 20, size=(n, L))
+    t = np.concatenate([a, b]).astype(np.int32)
+    rng.shuffle(t)
+    return t
+
+
+@pytest.mark.parametrize("dim", [2, 8, 20, 64, 128])
+def test_sequential_schedule_matches_oracle(dge_lib, oracle, ctx, dim):
+    rng = np.random.default_rng(dim)
+    tok = rng.integers(0, 40, size=(300, 8)).astype(np.int32)
+    tok[rng.random(tok.shape) < 0.08] = -1
+    tok[:, 0] = np.maximum(tok[:, 0], 0)
+    kw = dict(dim=dim, window=5, negative=5, min_count=2, seed=17)
+    ref = oracle.sgns_train(tok, 41, oracle.sgns_params(threads=1, **kw))
+    c = dge_lib.Corpus.from_tokens(ctx, tok, 41)
+    m = dge_lib.Model.train(ctx, [c], dge_lib.sgns_params(concurrency=1, **kw))
+    syn0, syn1, ids = m.vectors(want_syn1neg=True)
+    assert m.V == len(ref["id_of_word"]) and np.array_equal(ids, ref["id_of_word"])
+    assert m.pairs == ref["pairs"]
+    assert np.allclose(syn0, ref["syn0"], rtol=0, atol=SEQ_ATOL)
+    assert np.allclose(syn1, ref["syn1neg"], rtol=0, atol=SEQ_ATOL)
+
+
+def test_init_is_bit_identical_to_oracle(dge_lib, oracle, ctx):
+    """One sentence of one token trains nothing: syn0 is the (U-0.5)/dim initialisation."""
+    tok = np.zeros((5, 1), np.int32)
+    tok[:, 0] = [0, 1, 2, 1, 0]
+    for dim in (2, 20, 128):
+        c = dge_lib.Corpus.from_tokens(ctx, tok, 3)
+        m = dge_lib.Model.train(ctx, [c], dge_lib.sgns_params(dim=dim, min_count=1, seed=5))
+        syn0, ids = m.vectors()
+        assert m.pairs == 0
+        assert np.array_equal(syn0, oracle.init_syn0(3, dim, 5))
+
+
+def test_two_corpora_share_one_vocabulary(dge_lib, oracle, ctx):
+    """usespatial: FileSentenceIterator over both .seq files (DeepWalk.java:48-50)."""
+    rng = np.random.default_rng(4)
+    a = rng.integers(0, 30, size=(200, 8)).astype(np.int32)
+    b = rng.integers(0, 30, size=(100, 5)).astype(np.int32)
+    kw = dict(dim=8, window=8, min_count=1, seed=2)
+    bp = np.full((100, 8), -1, np.int32)
+    bp[:, :5] = b
+    ref = oracle.sgns_train(np.concatenate([a, bp]), 30, oracle.sgns_params(**kw))
+    ca, cb = dge_lib.Corpus.from_tokens(ctx, a, 30), dge_lib.Corpus.from_tokens(ctx, b, 30)
+    m = dge_lib.Model.train(ctx, [ca, cb], dge_lib.sgns_params(concurrency=1, **kw))
+    syn0, ids = m.vectors()
+    assert m.pairs == ref["pairs"] and np.array_equal(ids, ref["id_of_word"])
+    assert np.allclose(syn0, ref["syn0"], rtol=0, atol=SEQ_ATOL)
+
+
+@pytest.mark.parametrize("dim", [8, 20, 128])
+def test_parallel_schedule_learns_the_same_structure(dge_lib, oracle, ctx, dim):
+    tok = community_corpus()
+    kw = dict(dim=dim, window=5, min_count=1, seed=3)
+    ref = oracle.sgns_train(tok, 20, oracle.sgns_params(threads=8, **kw))
+    c = dge_lib.Corpus.from_tokens(ctx, tok, 20)
+    m = dge_lib.Model.train(ctx, [c], dge_lib.sgns_params(**kw))
+    assert m.pairs == ref["pairs"]  # the enumeration does not depend on the schedule
+    syn0, ids = m.vectors()
+    assert np.isfinite(syn0).all()
+
+    def gap(emb, ids):
+        e = np.zeros((20, emb.shape[1]), np.float32)
+        e[ids] = emb
+        e /= np.linalg.norm(e, axis=1, keepdims=True)
+        s = e @ e.T
+        within = ((s[:10, :10].sum() - 10) + (s[10:, 10:].sum() - 10)) / 180
+        return within - s[:10, 10:].mean()
+
+    g_ref, g_gpu = gap(ref["syn0"], ref["id_of_word"]), gap(syn0, ids)
+    assert g_ref > 0.5
+    assert g_gpu > 0.5 * g_ref, (g_gpu, g_ref)
+
+
+def test_vec_file_format(dge_lib, ctx, tmp_path):
+    """WordVectorSerializer.writeWordVectors as its consumers read it (embeddingEvaluation_tract.py:139-166,
+    skipheader=0): "<layer>-<region> v1 ... vD", one line per vocabulary word."""
+    tok = community_corpus(200)
+    c = dge_lib.Corpus.from_tokens(ctx, tok, 20)
+    m = dge_lib.Model.train(ctx, [c], dge_lib.sgns_params(dim=8, window=5, min_count=1))
+    layer = (np.arange(20) % 4).astype(np.int32)
+    region = (17000 + np.arange(20)).astype(np.int32)
+    p = tmp_path / "taxi-deepwalk-tract-usespatial.vec"
+    m.write_vec(str(p), layer, region)
+    syn0, ids = m.vectors()
+    lines = p.read_text().strip().split("\n")
+    assert len(lines) == m.V
+    for wd, line in enumerate(lines):
+        parts = line.split(" ")
+        k1, k2 = parts[0].split("-")
+        assert int(k1) == layer[ids[wd]] and int(k2) == region[ids[wd]]
+        assert np.array_equal(np.array(parts[1:], np.float32), syn0[wd])
+
+
+def test_sgns_error_behaviour(dge_lib, ctx):
+    c = dge_lib.Corpus.from_tokens(ctx, np.zeros((2, 2), np.int32), 1)
+    with pytest.raises(dge_lib.DgeError):
+        dge_lib.Model.train(ctx, [c], dge_lib.sgns_params(dim=0))
+    with pytest.raises(dge_lib.DgeError):
+        dge_lib.Model.train(ctx, [c], dge_lib.sgns_params(window=0))
+    with pytest.raises(dge_lib.DgeError):
+        dge_lib.Model.train(ctx, [c], dge_lib.sgns_params(dim=1024))
+    # everything below min_count: empty vocabulary, not an error
+    m = dge_lib.Model.train(ctx, [c], dge_lib.sgns_params(min_count=100))
+    assert m.V == 0 and m.pairs == 0

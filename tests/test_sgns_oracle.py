@@ -1,0 +1,79 @@
+"""CPU tests of the stage-2 oracle (oracle/sgns_oracle.c; parity UNPINNED -- see its header): internal
+consistency of the restated word2vec / DL4J-parameterised skip-gram."""
+import numpy as np
+
+
+def _corpus(n=400, L=8, ids=60, seed=0):
+    rng = np.random.default_rng(seed)
+    t = rng.integers(0, ids, size=(n, L)).astype(np.int32)
+    t[rng.random((n, L)) < 0.05] = -1
+    return t
+
+
+def test_vocab_order_and_min_count(oracle):
+    t = np.array([[0, 1, 1, 2], [2, 2, 3, -1], [4, 4, 4, 4]], np.int32)
+    h, v = oracle.vocab(t, 6, 2)
+    # counts: 0:1 1:2 2:3 3:1 4:4 5:0 -> keep 4(4), 2(3), 1(2)
+    assert v["V"] == 3 and v["id_of_word"].tolist() == [4, 2, 1] and v["count"].tolist() == [4, 3, 2]
+    assert v["word_of_id"].tolist() == [-1, 2, 1, -1, 0, -1] and v["total"] == 9
+    tab = oracle.neg_table(h, 1000)
+    assert tab.min() == 0 and tab.max() == 2 and np.all(np.diff(tab) >= 0)
+    frac = np.bincount(tab, minlength=3) / 1000.0
+    want = np.array([4, 3, 2]) ** 0.75
+    assert np.allclose(frac, want / want.sum(), atol=5e-3)
+    oracle.lib().ora_vocab_free(h)
+
+
+def test_pair_enumeration_bounds(oracle):
+    """Every position draws b in (-w, w); contexts are c in [i-w+b, i+w-b] minus i, clipped: for a full
+    sentence of n distinct tokens the pair count lies in [n*(n-1) * small, n*(n-1)]."""
+    n, L = 2000, 8
+    t = np.tile(np.arange(L, dtype=np.int32), (n, 1))
+    p = oracle.sgns_params(dim=4, window=8, min_count=1)
+    pairs = oracle.sgns_count_pairs(t, L, p)
+    assert 0.7 * n * L * (L - 1) < pairs <= n * L * (L - 1)
+    p1 = oracle.sgns_params(dim=4, window=1, min_count=1)  # b = 0 always: exactly two neighbours
+    assert oracle.sgns_count_pairs(t, L, p1) == n * (2 * L - 2)
+    # threads do not change the enumeration
+    p8 = oracle.sgns_params(dim=4, window=8, min_count=1, threads=8)
+    assert oracle.sgns_count_pairs(t, L, p8) == pairs
+
+
+def test_training_is_deterministic_single_thread_and_learns(oracle):
+    # two interleaved "communities": tokens 0..9 co-occur, tokens 10..19 co-occur
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 10, size=(3000, 8))
+    b = rng.integers(10, 20, size=(3000, 8))
+    t = np.concatenate([a, b]).astype(np.int32)
+    rng.shuffle(t)
+    p = oracle.sgns_params(dim=8, window=5, min_count=1, seed=3)
+    m1 = oracle.sgns_train(t, 20, p)
+    m2 = oracle.sgns_train(t, 20, p)
+    assert np.array_equal(m1["syn0"], m2["syn0"]) and m1["pairs"] == m2["pairs"] > 0
+    emb = np.zeros((20, 8), np.float32)
+    emb[m1["id_of_word"]] = m1["syn0"]
+    emb /= np.linalg.norm(emb, axis=1, keepdims=True)
+    sim = emb @ emb.T
+    within = (sim[:10, :10].sum() - 10) / 90 + (sim[10:, 10:].sum() - 10) / 90
+    across = sim[:10, 10:].mean() * 2
+    assert within > across + 0.5
+    # Hogwild run (8 threads) lands in the same place statistically
+    p.threads = 8
+    m3 = oracle.sgns_train(t, 20, p)
+    assert m3["pairs"] == m1["pairs"]
+
+
+def test_hs_switch_runs(oracle):
+    t = _corpus()
+    p = oracle.sgns_params(dim=8, window=4, min_count=1, use_hs=1)
+    m = oracle.sgns_train(t, 60, p)
+    assert np.isfinite(m["syn0"]).all() and m["pairs"] > 0
+
+
+def test_alpha_schedule(oracle):
+    import ctypes as C
+    p = oracle.sgns_params(lr=0.025, min_lr=1e-4, epochs=1)
+    f = oracle.lib().ora_alpha
+    assert abs(f(C.byref(p), 0, 0, 1000) - 0.025) < 1e-9
+    assert abs(f(C.byref(p), 0, 500, 1000) - 0.0125) < 1e-9
+    assert abs(f(C.byref(p), 0, 999, 1000) - 1e-4) < 1e-9  # floor
