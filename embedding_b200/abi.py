@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdge.so")
 
 SAMPLER_ALIAS, SAMPLER_CDF = 0, 1
+SCHEDULE_ITEMS, SCHEDULE_SENTENCE = 0, 1
 
 class DgeError(RuntimeError):
     def __init__(self, code, msg):
@@ -22,7 +23,7 @@ class DgeError(RuntimeError):
 class SgnsParams(C.Structure):
     _fields_ = [("dim", C.c_int32), ("window", C.c_int32), ("negative", C.c_int32), ("min_count", C.c_int32),
                 ("epochs", C.c_int32), ("neg_table_size", C.c_int32), ("exp_table_size", C.c_int32),
-                ("concurrency", C.c_int32), ("lr", C.c_float), ("min_lr", C.c_float), ("seed", C.c_uint64)]
+                ("concurrency", C.c_int32), ("schedule", C.c_int32), ("lr", C.c_float), ("min_lr", C.c_float), ("seed", C.c_uint64)]
 
 
 _lib = None

@@ -64,7 +64,8 @@ struct dge_corpus {
 struct dge_model {
     dge_ctx *ctx = nullptr;
     int32_t V = 0, dim = 0, stride = 0; // stride = dim rounded up to 4 floats (zero padded)
-    int64_t pairs = 0;
+    int64_t pairs = 0;   // (centre, context) updates executed
+    int64_t words = 0;   // in-vocabulary tokens of the corpus
     float *syn0 = nullptr, *syn1neg = nullptr; // device [V*stride]
     int32_t *id_of_word = nullptr;             // device [V]
 };

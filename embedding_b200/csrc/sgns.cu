@@ -21,18 +21,9 @@
 #define LCG_MUL 25214903917ULL
 #define LCG_ADD 11ULL
 
-struct sgns_corpus_view {
-    const int32_t *tok; // position-major [L][n]
-    int64_t n;
-    int64_t first;      // global index of its first sentence
-    int32_t L;
-};
-
 struct sgns_args {
-    sgns_corpus_view cv[SGNS_MAX_CORPORA];
-    int32_t n_corpora;
+    const int32_t *wtok;      // compacted corpus, vocabulary indices, position-major [Lmax][n_sent], -1 padded
     int64_t n_sent;
-    const int32_t *word_of_id;
     const int32_t *neg_table;
     const float *exp_table;
     float *syn0, *syn1neg;
@@ -43,16 +34,26 @@ struct sgns_args {
     int64_t n_groups;
 };
 
-__host__ __device__ static inline uint64_t sgns_sentence_rng(uint64_t seed, int32_t epoch, int64_t sentence) {
-    uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(sentence + 1) + 0xD1B54A32D192ED03ULL * (uint64_t)epoch;
+__host__ __device__ static inline uint64_t mix64(uint64_t z) {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    z = z ^ (z >> 31);
-    return z & 0x7FFFFFFFFFFFFFFFULL;
+    return z ^ (z >> 31);
 }
-__device__ static inline uint64_t lcg_abs(uint64_t r) { // Math.abs(r * 25214903917L + 11) on a Java long
-    int64_t x = (int64_t)(r * LCG_MUL + LCG_ADD);
-    return (uint64_t)(x < 0 ? -x : x);
+// Same draw definitions as oracle/sgns_oracle.c: pure functions of (seed, epoch, sentence, position[, context]).
+__host__ __device__ static inline uint64_t sgns_sentence_rng(uint64_t seed, int32_t epoch, int64_t sentence) {
+    return mix64(seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(sentence + 1) + 0xD1B54A32D192ED03ULL * (uint64_t)epoch) &
+           0x7FFFFFFFFFFFFFFFULL;
+}
+__host__ __device__ static inline uint64_t sgns_position_rng(uint64_t S, int32_t i) {
+    return mix64(S + 0x9E3779B97F4A7C15ULL * (uint64_t)(i + 1)) & 0x7FFFFFFFFFFFFFFFULL;
+}
+__host__ __device__ static inline uint64_t sgns_pair_rng(uint64_t S, int32_t i, int32_t c) {
+    return mix64(S ^ (0xD6E8FEB86659FD93ULL * (uint64_t)((int64_t)i * 65536 + c + 1)));
+}
+__device__ __forceinline__ float sgns_alpha(const sgns_args &a, int ep, int64_t s) {
+    double progress = (double)((int64_t)ep * a.n_sent + s) / (double)((int64_t)a.epochs * a.n_sent);
+    float alpha = a.lr * (float)(1.0 - progress);
+    return alpha < a.min_lr ? a.min_lr : alpha;
 }
 
 __global__ void k_hist(const int32_t *__restrict__ tok, int64_t total, unsigned int *__restrict__ cnt) {
@@ -62,6 +63,27 @@ __global__ void k_hist(const int32_t *__restrict__ tok, int64_t total, unsigned 
         int32_t t = tok[i];
         if (t >= 0) atomicAdd(&cnt[t], 1u);
     }
+}
+
+// corpus ids -> vocabulary indices, dropping padding and out-of-vocabulary tokens (DL4J removes words below
+// minWordFrequency from the sentence before windowing); thread per sentence, position-major on both sides.
+__global__ void k_compact(const int32_t *__restrict__ tok, int64_t n, int32_t L, const int32_t *__restrict__ word_of_id,
+                          int32_t *__restrict__ wtok, int64_t n_total, int64_t first, int32_t Lmax,
+                          unsigned long long *words) {
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    unsigned long long c = 0;
+    if (s < n) {
+        int cnt = 0;
+        for (int j = 0; j < L; j++) {
+            int32_t id = tok[(int64_t)j * n + s];
+            int32_t wd = id >= 0 ? word_of_id[id] : -1;
+            if (wd >= 0) { wtok[(int64_t)cnt * n_total + first + s] = wd; cnt++; }
+        }
+        c = cnt;
+        for (; cnt < Lmax; cnt++) wtok[(int64_t)cnt * n_total + first + s] = -1;
+    }
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(words, c);
 }
 
 // syn0 = (U[0,1) - 0.5) / dim from Philox(seed); same element stream as ora_init_syn0
@@ -84,63 +106,71 @@ __device__ __forceinline__ float group_sum(float v, unsigned gmask) {
     for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
     return v;
 }
+__device__ __forceinline__ float dot4(const float4 &a, const float4 &b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ void axpy4(float4 &y, float g, const float4 &x) { y.x += g * x.x; y.y += g * x.y; y.z += g * x.z; y.w += g * x.w; }
+__device__ __forceinline__ float4 scale4(float g, const float4 &x) { return make_float4(g * x.x, g * x.y, g * x.z, g * x.w); }
+// 128-bit reduction at L2: no lost update, no return value
+__device__ __forceinline__ void red_add4(float4 *p, const float4 &v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// gradient scale of one (input, target) dot product: libnd4j NegativeSampling aggregate with the expTable sigmoid
+__device__ __forceinline__ bool sgns_g(float dot, float label, float alpha, const float *s_exp, int E, float idx_scale, float &g) {
+    if (dot > SGNS_MAX_EXP) g = (label - 1.f) * alpha;
+    else if (dot < -SGNS_MAX_EXP) g = (label - 0.f) * alpha;
+    else {
+        int idx = (int)((dot + SGNS_MAX_EXP) * idx_scale);
+        if (idx < 0 || idx >= E) return false;
+        g = (label - s_exp[idx]) * alpha;
+    }
+    return true;
+}
+__device__ __forceinline__ int32_t sgns_negative(uint64_t &ns, const sgns_args &a) {
+    ns = ns * LCG_MUL + LCG_ADD;
+    int32_t t = a.neg_table[(ns >> 16) % (uint64_t)a.neg_table_size];
+    if (t <= 0 || t >= a.V) t = (int32_t)(ns % (uint64_t)(a.V - 1)) + 1;
+    return t;
+}
 
+// ---------------------------------------------------------------------------------------------------------
+// Kernel A: sentence per group, pairs and targets strictly in the oracle's order, plain (atomic-free) row
+// stores.  With concurrency 1 it reproduces oracle/sgns_oracle.c to fp32 tolerance; with many groups it is
+// the classic Hogwild schedule (use it when the vocabulary is much larger than the sentences in flight).
 template <int G, int VPL>
 __global__ void __launch_bounds__(128)
-k_sgns(const sgns_args a) {
+k_sgns_seq(const sgns_args a) {
     extern __shared__ int32_t smem[];
     float *s_exp = reinterpret_cast<float *>(smem);
-    int32_t *s_sent = smem + a.exp_table_size;
     const int gpb = blockDim.x / G;
     const int gl = threadIdx.x / G;
     const int lane = threadIdx.x % G;
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
     for (int i = threadIdx.x; i < a.exp_table_size; i += blockDim.x) s_exp[i] = a.exp_table[i];
     __syncthreads();
-
     const int64_t gid = (int64_t)blockIdx.x * gpb + gl;
     const int n4 = a.stride >> 2;
     const int E = a.exp_table_size;
     const float idx_scale = (float)E / SGNS_MAX_EXP / 2.0f;
     const int win = a.window;
+    const int64_t N = a.n_sent;
     unsigned long long pairs = 0;
-    // float4 slots of this lane: q = lane + v*G, active when q < n4
     for (int ep = 0; ep < a.epochs; ep++) {
-        for (int64_t s = gid; s < a.n_sent; s += a.n_groups) {
-            // ---- locate the sentence and compact it to vocabulary indices
-            int ci = 0;
-            while (ci + 1 < a.n_corpora && s >= a.cv[ci + 1].first) ci++;
-            const sgns_corpus_view cv = a.cv[ci];
-            const int64_t sl = s - cv.first;
+        for (int64_t s = gid; s < N; s += a.n_groups) {
             int n = 0;
-            for (int j = 0; j < cv.L; j++) {
-                int32_t id = cv.tok[(int64_t)j * cv.n + sl];
-                if (id < 0) continue;
-                int32_t wd = a.word_of_id[id];
-                if (wd < 0) continue;
-                if (lane == 0) s_sent[n * gpb + gl] = wd;
-                n++;
-            }
-            if (G > 1) __syncwarp(gmask);
-            double progress = (double)((int64_t)ep * a.n_sent + s) / (double)((int64_t)a.epochs * a.n_sent);
-            float alpha = a.lr * (float)(1.0 - progress);
-            if (alpha < a.min_lr) alpha = a.min_lr;
-            uint64_t r = sgns_sentence_rng(a.seed, ep, s);
+            while (n < a.Lmax && a.wtok[(int64_t)n * N + s] >= 0) n++;
+            const float alpha = sgns_alpha(a, ep, s);
+            const uint64_t S = sgns_sentence_rng(a.seed, ep, s);
             for (int i = 0; i < n; i++) {
-                r = lcg_abs(r);
-                const int b = (int32_t)(uint32_t)r % win;
-                const int32_t w1 = s_sent[i * gpb + gl];
+                const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
+                const int32_t w1 = a.wtok[(int64_t)i * N + s];
                 const int end = win * 2 + 1 - b;
                 for (int aa = b; aa < end; aa++) {
                     if (aa == win) continue;
                     const int c = i - win + aa;
                     if (c < 0 || c >= n) continue;
-                    const int32_t last = s_sent[c * gpb + gl];
+                    const int32_t last = a.wtok[(int64_t)c * N + s];
                     if (last == w1) continue;
-                    uint64_t ns = r;
-                    r = lcg_abs(r);
+                    uint64_t ns = sgns_pair_rng(S, i, c);
                     pairs++;
-                    // ---- one (centre w1, context last) update
                     float4 v0[VPL], neu[VPL];
                     float4 *p0 = reinterpret_cast<float4 *>(a.syn0 + (int64_t)last * a.stride);
 #pragma unroll
@@ -155,9 +185,7 @@ k_sgns(const sgns_args a) {
                         if (k == 0) { target = w1; label = 1.f; }
                         else {
                             if (a.V < 2) break;
-                            ns = ns * LCG_MUL + LCG_ADD;
-                            target = a.neg_table[(ns >> 16) % (uint64_t)a.neg_table_size];
-                            if (target <= 0 || target >= a.V) target = (int32_t)(ns % (uint64_t)(a.V - 1)) + 1;
+                            target = sgns_negative(ns, a);
                             if (target == w1) continue;
                             label = 0.f;
                         }
@@ -168,22 +196,16 @@ k_sgns(const sgns_args a) {
                         for (int v = 0; v < VPL; v++) {
                             int q = lane + v * G;
                             v1[v] = q < n4 ? __ldcg(p1 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            dot += v0[v].x * v1[v].x + v0[v].y * v1[v].y + v0[v].z * v1[v].z + v0[v].w * v1[v].w;
+                            dot += dot4(v0[v], v1[v]);
                         }
                         dot = group_sum<G>(dot, gmask);
                         float g;
-                        if (dot > SGNS_MAX_EXP) g = (label - 1.f) * alpha;
-                        else if (dot < -SGNS_MAX_EXP) g = (label - 0.f) * alpha;
-                        else {
-                            int idx = (int)((dot + SGNS_MAX_EXP) * idx_scale);
-                            if (idx < 0 || idx >= E) continue;
-                            g = (label - s_exp[idx]) * alpha;
-                        }
+                        if (!sgns_g(dot, label, alpha, s_exp, E, idx_scale, g)) continue;
 #pragma unroll
                         for (int v = 0; v < VPL; v++) {
                             int q = lane + v * G;
-                            neu[v].x += g * v1[v].x; neu[v].y += g * v1[v].y; neu[v].z += g * v1[v].z; neu[v].w += g * v1[v].w;
-                            v1[v].x += g * v0[v].x; v1[v].y += g * v0[v].y; v1[v].z += g * v0[v].z; v1[v].w += g * v0[v].w;
+                            axpy4(neu[v], g, v1[v]);
+                            axpy4(v1[v], g, v0[v]);
                             if (q < n4) __stcg(p1 + q, v1[v]);
                         }
                     }
@@ -195,28 +217,158 @@ k_sgns(const sgns_args a) {
                     }
                 }
             }
-            if (G > 1) __syncwarp(gmask); // s_sent is reused by the next sentence
         }
     }
     if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
 }
 
-typedef void (*sgns_kernel_t)(const sgns_args);
-struct sgns_variant { int G, VPL; sgns_kernel_t fn; };
+// ---------------------------------------------------------------------------------------------------------
+// Kernel B: the throughput kernel.  Work item = (sentence, centre position); a group of G lanes owns one
+// item and walks its contexts in order.  The centre's output row syn1neg[w1] stays in registers for the
+// whole item (read once, its delta reduced once); per pair the K negative rows are fetched up front (memory-
+// level parallelism: K+1 independent 128-bit loads per lane), and every update is a 128-bit L2 reduction
+// (red.global.add.v4.f32): updates are never lost, they are only applied to slightly stale rows -- the
+// Hogwild contract without its failure mode on small vocabularies (DESIGN.md "SGNS schedule").
+// Items are taken in corpus order by a grid-stride loop, so n_groups bounds the sentences in flight.
+#define SGNS_NEG_CHUNK 5
+template <int G, int VPL>
+__global__ void __launch_bounds__(128)
+k_sgns_items(const sgns_args a) {
+    extern __shared__ int32_t smem[];
+    float *s_exp = reinterpret_cast<float *>(smem);
+    const int gpb = blockDim.x / G;
+    const int gl = threadIdx.x / G;
+    const int lane = threadIdx.x % G;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+    for (int i = threadIdx.x; i < a.exp_table_size; i += blockDim.x) s_exp[i] = a.exp_table[i];
+    __syncthreads();
+    const int64_t gid = (int64_t)blockIdx.x * gpb + gl;
+    const int n4 = a.stride >> 2;
+    const int E = a.exp_table_size;
+    const float idx_scale = (float)E / SGNS_MAX_EXP / 2.0f;
+    const int win = a.window;
+    const int64_t N = a.n_sent;
+    const int64_t n_items = N * a.Lmax;
+    const bool act = lane < n4 || VPL > 1;
+    unsigned long long pairs = 0;
+    for (int ep = 0; ep < a.epochs; ep++) {
+        for (int64_t item = gid; item < n_items; item += a.n_groups) {
+            const int64_t s = item / a.Lmax;
+            const int i = (int)(item - s * a.Lmax);
+            const int32_t w1 = a.wtok[(int64_t)i * N + s];
+            if (w1 < 0) continue;
+            const float alpha = sgns_alpha(a, ep, s);
+            const uint64_t S = sgns_sentence_rng(a.seed, ep, s);
+            const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
+            int lo = i - win + b, hi = i + win - b; // inclusive context range
+            if (lo < 0) lo = 0;
+            if (hi > a.Lmax - 1) hi = a.Lmax - 1;
+            float4 *pw = reinterpret_cast<float4 *>(a.syn1neg + (int64_t)w1 * a.stride);
+            float4 t1[VPL], d1[VPL];
+#pragma unroll
+            for (int v = 0; v < VPL; v++) {
+                int q = lane + v * G;
+                t1[v] = q < n4 ? __ldcg(pw + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                d1[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            for (int c = lo; c <= hi; c++) {
+                if (c == i) continue;
+                const int32_t last = a.wtok[(int64_t)c * N + s];
+                if (last < 0) break; // padding is a suffix
+                if (last == w1) continue;
+                uint64_t ns = sgns_pair_rng(S, i, c);
+                pairs++;
+                float4 *p0 = reinterpret_cast<float4 *>(a.syn0 + (int64_t)last * a.stride);
+                float4 v0[VPL], neu[VPL];
+#pragma unroll
+                for (int v = 0; v < VPL; v++) {
+                    int q = lane + v * G;
+                    v0[v] = q < n4 ? __ldcg(p0 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    neu[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                // positive target: the item's private, always-current copy of syn1neg[w1]
+                {
+                    float dot = 0.f;
+                    float4 cur[VPL];
+#pragma unroll
+                    for (int v = 0; v < VPL; v++) {
+                        cur[v] = make_float4(t1[v].x + d1[v].x, t1[v].y + d1[v].y, t1[v].z + d1[v].z, t1[v].w + d1[v].w);
+                        dot += dot4(v0[v], cur[v]);
+                    }
+                    dot = group_sum<G>(dot, gmask);
+                    float g;
+                    if (sgns_g(dot, 1.f, alpha, s_exp, E, idx_scale, g)) {
+#pragma unroll
+                        for (int v = 0; v < VPL; v++) { axpy4(neu[v], g, cur[v]); axpy4(d1[v], g, v0[v]); }
+                    }
+                }
+                if (a.V >= 2) {
+                    for (int k0 = 0; k0 < a.negative; k0 += SGNS_NEG_CHUNK) {
+                        int32_t tg[SGNS_NEG_CHUNK];
+                        float4 vk[SGNS_NEG_CHUNK][VPL];
+#pragma unroll
+                        for (int k = 0; k < SGNS_NEG_CHUNK; k++) {
+                            tg[k] = -1;
+                            if (k0 + k < a.negative) {
+                                int32_t t = sgns_negative(ns, a);
+                                if (t != w1) tg[k] = t;
+                            }
+                            const float4 *pk = reinterpret_cast<const float4 *>(a.syn1neg + (int64_t)(tg[k] < 0 ? 0 : tg[k]) * a.stride);
+#pragma unroll
+                            for (int v = 0; v < VPL; v++) {
+                                int q = lane + v * G;
+                                vk[k][v] = (tg[k] >= 0 && q < n4) ? __ldcg(pk + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < SGNS_NEG_CHUNK; k++) {
+                            if (tg[k] < 0) continue; // group-uniform
+                            float dot = 0.f;
+#pragma unroll
+                            for (int v = 0; v < VPL; v++) dot += dot4(v0[v], vk[k][v]);
+                            dot = group_sum<G>(dot, gmask);
+                            float g;
+                            if (!sgns_g(dot, 0.f, alpha, s_exp, E, idx_scale, g)) continue;
+                            float4 *pk = reinterpret_cast<float4 *>(a.syn1neg + (int64_t)tg[k] * a.stride);
+#pragma unroll
+                            for (int v = 0; v < VPL; v++) {
+                                int q = lane + v * G;
+                                axpy4(neu[v], g, vk[k][v]);
+                                if (q < n4) red_add4(pk + q, scale4(g, v0[v]));
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < VPL; v++) {
+                    int q = lane + v * G;
+                    if (q < n4) red_add4(p0 + q, neu[v]);
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < VPL; v++) {
+                int q = lane + v * G;
+                if (q < n4) red_add4(pw + q, d1[v]);
+            }
+        }
+    }
+    (void)act;
+    if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
+}
 
+typedef void (*sgns_kernel_t)(const sgns_args);
+struct sgns_variant { int G, VPL; sgns_kernel_t seq, items; };
+
+// lanes per group: the smallest power of two covering the row's float4 slots (one 128-bit slot per lane);
+// rows wider than 32 slots give each lane 2 or 4 slots.
 static bool pick_variant(int n4, sgns_variant *out) {
-    static const sgns_variant table[] = {
-        {1, 1, k_sgns<1, 1>}, {1, 2, k_sgns<1, 2>}, {1, 3, k_sgns<1, 3>}, {1, 4, k_sgns<1, 4>},
-        {1, 5, k_sgns<1, 5>}, {1, 6, k_sgns<1, 6>}, {1, 7, k_sgns<1, 7>}, {1, 8, k_sgns<1, 8>},
-        {16, 1, k_sgns<16, 1>}, {32, 1, k_sgns<32, 1>}, {32, 2, k_sgns<32, 2>}, {32, 4, k_sgns<32, 4>},
-    };
-    int G, VPL;
-    if (n4 <= 8) { G = 1; VPL = n4; }
-    else if (n4 <= 16) { G = 16; VPL = 1; }
-    else if (n4 <= 32) { G = 32; VPL = 1; }
-    else if (n4 <= 64) { G = 32; VPL = 2; }
-    else if (n4 <= 128) { G = 32; VPL = 4; }
-    else return false;
+#define V_(g, v) {g, v, k_sgns_seq<g, v>, k_sgns_items<g, v>}
+    static const sgns_variant table[] = {V_(1, 1), V_(2, 1), V_(4, 1), V_(8, 1), V_(16, 1), V_(32, 1), V_(32, 2), V_(32, 4)};
+#undef V_
+    int G = 1, VPL = 1;
+    while (G < 32 && G < n4) G <<= 1;
+    if (n4 > 32) VPL = n4 <= 64 ? 2 : 4;
+    if (n4 > 128) return false;
     for (const auto &t : table)
         if (t.G == G && t.VPL == VPL) { *out = t; return true; }
     return false;
@@ -233,7 +385,7 @@ extern "C" {
 void dge_sgns_default_params(dge_sgns_params *p) {
     if (!p) return;
     p->dim = 20; p->window = 8; p->negative = 5; p->min_count = 2; p->epochs = 1;
-    p->neg_table_size = 100000; p->exp_table_size = 1000; p->concurrency = 0;
+    p->neg_table_size = 100000; p->exp_table_size = 1000; p->concurrency = 0; p->schedule = DGE_SCHEDULE_ITEMS;
     p->lr = 0.025f; p->min_lr = 1e-4f; p->seed = 1;
 }
 
@@ -245,7 +397,8 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
     if (!corpora || !p || n_corpora < 1 || n_corpora > SGNS_MAX_CORPORA)
         return dge_fail(ctx, DGE_E_INVALID, "dge_sgns_train: need 1..4 corpora and params");
     if (p->dim < 1 || p->window < 1 || p->negative < 0 || p->epochs < 1 || p->neg_table_size < 1 ||
-        p->exp_table_size < 2 || p->min_count < 0 || p->concurrency < 0)
+        p->exp_table_size < 2 || p->min_count < 0 || p->concurrency < 0 ||
+        (p->schedule != DGE_SCHEDULE_ITEMS && p->schedule != DGE_SCHEDULE_SENTENCE))
         return dge_fail(ctx, DGE_E_INVALID, "dge_sgns_train: invalid hyper-parameter");
     int32_t n_ids = corpora[0] ? corpora[0]->n_ids : 0;
     int32_t Lmax = 0;
@@ -328,11 +481,11 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
     if (dge_malloc(&m->syn0, nel) != cudaSuccess || dge_malloc(&m->syn1neg, nel) != cudaSuccess ||
         dge_malloc(&m->id_of_word, (size_t)V) != cudaSuccess || dge_malloc(&d_word_of_id, (size_t)n_ids) != cudaSuccess ||
         dge_malloc(&d_table, (size_t)p->neg_table_size) != cudaSuccess ||
-        dge_malloc(&d_exp, (size_t)p->exp_table_size) != cudaSuccess || dge_malloc(&d_pairs, 1) != cudaSuccess)
+        dge_malloc(&d_exp, (size_t)p->exp_table_size) != cudaSuccess || dge_malloc(&d_pairs, 2) != cudaSuccess)
         return fail("dge_sgns_train: cudaMalloc failed");
     cudaMemsetAsync(m->syn0, 0, nel * sizeof(float), st);
     cudaMemsetAsync(m->syn1neg, 0, nel * sizeof(float), st);
-    cudaMemsetAsync(d_pairs, 0, sizeof(unsigned long long), st);
+    cudaMemsetAsync(d_pairs, 0, 2 * sizeof(unsigned long long), st);
     if (V) cudaMemcpyAsync(m->id_of_word, order.data(), sizeof(int32_t) * (size_t)V, cudaMemcpyHostToDevice, st);
     if (n_ids) cudaMemcpyAsync(d_word_of_id, word_of_id.data(), sizeof(int32_t) * (size_t)n_ids, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_table, table.data(), sizeof(int32_t) * table.size(), cudaMemcpyHostToDevice, st);
@@ -343,54 +496,70 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         ctx->launches++;
     }
 
+    int32_t *d_wtok = nullptr;
     if (V > 0 && n_sent > 0) {
-        sgns_args a;
-        memset(&a, 0, sizeof(a));
+        // ---- compacted corpus in vocabulary indices (position-major, all corpora concatenated)
+        dge_phase_timer t_prep(ctx, "compact");
+        if (dge_malloc(&d_wtok, (size_t)n_sent * (size_t)Lmax) != cudaSuccess) return fail("dge_sgns_train: cudaMalloc corpus failed");
         int64_t first = 0;
         for (int i = 0; i < n_corpora; i++) {
-            a.cv[i].tok = corpora[i]->tok; a.cv[i].n = corpora[i]->n; a.cv[i].L = corpora[i]->L; a.cv[i].first = first;
+            if (corpora[i]->n > 0) {
+                k_compact<<<(unsigned)((corpora[i]->n + 255) / 256), 256, 0, st>>>(corpora[i]->tok, corpora[i]->n, corpora[i]->L,
+                                                                                 d_word_of_id, d_wtok, n_sent, first, Lmax, d_pairs + 1);
+                ctx->launches++;
+            }
             first += corpora[i]->n;
         }
-        a.n_corpora = n_corpora; a.n_sent = n_sent;
-        a.word_of_id = d_word_of_id; a.neg_table = d_table; a.exp_table = d_exp;
+        t_prep.stop();
+
+        sgns_args a;
+        memset(&a, 0, sizeof(a));
+        a.wtok = d_wtok; a.n_sent = n_sent;
+        a.neg_table = d_table; a.exp_table = d_exp;
         a.syn0 = m->syn0; a.syn1neg = m->syn1neg;
         a.V = V; a.dim = p->dim; a.stride = stride; a.window = p->window; a.negative = p->negative; a.epochs = p->epochs;
         a.neg_table_size = p->neg_table_size; a.exp_table_size = p->exp_table_size; a.Lmax = Lmax;
         a.lr = p->lr; a.min_lr = p->min_lr; a.seed = p->seed; a.pairs = d_pairs;
 
+        // ---- schedule
+        //  concurrency 1            : kernel A, one group: the oracle's sequential order (parity tests)
+        //  schedule SENTENCE        : kernel A, Hogwild with plain stores, `concurrency` sentences in flight (0 = fill)
+        //  schedule ITEMS (default) : kernel B, (sentence, centre) items with L2 reductions; in flight:
+        //                             concurrency * Lmax items, or (auto) min(full GPU, 32 * V / (negative + 1)) so
+        //                             that a row sees at most ~32 concurrent stale updates
+        const bool sequential = p->concurrency == 1 || p->schedule == DGE_SCHEDULE_SENTENCE;
+        sgns_kernel_t fn = sequential ? var.seq : var.items;
         int threads = 128;
         int gpb = threads / var.G;
-        int64_t want_groups = p->concurrency;
-        int blocks;
-        size_t smem = 0;
-        if (want_groups == 0) {
-            smem = sizeof(int32_t) * ((size_t)p->exp_table_size + (size_t)Lmax * gpb);
-            int per_sm = 0;
-            cudaFuncSetAttribute(var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, var.fn, threads, smem);
-            if (per_sm < 1) per_sm = 1;
-            blocks = ctx->sm_count * per_sm;
-            int64_t need = (n_sent + gpb - 1) / gpb;
-            if (blocks > need) blocks = (int)need;
-        } else {
-            // exactly `concurrency` sentences in flight (1 = the sequential schedule of the oracle)
-            if (want_groups < gpb) { gpb = (int)want_groups; threads = gpb * var.G; }
-            blocks = (int)((want_groups + gpb - 1) / gpb);
-            smem = sizeof(int32_t) * ((size_t)p->exp_table_size + (size_t)Lmax * gpb);
-            cudaFuncSetAttribute(var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        }
+        size_t smem = sizeof(float) * (size_t)p->exp_table_size;
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
+        if (per_sm < 1) per_sm = 1;
+        const int64_t full_groups = (int64_t)ctx->sm_count * per_sm * gpb;
+        const int64_t units = sequential ? n_sent : n_sent * (int64_t)Lmax;
+        int64_t want;
+        if (p->concurrency > 0) want = sequential ? (int64_t)p->concurrency : (int64_t)p->concurrency * Lmax;
+        else if (sequential) want = full_groups;
+        else want = std::min<int64_t>(full_groups, std::max<int64_t>(gpb, 32LL * V / (p->negative + 1)));
+        want = std::max<int64_t>(1, std::min(want, units));
+        if (want < gpb) { gpb = (int)want; threads = gpb * var.G; }
+        int blocks = (int)((want + gpb - 1) / gpb);
         a.n_groups = (int64_t)blocks * gpb;
+        ctx->phase_ms["sgns_groups"] = (float)a.n_groups;
         dge_phase_timer t_sgns(ctx, "sgns");
-        var.fn<<<blocks, threads, smem, st>>>(a);
+        fn<<<blocks, threads, smem, st>>>(a);
         ctx->launches++;
         t_sgns.stop();
         ce = cudaGetLastError();
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-        if (ce != cudaSuccess) return fail(std::string("dge_sgns_train: kernel: ") + cudaGetErrorString(ce));
-        unsigned long long h_pairs = 0;
-        cudaMemcpy(&h_pairs, d_pairs, sizeof(h_pairs), cudaMemcpyDeviceToHost);
-        m->pairs = (int64_t)h_pairs;
+        if (ce != cudaSuccess) { cudaFree(d_wtok); return fail(std::string("dge_sgns_train: kernel: ") + cudaGetErrorString(ce)); }
+        unsigned long long h_pairs[2] = {0, 0};
+        cudaMemcpy(h_pairs, d_pairs, sizeof(h_pairs), cudaMemcpyDeviceToHost);
+        m->pairs = (int64_t)h_pairs[0];
+        m->words = (int64_t)h_pairs[1];
     }
+    cudaFree(d_wtok);
     ce = cudaStreamSynchronize(st);
     if (ce != cudaSuccess) return fail(std::string("dge_sgns_train: ") + cudaGetErrorString(ce));
     cleanup();

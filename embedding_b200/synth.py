@@ -68,3 +68,52 @@ def powerlaw_flow_graph(n_regions, L=24, seed=100000, mean_degree=42, cap=4096, 
     v = np.arange(nv, dtype=np.int32)
     return dict(n_vertices=nv, src=src, dst=dst, w=w, sources=np.arange(n_regions, dtype=np.int32),
                 v_layer=(v // n_regions).astype(np.int32), v_region=(v % n_regions).astype(np.int32))
+
+
+def poi_latents():
+    """Per-tract latent vectors: the 10 POI category counts of the reference's miscs/POI_tract.pickle
+    (ground truth of python/embeddingEvaluation_tract.py:63-103), in tract_ids() order; zeros if absent."""
+    header = ['Food', 'Residence', 'Travel', 'Arts & Entertainment', 'Outdoors & Recreation',
+              'College & Education', 'Nightlife', 'Professional', 'Shops', 'Event']
+    with open(os.path.join(_GOLDEN, "poi_tract.json")) as f:
+        d = json.load(f)
+    z = np.zeros((len(d["tract_ids"]), len(header)))
+    for i, t in enumerate(d["tract_ids"]):
+        for j, c in enumerate(header):
+            z[i, j] = d["poi"].get(str(t), {}).get(c, 0)
+    return z
+
+
+def ca_latents():
+    """Per-community-area latent vectors: the 20 binary label sets of miscs/{crime,lehd,demo,poi}-label."""
+    with open(os.path.join(_GOLDEN, "ca_labels.json")) as f:
+        d = json.load(f)
+    cols = [d["crime-label"], d["lehd-label"]] + [d["demo-label"][k] for k in sorted(d["demo-label"])] + \
+           [d["poi-label"][k] for k in sorted(d["poi-label"])]
+    return np.array(cols, np.float64).T
+
+
+def planted_flow_tensor(z, seed=2013, mean_trips_per_pair_hour=0.05, kappa=3.0):
+    """F[src, hour, dst] int32 ~ Poisson(rate) with a planted structure, so that the reference's downstream
+    metrics (which compare embeddings with POI / label ground truth) are informative on synthetic data:
+        rate(s, h, d) ~ emit_s(h) * attract_d(h) * exp(kappa * cos(z_s, z_d))
+    where emit / attract mix per-category hour profiles by the region's latent vector z (regions with similar
+    z send and receive similar flows).  The real flow records are absent from the reference."""
+    rng = np.random.default_rng(seed)
+    n, c = z.shape
+    zn = z / np.maximum(np.linalg.norm(z, axis=1, keepdims=True), 1e-12)
+    hours = np.arange(24)
+    prof_out = np.stack([np.exp(-0.5 * ((hours - rng.uniform(5, 22)) / rng.uniform(2, 5)) ** 2) for _ in range(c)])
+    prof_in = np.stack([np.exp(-0.5 * ((hours - rng.uniform(5, 22)) / rng.uniform(2, 5)) ** 2) for _ in range(c)])
+    size = 0.2 + z.sum(1) / max(z.sum(1).mean(), 1e-12)              # busier regions emit / attract more
+    emit = (zn @ prof_out + 0.05) * size[:, None]                     # [n, 24]
+    attract = (zn @ prof_in + 0.05) * size[:, None]                   # [n, 24]
+    aff = np.exp(kappa * (zn @ zn.T))                                 # [n, n]
+    F = np.empty((n, 24, n), np.int32)
+    total_target = mean_trips_per_pair_hour * n * n * 24
+    raw_total = sum(float((emit[:, h][:, None] * attract[:, h][None, :] * aff).sum()) for h in range(24))
+    scale = total_target / raw_total
+    for h in range(24):
+        rate = emit[:, h][:, None] * attract[:, h][None, :] * aff * scale
+        F[:, h, :] = rng.poisson(rate).astype(np.int32)
+    return F

@@ -119,6 +119,8 @@ void dge_corpus_free(dge_corpus *c);
 /* ------------------------------------------------------------------ stage 2: skip-gram
  * Stands under DeepWalk.learnEmbedding :32-83: Word2Vec.Builder()...build() :73-76 and w2v.fit() :79
  * (DL4J 0.7.2, external) and WordVectorSerializer.writeWordVectors :82. */
+enum { DGE_SCHEDULE_ITEMS = 0,     /* work item = (sentence, centre); row updates are 128-bit L2 reductions */
+       DGE_SCHEDULE_SENTENCE = 1 }; /* work item = sentence; plain atomic-free row stores (classic Hogwild) */
 typedef struct {
     int32_t dim;            /* layerSize(...)         DeepWalk.java:62-66,74 */
     int32_t window;         /* windowSize(numLayer)   :74 */
@@ -127,8 +129,10 @@ typedef struct {
     int32_t epochs;         /* iterations(1) x epochs(1) */
     int32_t neg_table_size; /* DL4J: 100000 */
     int32_t exp_table_size; /* sigmoid lookup table entries (1000) */
-    int32_t concurrency;    /* sentences in flight: 0 = fill the GPU; 1 = sequential (parity tests);
-                               the analogue of workers(8), :75 */
+    int32_t concurrency;    /* sentences in flight, the analogue of workers(8) :75.  0 = automatic (bounded by
+                               the vocabulary size); 1 = one sentence at a time in the oracle's
+                               exact order (parity tests); N = N sentences in flight */
+    int32_t schedule;       /* DGE_SCHEDULE_ITEMS (default) or DGE_SCHEDULE_SENTENCE */
     float lr;               /* 0.025 */
     float min_lr;           /* 1e-4 */
     uint64_t seed;

@@ -110,9 +110,22 @@ float ora_alpha(const ora_sgns_params *p, int32_t epoch, int64_t sentence, int64
     return a < p->min_lr ? p->min_lr : a;
 }
 
-static inline uint64_t lcg_abs(uint64_t r) { /* Math.abs(r * 25214903917L + 11) on a Java long */
-    int64_t x = (int64_t)(r * LCG_MUL + LCG_ADD);
-    return (uint64_t)(x < 0 ? -(uint64_t)x : (uint64_t)x);
+static inline uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+/* DL4J draws the window shrink b and the negative-sampling seed of each pair from a per-thread LCG
+ * chain (nextRandom), whose values depend on thread scheduling and are not reproducible.  The
+ * restatement keeps the same distributions but makes every draw a pure function of
+ * (seed, epoch, sentence, position[, context]) so that any schedule enumerates the same pairs:
+ *   position i : r = 63-bit uniform -> b = ((int) r) % window            (SkipGram.learnSequence)
+ *   pair (i,c) : 64-bit initial state of the aggregate's negative-sampling LCG (AggregateSkipGram) */
+uint64_t ora_position_rng(uint64_t S, int32_t i) {
+    return mix64(S + 0x9E3779B97F4A7C15ULL * (uint64_t)(i + 1)) & 0x7FFFFFFFFFFFFFFFULL;
+}
+uint64_t ora_pair_rng(uint64_t S, int32_t i, int32_t c) {
+    return mix64(S ^ (0xD6E8FEB86659FD93ULL * (uint64_t)((int64_t)i * 65536 + c + 1)));
 }
 
 /* Huffman tree (word2vec.c CreateBinaryTree): codes/points per word, for the optional HS rounds. */
@@ -194,9 +207,9 @@ static void *worker_run(void *arg) {
                 if (wd >= 0) sent[n++] = wd;
             }
             float alpha = ora_alpha(p, ep, s, w->n_sent);
-            uint64_t r = ora_sentence_rng(p->seed, ep, s);
+            const uint64_t S = ora_sentence_rng(p->seed, ep, s);
             for (int32_t i = 0; i < n; i++) {
-                r = lcg_abs(r);
+                uint64_t r = ora_position_rng(S, i);
                 int32_t b = (int32_t)(uint32_t)r % win; /* ((int) nextRandom) % window, may be negative */
                 int32_t w1 = sent[i];
                 int32_t end = win * 2 + 1 - b;
@@ -206,8 +219,7 @@ static void *worker_run(void *arg) {
                     if (c < 0 || c >= n) continue;
                     int32_t last = sent[c];
                     if (last == w1) continue;
-                    uint64_t ns = r;
-                    r = lcg_abs(r);
+                    uint64_t ns = ora_pair_rng(S, i, c);
                     pairs++;
                     if (w->count_only) continue;
                     float *v0 = syn0 + (int64_t)last * D;

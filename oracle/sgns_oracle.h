@@ -66,6 +66,8 @@ int64_t ora_sgns_count_pairs(const int32_t *tokens, int64_t n_sent, int32_t L, i
 
 /* building blocks exposed for tests */
 uint64_t ora_sentence_rng(uint64_t seed, int32_t epoch, int64_t sentence);
+uint64_t ora_position_rng(uint64_t sentence_key, int32_t position);
+uint64_t ora_pair_rng(uint64_t sentence_key, int32_t position, int32_t context);
 float ora_alpha(const ora_sgns_params *p, int32_t epoch, int64_t sentence, int64_t n_sent);
 
 #ifdef __cplusplus
