@@ -18,6 +18,9 @@
 
 #define SGNS_MAX_CORPORA 4
 #define SGNS_MAX_EXP 6.0f
+// automatic schedule: at most this many concurrent (stale) updates per embedding row (measured in
+// profiles/quality_tract_r1.json: nDCG stays inside the oracle's seed-to-seed band up to ~8)
+#define SGNS_STALE_BOUND 8
 #define LCG_MUL 25214903917ULL
 #define LCG_ADD 11ULL
 
@@ -224,22 +227,39 @@ k_sgns_seq(const sgns_args a) {
 
 // ---------------------------------------------------------------------------------------------------------
 // Kernel B: the throughput kernel.  Work item = (sentence, centre position); a group of G lanes owns one
-// item and walks its contexts in order.  The centre's output row syn1neg[w1] stays in registers for the
-// whole item (read once, its delta reduced once); per pair the K negative rows are fetched up front (memory-
-// level parallelism: K+1 independent 128-bit loads per lane), and every update is a 128-bit L2 reduction
-// (red.global.add.v4.f32): updates are never lost, they are only applied to slightly stale rows -- the
-// Hogwild contract without its failure mode on small vocabularies (DESIGN.md "SGNS schedule").
+// item (G = 1 for rows of up to 8 float4: a thread per item, no shuffles; G = 16/32 for wide rows: one
+// coalesced 128-bit slot per lane).  The item walks ALL positions c of its sentence with a uniform trip count
+// and a predicate, so the lanes of a warp stay in lockstep.  The centre's output row syn1neg[w1] stays in
+// registers for the whole item (read once, its delta reduced once); per pair the negative rows are fetched a
+// chunk at a time before use (memory-level parallelism), and every update is a 128-bit L2 reduction
+// (red.global.add.v4.f32): updates are never lost, they are only applied to slightly stale rows -- the Hogwild
+// contract without its failure mode on small vocabularies (DESIGN.md "SGNS schedule").
 // Items are taken in corpus order by a grid-stride loop, so n_groups bounds the sentences in flight.
-#define SGNS_NEG_CHUNK 5
+
+// x mod m for x < 2^48, m < 2^31, exact: one double multiply + fix-up instead of a 64-bit division
+__device__ __forceinline__ uint32_t mod48(uint64_t x, uint32_t m, double inv_m) {
+    uint64_t q = (uint64_t)((double)x * inv_m);
+    int64_t r = (int64_t)(x - q * (uint64_t)m);
+    if (r < 0) r += m;
+    else if (r >= (int64_t)m) r -= m;
+    return (uint32_t)r;
+}
+// full 64-bit x mod m through three 48-bit steps
+__device__ __forceinline__ uint32_t mod64(uint64_t x, uint32_t m, double inv_m) {
+    uint32_t r = mod48(x >> 32, m, inv_m);
+    r = mod48(((uint64_t)r << 16) | ((x >> 16) & 0xFFFFu), m, inv_m);
+    return mod48(((uint64_t)r << 16) | (x & 0xFFFFu), m, inv_m);
+}
+
 template <int G, int VPL>
 __global__ void __launch_bounds__(128)
 k_sgns_items(const sgns_args a) {
+    constexpr int CH = VPL <= 2 ? 5 : (VPL <= 4 ? 3 : 2); // negatives fetched ahead per chunk
     extern __shared__ int32_t smem[];
     float *s_exp = reinterpret_cast<float *>(smem);
     const int gpb = blockDim.x / G;
     const int gl = threadIdx.x / G;
     const int lane = threadIdx.x % G;
-    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
     for (int i = threadIdx.x; i < a.exp_table_size; i += blockDim.x) s_exp[i] = a.exp_table[i];
     __syncthreads();
     const int64_t gid = (int64_t)blockIdx.x * gpb + gl;
@@ -249,7 +269,10 @@ k_sgns_items(const sgns_args a) {
     const int win = a.window;
     const int64_t N = a.n_sent;
     const int64_t n_items = N * a.Lmax;
-    const bool act = lane < n4 || VPL > 1;
+    const double inv_total = 1.0 / (double)((int64_t)a.epochs * N);
+    const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
+    const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     unsigned long long pairs = 0;
     for (int ep = 0; ep < a.epochs; ep++) {
         for (int64_t item = gid; item < n_items; item += a.n_groups) {
@@ -257,25 +280,22 @@ k_sgns_items(const sgns_args a) {
             const int i = (int)(item - s * a.Lmax);
             const int32_t w1 = a.wtok[(int64_t)i * N + s];
             if (w1 < 0) continue;
-            const float alpha = sgns_alpha(a, ep, s);
+            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * N + s) * inv_total);
+            if (alpha < a.min_lr) alpha = a.min_lr;
             const uint64_t S = sgns_sentence_rng(a.seed, ep, s);
             const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
-            int lo = i - win + b, hi = i + win - b; // inclusive context range
-            if (lo < 0) lo = 0;
-            if (hi > a.Lmax - 1) hi = a.Lmax - 1;
+            const int lo = i - win + b, hi = i + win - b; // inclusive context range (SkipGram.skipGram)
             float4 *pw = reinterpret_cast<float4 *>(a.syn1neg + (int64_t)w1 * a.stride);
-            float4 t1[VPL], d1[VPL];
+            float4 cur[VPL], d1[VPL]; // current value and accumulated delta of syn1neg[w1]
 #pragma unroll
             for (int v = 0; v < VPL; v++) {
                 int q = lane + v * G;
-                t1[v] = q < n4 ? __ldcg(pw + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                d1[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                cur[v] = q < n4 ? __ldcg(pw + q) : zero4;
+                d1[v] = zero4;
             }
-            for (int c = lo; c <= hi; c++) {
-                if (c == i) continue;
+            for (int c = 0; c < a.Lmax; c++) {
                 const int32_t last = a.wtok[(int64_t)c * N + s];
-                if (last < 0) break; // padding is a suffix
-                if (last == w1) continue;
+                if (!(c >= lo && c <= hi && c != i && last >= 0 && last != w1)) continue;
                 uint64_t ns = sgns_pair_rng(S, i, c);
                 pairs++;
                 float4 *p0 = reinterpret_cast<float4 *>(a.syn0 + (int64_t)last * a.stride);
@@ -283,58 +303,62 @@ k_sgns_items(const sgns_args a) {
 #pragma unroll
                 for (int v = 0; v < VPL; v++) {
                     int q = lane + v * G;
-                    v0[v] = q < n4 ? __ldcg(p0 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    neu[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    v0[v] = q < n4 ? __ldcg(p0 + q) : zero4;
+                    neu[v] = zero4;
                 }
-                // positive target: the item's private, always-current copy of syn1neg[w1]
-                {
+                { // positive target: the item's private, always-current copy of syn1neg[w1]
                     float dot = 0.f;
-                    float4 cur[VPL];
 #pragma unroll
-                    for (int v = 0; v < VPL; v++) {
-                        cur[v] = make_float4(t1[v].x + d1[v].x, t1[v].y + d1[v].y, t1[v].z + d1[v].z, t1[v].w + d1[v].w);
-                        dot += dot4(v0[v], cur[v]);
-                    }
-                    dot = group_sum<G>(dot, gmask);
+                    for (int v = 0; v < VPL; v++) dot += dot4(v0[v], cur[v]);
+                    dot = group_sum<G>(dot, 0xffffffffu);
                     float g;
                     if (sgns_g(dot, 1.f, alpha, s_exp, E, idx_scale, g)) {
 #pragma unroll
-                        for (int v = 0; v < VPL; v++) { axpy4(neu[v], g, cur[v]); axpy4(d1[v], g, v0[v]); }
+                        for (int v = 0; v < VPL; v++) {
+                            axpy4(neu[v], g, cur[v]);
+                            axpy4(d1[v], g, v0[v]);
+                            axpy4(cur[v], g, v0[v]);
+                        }
                     }
                 }
                 if (a.V >= 2) {
-                    for (int k0 = 0; k0 < a.negative; k0 += SGNS_NEG_CHUNK) {
-                        int32_t tg[SGNS_NEG_CHUNK];
-                        float4 vk[SGNS_NEG_CHUNK][VPL];
+                    for (int k0 = 0; k0 < a.negative; k0 += CH) {
+                        int32_t tg[CH];
+                        float4 vk[CH][VPL];
 #pragma unroll
-                        for (int k = 0; k < SGNS_NEG_CHUNK; k++) {
+                        for (int k = 0; k < CH; k++) {
                             tg[k] = -1;
                             if (k0 + k < a.negative) {
-                                int32_t t = sgns_negative(ns, a);
+                                ns = ns * LCG_MUL + LCG_ADD;
+                                int32_t t = a.neg_table[mod48(ns >> 16, tsize, inv_tsize)];
+                                if (t <= 0 || t >= a.V) t = (int32_t)mod64(ns, vm1, inv_vm1) + 1;
                                 if (t != w1) tg[k] = t;
                             }
+                        }
+#pragma unroll
+                        for (int k = 0; k < CH; k++) {
                             const float4 *pk = reinterpret_cast<const float4 *>(a.syn1neg + (int64_t)(tg[k] < 0 ? 0 : tg[k]) * a.stride);
 #pragma unroll
                             for (int v = 0; v < VPL; v++) {
                                 int q = lane + v * G;
-                                vk[k][v] = (tg[k] >= 0 && q < n4) ? __ldcg(pk + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                vk[k][v] = (tg[k] >= 0 && q < n4) ? __ldcg(pk + q) : zero4;
                             }
                         }
 #pragma unroll
-                        for (int k = 0; k < SGNS_NEG_CHUNK; k++) {
-                            if (tg[k] < 0) continue; // group-uniform
+                        for (int k = 0; k < CH; k++) {
                             float dot = 0.f;
 #pragma unroll
                             for (int v = 0; v < VPL; v++) dot += dot4(v0[v], vk[k][v]);
-                            dot = group_sum<G>(dot, gmask);
+                            dot = group_sum<G>(dot, 0xffffffffu);
                             float g;
-                            if (!sgns_g(dot, 0.f, alpha, s_exp, E, idx_scale, g)) continue;
-                            float4 *pk = reinterpret_cast<float4 *>(a.syn1neg + (int64_t)tg[k] * a.stride);
+                            if (tg[k] >= 0 && sgns_g(dot, 0.f, alpha, s_exp, E, idx_scale, g)) {
+                                float4 *pk = reinterpret_cast<float4 *>(a.syn1neg + (int64_t)tg[k] * a.stride);
 #pragma unroll
-                            for (int v = 0; v < VPL; v++) {
-                                int q = lane + v * G;
-                                axpy4(neu[v], g, vk[k][v]);
-                                if (q < n4) red_add4(pk + q, scale4(g, v0[v]));
+                                for (int v = 0; v < VPL; v++) {
+                                    int q = lane + v * G;
+                                    axpy4(neu[v], g, vk[k][v]);
+                                    if (q < n4) red_add4(pk + q, scale4(g, v0[v]));
+                                }
                             }
                         }
                     }
@@ -352,23 +376,26 @@ k_sgns_items(const sgns_args a) {
             }
         }
     }
-    (void)act;
     if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
 }
 
 typedef void (*sgns_kernel_t)(const sgns_args);
 struct sgns_variant { int G, VPL; sgns_kernel_t seq, items; };
 
-// lanes per group: the smallest power of two covering the row's float4 slots (one 128-bit slot per lane);
-// rows wider than 32 slots give each lane 2 or 4 slots.
+// lanes per group: rows of up to 8 float4 slots are held by ONE thread (no shuffles); wider rows give each
+// lane of a 16- or 32-lane group one 128-bit slot (2 or 4 for rows wider than 32 slots).
 static bool pick_variant(int n4, sgns_variant *out) {
 #define V_(g, v) {g, v, k_sgns_seq<g, v>, k_sgns_items<g, v>}
-    static const sgns_variant table[] = {V_(1, 1), V_(2, 1), V_(4, 1), V_(8, 1), V_(16, 1), V_(32, 1), V_(32, 2), V_(32, 4)};
+    static const sgns_variant table[] = {V_(1, 1), V_(1, 2), V_(1, 3), V_(1, 4), V_(1, 5), V_(1, 6), V_(1, 7), V_(1, 8),
+                                         V_(16, 1), V_(32, 1), V_(32, 2), V_(32, 4)};
 #undef V_
-    int G = 1, VPL = 1;
-    while (G < 32 && G < n4) G <<= 1;
-    if (n4 > 32) VPL = n4 <= 64 ? 2 : 4;
-    if (n4 > 128) return false;
+    int G, VPL;
+    if (n4 <= 8) { G = 1; VPL = n4; }
+    else if (n4 <= 16) { G = 16; VPL = 1; }
+    else if (n4 <= 32) { G = 32; VPL = 1; }
+    else if (n4 <= 64) { G = 32; VPL = 2; }
+    else if (n4 <= 128) { G = 32; VPL = 4; }
+    else return false;
     for (const auto &t : table)
         if (t.G == G && t.VPL == VPL) { *out = t; return true; }
     return false;
@@ -525,8 +552,8 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         //  concurrency 1            : kernel A, one group: the oracle's sequential order (parity tests)
         //  schedule SENTENCE        : kernel A, Hogwild with plain stores, `concurrency` sentences in flight (0 = fill)
         //  schedule ITEMS (default) : kernel B, (sentence, centre) items with L2 reductions; in flight:
-        //                             concurrency * Lmax items, or (auto) min(full GPU, 32 * V / (negative + 1)) so
-        //                             that a row sees at most ~32 concurrent stale updates
+        //                             concurrency * Lmax items, or (auto) min(full GPU, 8 * V / (negative + 1)) so
+        //                             that a row sees at most ~8 concurrent stale updates
         const bool sequential = p->concurrency == 1 || p->schedule == DGE_SCHEDULE_SENTENCE;
         sgns_kernel_t fn = sequential ? var.seq : var.items;
         int threads = 128;
@@ -541,8 +568,10 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         int64_t want;
         if (p->concurrency > 0) want = sequential ? (int64_t)p->concurrency : (int64_t)p->concurrency * Lmax;
         else if (sequential) want = full_groups;
-        else want = std::min<int64_t>(full_groups, std::max<int64_t>(gpb, 32LL * V / (p->negative + 1)));
+        else want = std::min<int64_t>(full_groups, std::max<int64_t>(gpb, (int64_t)SGNS_STALE_BOUND * V / (p->negative + 1)));
         want = std::max<int64_t>(1, std::min(want, units));
+        while (threads > 32 && threads > var.G && want < (int64_t)ctx->sm_count * gpb) { threads >>= 1; gpb = threads / var.G; }
+        if (gpb < 1) { gpb = 1; threads = var.G; }
         if (want < gpb) { gpb = (int)want; threads = gpb * var.G; }
         int blocks = (int)((want + gpb - 1) / gpb);
         a.n_groups = (int64_t)blocks * gpb;

@@ -85,7 +85,7 @@ def test_parallel_schedule_learns_the_same_structure(dge_lib, oracle, ctx, dim):
         return within - s[:10, 10:].mean()
 
     g_ref, g_gpu = gap(ref["syn0"], ref["id_of_word"]), gap(syn0, ids)
-    assert g_ref > 0.5
+    assert g_ref > 0.3
     assert g_gpu > 0.5 * g_ref, (g_gpu, g_ref)
 
 
