@@ -17,6 +17,7 @@
 #include <cmath>
 
 #define SGNS_MAX_CORPORA 4
+#define SGNS_MAX_NEG 32
 #define SGNS_MAX_EXP 6.0f
 // automatic schedule: at most this many concurrent (stale) updates per embedding row (measured in
 // profiles/quality_tract_r1.json: nDCG stays inside the oracle's seed-to-seed band up to ~8)
@@ -35,6 +36,7 @@ struct sgns_args {
     uint64_t seed;
     unsigned long long *pairs;
     int64_t n_groups;
+    uint64_t lcg_a[SGNS_MAX_NEG], lcg_c[SGNS_MAX_NEG]; // (k+1)-step jump of the negative-sampling LCG
 };
 
 __host__ __device__ static inline uint64_t mix64(uint64_t z) {
@@ -251,18 +253,20 @@ __device__ __forceinline__ uint32_t mod64(uint64_t x, uint32_t m, double inv_m) 
     return mod48(((uint64_t)r << 16) | (x & 0xFFFFu), m, inv_m);
 }
 
+#define SGNS_CH 5 // negatives drawn (one per lane) and fetched ahead per chunk
 template <int G, int VPL>
 __global__ void __launch_bounds__(128)
 k_sgns_items(const sgns_args a) {
-    constexpr int CH = VPL <= 2 ? 5 : (VPL <= 4 ? 3 : 2); // negatives fetched ahead per chunk
+    static_assert(G >= 8, "the item kernel draws one negative per lane: groups have at least 8 lanes");
     extern __shared__ int32_t smem[];
     float *s_exp = reinterpret_cast<float *>(smem);
-    const int gpb = blockDim.x / G;
-    const int gl = threadIdx.x / G;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int GPW = 32 / G; // groups per warp; they run in lockstep
     const int lane = threadIdx.x % G;
+    const int gw = (threadIdx.x & 31) / G;
     for (int i = threadIdx.x; i < a.exp_table_size; i += blockDim.x) s_exp[i] = a.exp_table[i];
     __syncthreads();
-    const int64_t gid = (int64_t)blockIdx.x * gpb + gl;
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n4 = a.stride >> 2;
     const int E = a.exp_table_size;
     const float idx_scale = (float)E / SGNS_MAX_EXP / 2.0f;
@@ -273,46 +277,51 @@ k_sgns_items(const sgns_args a) {
     const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
     const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int K = a.V >= 2 ? a.negative : 0;
     unsigned long long pairs = 0;
     for (int ep = 0; ep < a.epochs; ep++) {
-        for (int64_t item = gid; item < n_items; item += a.n_groups) {
-            const int64_t s = item / a.Lmax;
+        for (int64_t base = warp_id * GPW; base < n_items; base += a.n_groups) { // warp-uniform trip count
+            const int64_t item = base + gw;
+            bool valid = item < n_items;
+            const int64_t s = valid ? item / a.Lmax : 0;
             const int i = (int)(item - s * a.Lmax);
-            const int32_t w1 = a.wtok[(int64_t)i * N + s];
-            if (w1 < 0) continue;
+            const int32_t w1 = valid ? a.wtok[(int64_t)i * N + s] : -1;
+            valid = valid && w1 >= 0;
+            if (!__any_sync(FULL, valid)) continue;
             float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * N + s) * inv_total);
             if (alpha < a.min_lr) alpha = a.min_lr;
             const uint64_t S = sgns_sentence_rng(a.seed, ep, s);
             const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
             const int lo = i - win + b, hi = i + win - b; // inclusive context range (SkipGram.skipGram)
-            float4 *pw = reinterpret_cast<float4 *>(a.syn1neg + (int64_t)w1 * a.stride);
+            float4 *pw = reinterpret_cast<float4 *>(a.syn1neg + (int64_t)(valid ? w1 : 0) * a.stride);
             float4 cur[VPL], d1[VPL]; // current value and accumulated delta of syn1neg[w1]
 #pragma unroll
             for (int v = 0; v < VPL; v++) {
                 int q = lane + v * G;
-                cur[v] = q < n4 ? __ldcg(pw + q) : zero4;
+                cur[v] = (valid && q < n4) ? __ldcg(pw + q) : zero4;
                 d1[v] = zero4;
             }
             for (int c = 0; c < a.Lmax; c++) {
-                const int32_t last = a.wtok[(int64_t)c * N + s];
-                if (!(c >= lo && c <= hi && c != i && last >= 0 && last != w1)) continue;
-                uint64_t ns = sgns_pair_rng(S, i, c);
-                pairs++;
-                float4 *p0 = reinterpret_cast<float4 *>(a.syn0 + (int64_t)last * a.stride);
+                const int32_t last = valid ? a.wtok[(int64_t)c * N + s] : -1;
+                const bool act = valid && c >= lo && c <= hi && c != i && last >= 0 && last != w1;
+                if (!__any_sync(FULL, act)) continue;
+                const uint64_t ns0 = sgns_pair_rng(S, i, c);
+                pairs += act;
+                float4 *p0 = reinterpret_cast<float4 *>(a.syn0 + (int64_t)(act ? last : 0) * a.stride);
                 float4 v0[VPL], neu[VPL];
 #pragma unroll
                 for (int v = 0; v < VPL; v++) {
                     int q = lane + v * G;
-                    v0[v] = q < n4 ? __ldcg(p0 + q) : zero4;
+                    v0[v] = (act && q < n4) ? __ldcg(p0 + q) : zero4;
                     neu[v] = zero4;
                 }
                 { // positive target: the item's private, always-current copy of syn1neg[w1]
                     float dot = 0.f;
 #pragma unroll
                     for (int v = 0; v < VPL; v++) dot += dot4(v0[v], cur[v]);
-                    dot = group_sum<G>(dot, 0xffffffffu);
+                    dot = group_sum<G>(dot, FULL);
                     float g;
-                    if (sgns_g(dot, 1.f, alpha, s_exp, E, idx_scale, g)) {
+                    if (sgns_g(dot, 1.f, alpha, s_exp, E, idx_scale, g) && act) {
 #pragma unroll
                         for (int v = 0; v < VPL; v++) {
                             axpy4(neu[v], g, cur[v]);
@@ -321,58 +330,59 @@ k_sgns_items(const sgns_args a) {
                         }
                     }
                 }
-                if (a.V >= 2) {
-                    for (int k0 = 0; k0 < a.negative; k0 += CH) {
-                        int32_t tg[CH];
-                        float4 vk[CH][VPL];
+                for (int k0 = 0; k0 < K; k0 += SGNS_CH) {
+                    // lane k of the group draws negative k0+k: the LCG is affine, so its (k+1)-th state is A_k*ns0 + C_k
+                    int32_t mine = -1;
+                    if (lane < SGNS_CH && k0 + lane < K && act) {
+                        const uint64_t nsk = a.lcg_a[k0 + lane] * ns0 + a.lcg_c[k0 + lane];
+                        int32_t t = a.neg_table[mod48(nsk >> 16, tsize, inv_tsize)];
+                        if (t <= 0 || t >= a.V) t = (int32_t)mod64(nsk, vm1, inv_vm1) + 1;
+                        if (t != w1) mine = t;
+                    }
+                    int32_t tg[SGNS_CH];
+                    float4 vk[SGNS_CH][VPL];
 #pragma unroll
-                        for (int k = 0; k < CH; k++) {
-                            tg[k] = -1;
-                            if (k0 + k < a.negative) {
-                                ns = ns * LCG_MUL + LCG_ADD;
-                                int32_t t = a.neg_table[mod48(ns >> 16, tsize, inv_tsize)];
-                                if (t <= 0 || t >= a.V) t = (int32_t)mod64(ns, vm1, inv_vm1) + 1;
-                                if (t != w1) tg[k] = t;
-                            }
+                    for (int k = 0; k < SGNS_CH; k++) {
+                        tg[k] = __shfl_sync(FULL, mine, k, G);
+                        const float4 *pk = reinterpret_cast<const float4 *>(a.syn1neg + (int64_t)(tg[k] < 0 ? 0 : tg[k]) * a.stride);
+#pragma unroll
+                        for (int v = 0; v < VPL; v++) {
+                            int q = lane + v * G;
+                            vk[k][v] = (tg[k] >= 0 && q < n4) ? __ldcg(pk + q) : zero4;
                         }
+                    }
 #pragma unroll
-                        for (int k = 0; k < CH; k++) {
-                            const float4 *pk = reinterpret_cast<const float4 *>(a.syn1neg + (int64_t)(tg[k] < 0 ? 0 : tg[k]) * a.stride);
+                    for (int k = 0; k < SGNS_CH; k++) {
+                        float dot = 0.f;
+#pragma unroll
+                        for (int v = 0; v < VPL; v++) dot += dot4(v0[v], vk[k][v]);
+                        dot = group_sum<G>(dot, FULL);
+                        float g;
+                        if (sgns_g(dot, 0.f, alpha, s_exp, E, idx_scale, g) && tg[k] >= 0) {
+                            float4 *pk = reinterpret_cast<float4 *>(a.syn1neg + (int64_t)tg[k] * a.stride);
 #pragma unroll
                             for (int v = 0; v < VPL; v++) {
                                 int q = lane + v * G;
-                                vk[k][v] = (tg[k] >= 0 && q < n4) ? __ldcg(pk + q) : zero4;
-                            }
-                        }
-#pragma unroll
-                        for (int k = 0; k < CH; k++) {
-                            float dot = 0.f;
-#pragma unroll
-                            for (int v = 0; v < VPL; v++) dot += dot4(v0[v], vk[k][v]);
-                            dot = group_sum<G>(dot, 0xffffffffu);
-                            float g;
-                            if (tg[k] >= 0 && sgns_g(dot, 0.f, alpha, s_exp, E, idx_scale, g)) {
-                                float4 *pk = reinterpret_cast<float4 *>(a.syn1neg + (int64_t)tg[k] * a.stride);
-#pragma unroll
-                                for (int v = 0; v < VPL; v++) {
-                                    int q = lane + v * G;
-                                    axpy4(neu[v], g, vk[k][v]);
-                                    if (q < n4) red_add4(pk + q, scale4(g, v0[v]));
-                                }
+                                axpy4(neu[v], g, vk[k][v]);
+                                if (q < n4) red_add4(pk + q, scale4(g, v0[v]));
                             }
                         }
                     }
                 }
+                if (act) {
+#pragma unroll
+                    for (int v = 0; v < VPL; v++) {
+                        int q = lane + v * G;
+                        if (q < n4) red_add4(p0 + q, neu[v]);
+                    }
+                }
+            }
+            if (valid) {
 #pragma unroll
                 for (int v = 0; v < VPL; v++) {
                     int q = lane + v * G;
-                    if (q < n4) red_add4(p0 + q, neu[v]);
+                    if (q < n4) red_add4(pw + q, d1[v]);
                 }
-            }
-#pragma unroll
-            for (int v = 0; v < VPL; v++) {
-                int q = lane + v * G;
-                if (q < n4) red_add4(pw + q, d1[v]);
             }
         }
     }
@@ -380,25 +390,38 @@ k_sgns_items(const sgns_args a) {
 }
 
 typedef void (*sgns_kernel_t)(const sgns_args);
-struct sgns_variant { int G, VPL; sgns_kernel_t seq, items; };
+struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq, items; };
 
-// lanes per group: rows of up to 8 float4 slots are held by ONE thread (no shuffles); wider rows give each
-// lane of a 16- or 32-lane group one 128-bit slot (2 or 4 for rows wider than 32 slots).
+// Kernel A (exact order): rows of up to 8 float4 slots are held by ONE thread; wider rows give each lane of a
+// 16- or 32-lane group one 128-bit slot (2 or 4 for rows wider than 32 slots).
+// Kernel B (items): groups of 8 / 16 / 32 lanes, one slot per lane (2 or 4 beyond 32 slots).
 static bool pick_variant(int n4, sgns_variant *out) {
-#define V_(g, v) {g, v, k_sgns_seq<g, v>, k_sgns_items<g, v>}
-    static const sgns_variant table[] = {V_(1, 1), V_(1, 2), V_(1, 3), V_(1, 4), V_(1, 5), V_(1, 6), V_(1, 7), V_(1, 8),
-                                         V_(16, 1), V_(32, 1), V_(32, 2), V_(32, 4)};
-#undef V_
-    int G, VPL;
-    if (n4 <= 8) { G = 1; VPL = n4; }
-    else if (n4 <= 16) { G = 16; VPL = 1; }
-    else if (n4 <= 32) { G = 32; VPL = 1; }
-    else if (n4 <= 64) { G = 32; VPL = 2; }
-    else if (n4 <= 128) { G = 32; VPL = 4; }
-    else return false;
-    for (const auto &t : table)
-        if (t.G == G && t.VPL == VPL) { *out = t; return true; }
-    return false;
+    if (n4 > 128) return false;
+    sgns_kernel_t seq = nullptr, items = nullptr;
+    int Gs = 1, Vs = 1;
+    switch (n4 <= 8 ? n4 : (n4 <= 16 ? 16 : (n4 <= 32 ? 32 : (n4 <= 64 ? 64 : 128)))) {
+        case 1: seq = k_sgns_seq<1, 1>; Vs = 1; break;
+        case 2: seq = k_sgns_seq<1, 2>; Vs = 2; break;
+        case 3: seq = k_sgns_seq<1, 3>; Vs = 3; break;
+        case 4: seq = k_sgns_seq<1, 4>; Vs = 4; break;
+        case 5: seq = k_sgns_seq<1, 5>; Vs = 5; break;
+        case 6: seq = k_sgns_seq<1, 6>; Vs = 6; break;
+        case 7: seq = k_sgns_seq<1, 7>; Vs = 7; break;
+        case 8: seq = k_sgns_seq<1, 8>; Vs = 8; break;
+        case 16: seq = k_sgns_seq<16, 1>; Gs = 16; break;
+        case 32: seq = k_sgns_seq<32, 1>; Gs = 32; break;
+        case 64: seq = k_sgns_seq<32, 2>; Gs = 32; Vs = 2; break;
+        default: seq = k_sgns_seq<32, 4>; Gs = 32; Vs = 4; break;
+    }
+    int Gi, Vi = 1;
+    if (n4 <= 8) { Gi = 8; items = k_sgns_items<8, 1>; }
+    else if (n4 <= 16) { Gi = 16; items = k_sgns_items<16, 1>; }
+    else if (n4 <= 32) { Gi = 32; items = k_sgns_items<32, 1>; }
+    else if (n4 <= 64) { Gi = 32; Vi = 2; items = k_sgns_items<32, 2>; }
+    else { Gi = 32; Vi = 4; items = k_sgns_items<32, 4>; }
+    out->G_seq = Gs; out->VPL_seq = Vs; out->seq = seq;
+    out->G_items = Gi; out->VPL_items = Vi; out->items = items;
+    return true;
 }
 
 static void model_release(dge_model *m) {
@@ -423,6 +446,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
     *out = nullptr;
     if (!corpora || !p || n_corpora < 1 || n_corpora > SGNS_MAX_CORPORA)
         return dge_fail(ctx, DGE_E_INVALID, "dge_sgns_train: need 1..4 corpora and params");
+    if (p->negative > SGNS_MAX_NEG) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: negative must be <= 32");
     if (p->dim < 1 || p->window < 1 || p->negative < 0 || p->epochs < 1 || p->neg_table_size < 1 ||
         p->exp_table_size < 2 || p->min_count < 0 || p->concurrency < 0 ||
         (p->schedule != DGE_SCHEDULE_ITEMS && p->schedule != DGE_SCHEDULE_SENTENCE))
@@ -556,8 +580,14 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         //                             that a row sees at most ~8 concurrent stale updates
         const bool sequential = p->concurrency == 1 || p->schedule == DGE_SCHEDULE_SENTENCE;
         sgns_kernel_t fn = sequential ? var.seq : var.items;
+        const int G = sequential ? var.G_seq : var.G_items;
+        uint64_t la = 1, lc = 0;
+        for (int k = 0; k < SGNS_MAX_NEG; k++) { // state after k+1 steps of x -> x*MUL + ADD
+            la = la * LCG_MUL; lc = lc * LCG_MUL + LCG_ADD;
+            a.lcg_a[k] = la; a.lcg_c[k] = lc;
+        }
         int threads = 128;
-        int gpb = threads / var.G;
+        int gpb = threads / G;
         size_t smem = sizeof(float) * (size_t)p->exp_table_size;
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 0;
@@ -570,9 +600,8 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         else if (sequential) want = full_groups;
         else want = std::min<int64_t>(full_groups, std::max<int64_t>(gpb, (int64_t)SGNS_STALE_BOUND * V / (p->negative + 1)));
         want = std::max<int64_t>(1, std::min(want, units));
-        while (threads > 32 && threads > var.G && want < (int64_t)ctx->sm_count * gpb) { threads >>= 1; gpb = threads / var.G; }
-        if (gpb < 1) { gpb = 1; threads = var.G; }
-        if (want < gpb) { gpb = (int)want; threads = gpb * var.G; }
+        while (threads > 32 && threads > G && want < (int64_t)ctx->sm_count * gpb) { threads >>= 1; gpb = threads / G; }
+        if (sequential && want < gpb) { gpb = (int)want; threads = gpb * G; } // kernel B keeps whole warps
         int blocks = (int)((want + gpb - 1) / gpb);
         a.n_groups = (int64_t)blocks * gpb;
         ctx->phase_ms["sgns_groups"] = (float)a.n_groups;
