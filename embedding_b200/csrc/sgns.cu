@@ -267,7 +267,6 @@ k_sgns_items(const sgns_args a) {
     for (int i = threadIdx.x; i < a.exp_table_size; i += blockDim.x) s_exp[i] = a.exp_table[i];
     __syncthreads();
     const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int n4 = a.stride >> 2;
     const int E = a.exp_table_size;
     const float idx_scale = (float)E / SGNS_MAX_EXP / 2.0f;
     const int win = a.window;
@@ -278,14 +277,18 @@ k_sgns_items(const sgns_args a) {
     const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const int K = a.V >= 2 ? a.negative : 0;
+    // Rows are zero-padded to a multiple of G float4 slots (stride = 4*G*VPL floats), so every lane owns VPL
+    // slots of every row and no loaded value ever needs masking: invalid work is cancelled through g = 0.
+    // (A predicated or masked load makes ptxas consume each load before issuing the next; plain back-to-back
+    // loads keep K+1 rows in flight per lane.)
     unsigned long long pairs = 0;
     for (int ep = 0; ep < a.epochs; ep++) {
         for (int64_t base = warp_id * GPW; base < n_items; base += a.n_groups) { // warp-uniform trip count
             const int64_t item = base + gw;
             bool valid = item < n_items;
             const int64_t s = valid ? item / a.Lmax : 0;
-            const int i = (int)(item - s * a.Lmax);
-            const int32_t w1 = valid ? a.wtok[(int64_t)i * N + s] : -1;
+            const int i = valid ? (int)(item - s * a.Lmax) : 0;
+            const int32_t w1 = a.wtok[(int64_t)i * N + s]; // (s, i) = (0, 0) when the item is out of range: in bounds
             valid = valid && w1 >= 0;
             if (!__any_sync(FULL, valid)) continue;
             float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * N + s) * inv_total);
@@ -296,13 +299,9 @@ k_sgns_items(const sgns_args a) {
             float4 *pw = reinterpret_cast<float4 *>(a.syn1neg + (int64_t)(valid ? w1 : 0) * a.stride);
             float4 cur[VPL], d1[VPL]; // current value and accumulated delta of syn1neg[w1]
 #pragma unroll
-            for (int v = 0; v < VPL; v++) {
-                int q = lane + v * G;
-                cur[v] = (valid && q < n4) ? __ldcg(pw + q) : zero4;
-                d1[v] = zero4;
-            }
+            for (int v = 0; v < VPL; v++) { cur[v] = __ldcg(pw + lane + v * G); d1[v] = zero4; }
             for (int c = 0; c < a.Lmax; c++) {
-                const int32_t last = valid ? a.wtok[(int64_t)c * N + s] : -1;
+                const int32_t last = a.wtok[(int64_t)c * N + s];
                 const bool act = valid && c >= lo && c <= hi && c != i && last >= 0 && last != w1;
                 if (!__any_sync(FULL, act)) continue;
                 const uint64_t ns0 = sgns_pair_rng(S, i, c);
@@ -310,18 +309,23 @@ k_sgns_items(const sgns_args a) {
                 float4 *p0 = reinterpret_cast<float4 *>(a.syn0 + (int64_t)(act ? last : 0) * a.stride);
                 float4 v0[VPL], neu[VPL];
 #pragma unroll
-                for (int v = 0; v < VPL; v++) {
-                    int q = lane + v * G;
-                    v0[v] = (act && q < n4) ? __ldcg(p0 + q) : zero4;
-                    neu[v] = zero4;
+                for (int v = 0; v < VPL; v++) { v0[v] = __ldcg(p0 + lane + v * G); neu[v] = zero4; }
+                // negatives of the first chunk: lane k draws negative k (the LCG is affine: state k+1 = A_k*ns0 + C_k)
+                int32_t mine = -1;
+                if (lane < SGNS_CH && lane < K && act) {
+                    const uint64_t nsk = a.lcg_a[lane] * ns0 + a.lcg_c[lane];
+                    int32_t t = a.neg_table[mod48(nsk >> 16, tsize, inv_tsize)];
+                    if (t <= 0 || t >= a.V) t = (int32_t)mod64(nsk, vm1, inv_vm1) + 1;
+                    if (t != w1) mine = t;
                 }
                 { // positive target: the item's private, always-current copy of syn1neg[w1]
                     float dot = 0.f;
 #pragma unroll
                     for (int v = 0; v < VPL; v++) dot += dot4(v0[v], cur[v]);
                     dot = group_sum<G>(dot, FULL);
-                    float g;
-                    if (sgns_g(dot, 1.f, alpha, s_exp, E, idx_scale, g) && act) {
+                    float g = 0.f;
+                    if (!(sgns_g(dot, 1.f, alpha, s_exp, E, idx_scale, g) && act)) g = 0.f;
+                    {
 #pragma unroll
                         for (int v = 0; v < VPL; v++) {
                             axpy4(neu[v], g, cur[v]);
@@ -331,25 +335,24 @@ k_sgns_items(const sgns_args a) {
                     }
                 }
                 for (int k0 = 0; k0 < K; k0 += SGNS_CH) {
-                    // lane k of the group draws negative k0+k: the LCG is affine, so its (k+1)-th state is A_k*ns0 + C_k
-                    int32_t mine = -1;
-                    if (lane < SGNS_CH && k0 + lane < K && act) {
-                        const uint64_t nsk = a.lcg_a[k0 + lane] * ns0 + a.lcg_c[k0 + lane];
-                        int32_t t = a.neg_table[mod48(nsk >> 16, tsize, inv_tsize)];
-                        if (t <= 0 || t >= a.V) t = (int32_t)mod64(nsk, vm1, inv_vm1) + 1;
-                        if (t != w1) mine = t;
+                    if (k0 > 0) { // further chunks (negative > 5)
+                        mine = -1;
+                        if (lane < SGNS_CH && k0 + lane < K && act) {
+                            const uint64_t nsk = a.lcg_a[k0 + lane] * ns0 + a.lcg_c[k0 + lane];
+                            int32_t t = a.neg_table[mod48(nsk >> 16, tsize, inv_tsize)];
+                            if (t <= 0 || t >= a.V) t = (int32_t)mod64(nsk, vm1, inv_vm1) + 1;
+                            if (t != w1) mine = t;
+                        }
                     }
                     int32_t tg[SGNS_CH];
                     float4 vk[SGNS_CH][VPL];
 #pragma unroll
+                    for (int k = 0; k < SGNS_CH; k++) tg[k] = __shfl_sync(FULL, mine, k, G);
+#pragma unroll
                     for (int k = 0; k < SGNS_CH; k++) {
-                        tg[k] = __shfl_sync(FULL, mine, k, G);
                         const float4 *pk = reinterpret_cast<const float4 *>(a.syn1neg + (int64_t)(tg[k] < 0 ? 0 : tg[k]) * a.stride);
 #pragma unroll
-                        for (int v = 0; v < VPL; v++) {
-                            int q = lane + v * G;
-                            vk[k][v] = (tg[k] >= 0 && q < n4) ? __ldcg(pk + q) : zero4;
-                        }
+                        for (int v = 0; v < VPL; v++) vk[k][v] = __ldcg(pk + lane + v * G);
                     }
 #pragma unroll
                     for (int k = 0; k < SGNS_CH; k++) {
@@ -357,32 +360,26 @@ k_sgns_items(const sgns_args a) {
 #pragma unroll
                         for (int v = 0; v < VPL; v++) dot += dot4(v0[v], vk[k][v]);
                         dot = group_sum<G>(dot, FULL);
-                        float g;
-                        if (sgns_g(dot, 0.f, alpha, s_exp, E, idx_scale, g) && tg[k] >= 0) {
+                        float g = 0.f;
+                        const bool upd = sgns_g(dot, 0.f, alpha, s_exp, E, idx_scale, g) && tg[k] >= 0;
+                        if (!upd) g = 0.f;
+#pragma unroll
+                        for (int v = 0; v < VPL; v++) axpy4(neu[v], g, vk[k][v]);
+                        if (upd) {
                             float4 *pk = reinterpret_cast<float4 *>(a.syn1neg + (int64_t)tg[k] * a.stride);
 #pragma unroll
-                            for (int v = 0; v < VPL; v++) {
-                                int q = lane + v * G;
-                                axpy4(neu[v], g, vk[k][v]);
-                                if (q < n4) red_add4(pk + q, scale4(g, v0[v]));
-                            }
+                            for (int v = 0; v < VPL; v++) red_add4(pk + lane + v * G, scale4(g, v0[v]));
                         }
                     }
                 }
                 if (act) {
 #pragma unroll
-                    for (int v = 0; v < VPL; v++) {
-                        int q = lane + v * G;
-                        if (q < n4) red_add4(p0 + q, neu[v]);
-                    }
+                    for (int v = 0; v < VPL; v++) red_add4(p0 + lane + v * G, neu[v]);
                 }
             }
             if (valid) {
 #pragma unroll
-                for (int v = 0; v < VPL; v++) {
-                    int q = lane + v * G;
-                    if (q < n4) red_add4(pw + q, d1[v]);
-                }
+                for (int v = 0; v < VPL; v++) red_add4(pw + lane + v * G, d1[v]);
             }
         }
     }
@@ -461,9 +458,13 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         Lmax = std::max(Lmax, corpora[i]->L);
         n_sent += corpora[i]->n;
     }
-    int32_t stride = (p->dim + 3) & ~3;
+    // rows are zero-padded to the item kernel's group width: 8 / 16 / 32 lanes x (1, 2 or 4) float4 slots
+    int32_t n4 = (p->dim + 3) / 4;
+    if (n4 > 128) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: dim must be <= 512");
+    n4 = n4 <= 8 ? 8 : (n4 <= 16 ? 16 : (n4 <= 32 ? 32 : (n4 <= 64 ? 64 : 128)));
+    const int32_t stride = n4 * 4;
     sgns_variant var;
-    if (!pick_variant(stride / 4, &var)) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: dim must be <= 512");
+    if (!pick_variant(n4, &var)) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: dim must be <= 512");
     DGE_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
 
