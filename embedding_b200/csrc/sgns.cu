@@ -277,10 +277,15 @@ k_sgns_items(const sgns_args a) {
     const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const int K = a.V >= 2 ? a.negative : 0;
-    // Rows are zero-padded to a multiple of G float4 slots (stride = 4*G*VPL floats), so every lane owns VPL
-    // slots of every row and no loaded value ever needs masking: invalid work is cancelled through g = 0.
-    // (A predicated or masked load makes ptxas consume each load before issuing the next; plain back-to-back
-    // loads keep K+1 rows in flight per lane.)
+    // Lane slots: slot q = lane + v*G holds floats 4q..4q+3 of a row.  A lane without a slot re-reads slot 0 (same
+    // sector, no extra traffic) and its dot-product term is dropped; invalid work is cancelled through g = 0.
+    // Loaded values are never masked or predicated: that makes ptxas consume each load before issuing the next,
+    // whereas plain back-to-back loads keep K+1 rows in flight per lane.
+    const int n4 = a.stride >> 2;
+    int slot[VPL];
+    bool live[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; v++) { live[v] = lane + v * G < n4; slot[v] = live[v] ? lane + v * G : 0; }
     unsigned long long pairs = 0;
     for (int ep = 0; ep < a.epochs; ep++) {
         for (int64_t base = warp_id * GPW; base < n_items; base += a.n_groups) { // warp-uniform trip count
@@ -299,7 +304,7 @@ k_sgns_items(const sgns_args a) {
             float4 *pw = reinterpret_cast<float4 *>(a.syn1neg + (int64_t)(valid ? w1 : 0) * a.stride);
             float4 cur[VPL], d1[VPL]; // current value and accumulated delta of syn1neg[w1]
 #pragma unroll
-            for (int v = 0; v < VPL; v++) { cur[v] = __ldcg(pw + lane + v * G); d1[v] = zero4; }
+            for (int v = 0; v < VPL; v++) { cur[v] = __ldcg(pw + slot[v]); d1[v] = zero4; }
             for (int c = 0; c < a.Lmax; c++) {
                 const int32_t last = a.wtok[(int64_t)c * N + s];
                 const bool act = valid && c >= lo && c <= hi && c != i && last >= 0 && last != w1;
@@ -309,7 +314,7 @@ k_sgns_items(const sgns_args a) {
                 float4 *p0 = reinterpret_cast<float4 *>(a.syn0 + (int64_t)(act ? last : 0) * a.stride);
                 float4 v0[VPL], neu[VPL];
 #pragma unroll
-                for (int v = 0; v < VPL; v++) { v0[v] = __ldcg(p0 + lane + v * G); neu[v] = zero4; }
+                for (int v = 0; v < VPL; v++) { v0[v] = __ldcg(p0 + slot[v]); neu[v] = zero4; }
                 // negatives of the first chunk: lane k draws negative k (the LCG is affine: state k+1 = A_k*ns0 + C_k)
                 int32_t mine = -1;
                 if (lane < SGNS_CH && lane < K && act) {
@@ -321,7 +326,7 @@ k_sgns_items(const sgns_args a) {
                 { // positive target: the item's private, always-current copy of syn1neg[w1]
                     float dot = 0.f;
 #pragma unroll
-                    for (int v = 0; v < VPL; v++) dot += dot4(v0[v], cur[v]);
+                    for (int v = 0; v < VPL; v++) dot += live[v] ? dot4(v0[v], cur[v]) : 0.f;
                     dot = group_sum<G>(dot, FULL);
                     float g = 0.f;
                     if (!(sgns_g(dot, 1.f, alpha, s_exp, E, idx_scale, g) && act)) g = 0.f;
@@ -352,13 +357,13 @@ k_sgns_items(const sgns_args a) {
                     for (int k = 0; k < SGNS_CH; k++) {
                         const float4 *pk = reinterpret_cast<const float4 *>(a.syn1neg + (int64_t)(tg[k] < 0 ? 0 : tg[k]) * a.stride);
 #pragma unroll
-                        for (int v = 0; v < VPL; v++) vk[k][v] = __ldcg(pk + lane + v * G);
+                        for (int v = 0; v < VPL; v++) vk[k][v] = __ldcg(pk + slot[v]);
                     }
 #pragma unroll
                     for (int k = 0; k < SGNS_CH; k++) {
                         float dot = 0.f;
 #pragma unroll
-                        for (int v = 0; v < VPL; v++) dot += dot4(v0[v], vk[k][v]);
+                        for (int v = 0; v < VPL; v++) dot += live[v] ? dot4(v0[v], vk[k][v]) : 0.f;
                         dot = group_sum<G>(dot, FULL);
                         float g = 0.f;
                         const bool upd = sgns_g(dot, 0.f, alpha, s_exp, E, idx_scale, g) && tg[k] >= 0;
@@ -368,18 +373,21 @@ k_sgns_items(const sgns_args a) {
                         if (upd) {
                             float4 *pk = reinterpret_cast<float4 *>(a.syn1neg + (int64_t)tg[k] * a.stride);
 #pragma unroll
-                            for (int v = 0; v < VPL; v++) red_add4(pk + lane + v * G, scale4(g, v0[v]));
+                            for (int v = 0; v < VPL; v++)
+                                if (live[v]) red_add4(pk + slot[v], scale4(g, v0[v]));
                         }
                     }
                 }
                 if (act) {
 #pragma unroll
-                    for (int v = 0; v < VPL; v++) red_add4(p0 + lane + v * G, neu[v]);
+                    for (int v = 0; v < VPL; v++)
+                        if (live[v]) red_add4(p0 + slot[v], neu[v]);
                 }
             }
             if (valid) {
 #pragma unroll
-                for (int v = 0; v < VPL; v++) red_add4(pw + lane + v * G, d1[v]);
+                for (int v = 0; v < VPL; v++)
+                    if (live[v]) red_add4(pw + slot[v], d1[v]);
             }
         }
     }
@@ -458,10 +466,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         Lmax = std::max(Lmax, corpora[i]->L);
         n_sent += corpora[i]->n;
     }
-    // rows are zero-padded to the item kernel's group width: 8 / 16 / 32 lanes x (1, 2 or 4) float4 slots
-    int32_t n4 = (p->dim + 3) / 4;
-    if (n4 > 128) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: dim must be <= 512");
-    n4 = n4 <= 8 ? 8 : (n4 <= 16 ? 16 : (n4 <= 32 ? 32 : (n4 <= 64 ? 64 : 128)));
+    const int32_t n4 = (p->dim + 3) / 4;   // rows are zero-padded to whole float4 slots
     const int32_t stride = n4 * 4;
     sgns_variant var;
     if (!pick_variant(n4, &var)) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: dim must be <= 512");
