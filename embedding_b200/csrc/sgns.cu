@@ -394,6 +394,159 @@ k_sgns_items(const sgns_args a) {
     if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Kernel B, software-pipelined (rows of up to 32 float4 slots, one slot per lane).  Same work decomposition and
+// arithmetic as k_sgns_items; the three dependent L2 round trips of a pair (token -> negative-table entry ->
+// rows) are taken off the critical path:
+//   * the item's sentence is staged in shared memory once;
+//   * iteration c issues the negative-table lookups of pair c+2, the row loads of pair c+1 (whose table entries
+//     were requested one iteration earlier) and only then computes pair c, whose rows were requested one
+//     iteration earlier.
+// With the bounded number of items in flight that the small-vocabulary configs allow, this is what keeps the
+// lanes busy: the kernel becomes issue / L2-reduction bound instead of L2-latency bound.
+template <int G>
+__global__ void __launch_bounds__(128)
+k_sgns_items_pipe(const sgns_args a) {
+    static_assert(G >= 8, "one negative per lane");
+    extern __shared__ int32_t smem[];
+    float *s_exp = reinterpret_cast<float *>(smem);
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int GPW = 32 / G;
+    const int lane = threadIdx.x % G;
+    const int gw = (threadIdx.x & 31) / G;
+    int32_t *mytok = smem + a.exp_table_size + (threadIdx.x / G) * a.Lmax;
+    for (int i = threadIdx.x; i < a.exp_table_size; i += blockDim.x) s_exp[i] = a.exp_table[i];
+    __syncthreads();
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int E = a.exp_table_size;
+    const float idx_scale = (float)E / SGNS_MAX_EXP / 2.0f;
+    const int win = a.window;
+    const int64_t N = a.n_sent;
+    const int Lmax = a.Lmax;
+    const int64_t n_items = N * Lmax;
+    const double inv_total = 1.0 / (double)((int64_t)a.epochs * N);
+    const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
+    const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int K = a.V >= 2 ? a.negative : 0;
+    const int n4 = a.stride >> 2;
+    const bool live = lane < n4;
+    const int slot = live ? lane : 0;
+    const bool drawer = lane < SGNS_CH && lane < K;
+    const uint64_t my_a = a.lcg_a[lane < SGNS_MAX_NEG ? lane : 0], my_c = a.lcg_c[lane < SGNS_MAX_NEG ? lane : 0];
+    unsigned long long pairs = 0;
+
+    struct stage_t { int32_t last; bool act; uint64_t ns0, nsk; int32_t traw; };
+    struct stage_r { int32_t last; bool act; uint64_t ns0; int32_t tg[SGNS_CH]; float4 row[SGNS_CH]; float4 v0; };
+
+    for (int ep = 0; ep < a.epochs; ep++) {
+        for (int64_t base = warp_id * GPW; base < n_items; base += a.n_groups) { // warp-uniform trip count
+            const int64_t item = base + gw;
+            bool valid = item < n_items;
+            const int64_t s = valid ? item / Lmax : 0;
+            const int i = valid ? (int)(item - s * Lmax) : 0;
+            __syncwarp();
+            for (int j = lane; j < Lmax; j += G) mytok[j] = a.wtok[(int64_t)j * N + s];
+            __syncwarp();
+            const int32_t w1 = mytok[i];
+            valid = valid && w1 >= 0;
+            if (!__any_sync(FULL, valid)) continue;
+            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * N + s) * inv_total);
+            if (alpha < a.min_lr) alpha = a.min_lr;
+            const uint64_t S = sgns_sentence_rng(a.seed, ep, s);
+            const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
+            const int lo = i - win + b, hi = i + win - b; // inclusive context range (SkipGram.skipGram)
+            float4 *pw = reinterpret_cast<float4 *>(a.syn1neg + (int64_t)(valid ? w1 : 0) * a.stride);
+            float4 cur = __ldcg(pw + slot), d1 = zero4; // current value and accumulated delta of syn1neg[w1]
+
+            auto stageT = [&](int c) { // which pair is position c, and request its negatives' table entries
+                stage_t t;
+                t.last = c < Lmax ? mytok[c] : -1;
+                t.act = valid && c >= lo && c <= hi && c != i && t.last >= 0 && t.last != w1;
+                t.ns0 = sgns_pair_rng(S, i, c);
+                t.nsk = my_a * t.ns0 + my_c; // lane k draws negative k: the LCG is affine
+                t.traw = a.neg_table[(drawer && t.act) ? mod48(t.nsk >> 16, tsize, inv_tsize) : 0];
+                return t;
+            };
+            auto stageR = [&](const stage_t &t) { // resolve the negatives and request all rows of the pair
+                stage_r r;
+                r.last = t.last; r.act = t.act; r.ns0 = t.ns0;
+                int32_t tt = t.traw;
+                if (tt <= 0 || tt >= a.V) tt = (int32_t)mod64(t.nsk, vm1, inv_vm1) + 1;
+                const int32_t mine = (drawer && t.act && tt != w1) ? tt : -1;
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) r.tg[k] = __shfl_sync(FULL, mine, k, G);
+                r.v0 = __ldcg(reinterpret_cast<const float4 *>(a.syn0 + (int64_t)(t.act ? t.last : 0) * a.stride) + slot);
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++)
+                    r.row[k] = __ldcg(reinterpret_cast<const float4 *>(a.syn1neg + (int64_t)(r.tg[k] < 0 ? 0 : r.tg[k]) * a.stride) + slot);
+                return r;
+            };
+
+            stage_t t1 = stageT(0);
+            stage_r r0 = stageR(t1);
+            t1 = stageT(1);
+            for (int c = 0; c < Lmax; c++) {
+                const stage_r rn = stageR(t1); // pair c+1
+                t1 = stageT(c + 2);            // pair c+2
+                if (__any_sync(FULL, r0.act)) { // ---- compute pair c
+                    pairs += r0.act;
+                    const float4 v0 = r0.v0;
+                    float4 neu = zero4;
+                    {
+                        float dot = group_sum<G>(live ? dot4(v0, cur) : 0.f, FULL);
+                        float g = 0.f;
+                        if (!(sgns_g(dot, 1.f, alpha, s_exp, E, idx_scale, g) && r0.act)) g = 0.f;
+                        axpy4(neu, g, cur);
+                        axpy4(d1, g, v0);
+                        axpy4(cur, g, v0);
+                    }
+#pragma unroll
+                    for (int k = 0; k < SGNS_CH; k++) {
+                        float dot = group_sum<G>(live ? dot4(v0, r0.row[k]) : 0.f, FULL);
+                        float g = 0.f;
+                        const bool upd = sgns_g(dot, 0.f, alpha, s_exp, E, idx_scale, g) && r0.tg[k] >= 0;
+                        if (!upd) g = 0.f;
+                        axpy4(neu, g, r0.row[k]);
+                        if (upd && live)
+                            red_add4(reinterpret_cast<float4 *>(a.syn1neg + (int64_t)r0.tg[k] * a.stride) + slot, scale4(g, v0));
+                    }
+                    for (int k0 = SGNS_CH; k0 < K; k0 += SGNS_CH) { // negative > 5: further chunks, not pipelined
+                        int32_t mine = -1;
+                        if (lane < SGNS_CH && k0 + lane < K && r0.act) {
+                            const uint64_t nsk = a.lcg_a[k0 + lane] * r0.ns0 + a.lcg_c[k0 + lane];
+                            int32_t t = a.neg_table[mod48(nsk >> 16, tsize, inv_tsize)];
+                            if (t <= 0 || t >= a.V) t = (int32_t)mod64(nsk, vm1, inv_vm1) + 1;
+                            if (t != w1) mine = t;
+                        }
+                        int32_t tg[SGNS_CH];
+                        float4 vk[SGNS_CH];
+#pragma unroll
+                        for (int k = 0; k < SGNS_CH; k++) tg[k] = __shfl_sync(FULL, mine, k, G);
+#pragma unroll
+                        for (int k = 0; k < SGNS_CH; k++)
+                            vk[k] = __ldcg(reinterpret_cast<const float4 *>(a.syn1neg + (int64_t)(tg[k] < 0 ? 0 : tg[k]) * a.stride) + slot);
+#pragma unroll
+                        for (int k = 0; k < SGNS_CH; k++) {
+                            float dot = group_sum<G>(live ? dot4(v0, vk[k]) : 0.f, FULL);
+                            float g = 0.f;
+                            const bool upd = sgns_g(dot, 0.f, alpha, s_exp, E, idx_scale, g) && tg[k] >= 0;
+                            if (!upd) g = 0.f;
+                            axpy4(neu, g, vk[k]);
+                            if (upd && live)
+                                red_add4(reinterpret_cast<float4 *>(a.syn1neg + (int64_t)tg[k] * a.stride) + slot, scale4(g, v0));
+                        }
+                    }
+                    if (r0.act && live) red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)r0.last * a.stride) + slot, neu);
+                }
+                r0 = rn;
+            }
+            if (valid && live) red_add4(pw + slot, d1);
+        }
+    }
+    if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
+}
+
 typedef void (*sgns_kernel_t)(const sgns_args);
 struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq, items; };
 
@@ -419,9 +572,9 @@ static bool pick_variant(int n4, sgns_variant *out) {
         default: seq = k_sgns_seq<32, 4>; Gs = 32; Vs = 4; break;
     }
     int Gi, Vi = 1;
-    if (n4 <= 8) { Gi = 8; items = k_sgns_items<8, 1>; }
-    else if (n4 <= 16) { Gi = 16; items = k_sgns_items<16, 1>; }
-    else if (n4 <= 32) { Gi = 32; items = k_sgns_items<32, 1>; }
+    if (n4 <= 8) { Gi = 8; items = k_sgns_items_pipe<8>; }
+    else if (n4 <= 16) { Gi = 16; items = k_sgns_items_pipe<16>; }
+    else if (n4 <= 32) { Gi = 32; items = k_sgns_items_pipe<32>; }
     else if (n4 <= 64) { Gi = 32; Vi = 2; items = k_sgns_items<32, 2>; }
     else { Gi = 32; Vi = 4; items = k_sgns_items<32, 4>; }
     out->G_seq = Gs; out->VPL_seq = Vs; out->seq = seq;
@@ -594,7 +747,11 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         }
         int threads = 128;
         int gpb = threads / G;
-        size_t smem = sizeof(float) * (size_t)p->exp_table_size;
+        // dynamic shared memory: the sigmoid table, plus (pipelined item kernel) one staged sentence per group
+        auto smem_for = [&](int thr) {
+            return sizeof(float) * (size_t)p->exp_table_size + (sequential ? 0 : sizeof(int32_t) * (size_t)(thr / G) * (size_t)Lmax);
+        };
+        size_t smem = smem_for(threads);
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
@@ -612,6 +769,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         a.n_groups = (int64_t)blocks * gpb;
         ctx->phase_ms["sgns_groups"] = (float)a.n_groups;
         dge_phase_timer t_sgns(ctx, "sgns");
+        smem = smem_for(threads);
         fn<<<blocks, threads, smem, st>>>(a);
         ctx->launches++;
         t_sgns.stop();
