@@ -15,6 +15,7 @@
 #include "dge_internal.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #define SGNS_MAX_CORPORA 4
 #define SGNS_MAX_NEG 32
@@ -37,6 +38,7 @@ struct sgns_args {
     unsigned long long *pairs;
     int64_t n_groups;
     uint64_t lcg_a[SGNS_MAX_NEG], lcg_c[SGNS_MAX_NEG]; // (k+1)-step jump of the negative-sampling LCG
+    int32_t dbg;
 };
 
 __host__ __device__ static inline uint64_t mix64(uint64_t z) {
@@ -117,6 +119,16 @@ __device__ __forceinline__ float4 scale4(float g, const float4 &x) { return make
 // 128-bit reduction at L2: no lost update, no return value
 __device__ __forceinline__ void red_add4(float4 *p, const float4 &v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// Predicated 128-bit L2 load: lanes with pred == false issue NO request and keep zeros.  Written as one PTX
+// statement so that no "else" move depends on the load (which would make ptxas wait for each load before
+// issuing the next); consecutive calls stay back to back and keep K+1 rows in flight per lane.
+__device__ __forceinline__ float4 ldcg4_if(const float4 *p, bool pred) {
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+                 : "+f"(r.x), "+f"(r.y), "+f"(r.z), "+f"(r.w)
+                 : "l"(p), "r"((int)pred));
+    return r;
 }
 // gradient scale of one (input, target) dot product: libnd4j NegativeSampling aggregate with the expTable sigmoid
 __device__ __forceinline__ bool sgns_g(float dot, float label, float alpha, const float *s_exp, int E, float idx_scale, float &g) {
@@ -457,7 +469,7 @@ k_sgns_items_pipe(const sgns_args a) {
             const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
             const int lo = i - win + b, hi = i + win - b; // inclusive context range (SkipGram.skipGram)
             float4 *pw = reinterpret_cast<float4 *>(a.syn1neg + (int64_t)(valid ? w1 : 0) * a.stride);
-            float4 cur = __ldcg(pw + slot), d1 = zero4; // current value and accumulated delta of syn1neg[w1]
+            float4 cur = ldcg4_if(pw + slot, valid && live), d1 = zero4; // current value and accumulated delta of syn1neg[w1]
 
             auto stageT = [&](int c) { // which pair is position c, and request its negatives' table entries
                 stage_t t;
@@ -465,7 +477,8 @@ k_sgns_items_pipe(const sgns_args a) {
                 t.act = valid && c >= lo && c <= hi && c != i && t.last >= 0 && t.last != w1;
                 t.ns0 = sgns_pair_rng(S, i, c);
                 t.nsk = my_a * t.ns0 + my_c; // lane k draws negative k: the LCG is affine
-                t.traw = a.neg_table[(drawer && t.act) ? mod48(t.nsk >> 16, tsize, inv_tsize) : 0];
+                t.traw = 1; // a valid entry for lanes that draw nothing
+                if (drawer && t.act) t.traw = a.neg_table[mod48(t.nsk >> 16, tsize, inv_tsize)];
                 return t;
             };
             auto stageR = [&](const stage_t &t) { // resolve the negatives and request all rows of the pair
@@ -476,10 +489,11 @@ k_sgns_items_pipe(const sgns_args a) {
                 const int32_t mine = (drawer && t.act && tt != w1) ? tt : -1;
 #pragma unroll
                 for (int k = 0; k < SGNS_CH; k++) r.tg[k] = __shfl_sync(FULL, mine, k, G);
-                r.v0 = __ldcg(reinterpret_cast<const float4 *>(a.syn0 + (int64_t)(t.act ? t.last : 0) * a.stride) + slot);
+                r.v0 = ldcg4_if(reinterpret_cast<const float4 *>(a.syn0 + (int64_t)(t.act ? t.last : 0) * a.stride) + slot, t.act && live);
 #pragma unroll
                 for (int k = 0; k < SGNS_CH; k++)
-                    r.row[k] = __ldcg(reinterpret_cast<const float4 *>(a.syn1neg + (int64_t)(r.tg[k] < 0 ? 0 : r.tg[k]) * a.stride) + slot);
+                    r.row[k] = ldcg4_if(reinterpret_cast<const float4 *>(a.syn1neg + (int64_t)(r.tg[k] < 0 ? 0 : r.tg[k]) * a.stride) + slot,
+                                        r.tg[k] >= 0 && live);
                 return r;
             };
 
@@ -494,7 +508,7 @@ k_sgns_items_pipe(const sgns_args a) {
                     const float4 v0 = r0.v0;
                     float4 neu = zero4;
                     {
-                        float dot = group_sum<G>(live ? dot4(v0, cur) : 0.f, FULL);
+                        float dot = group_sum<G>(dot4(v0, cur), FULL);
                         float g = 0.f;
                         if (!(sgns_g(dot, 1.f, alpha, s_exp, E, idx_scale, g) && r0.act)) g = 0.f;
                         axpy4(neu, g, cur);
@@ -503,12 +517,12 @@ k_sgns_items_pipe(const sgns_args a) {
                     }
 #pragma unroll
                     for (int k = 0; k < SGNS_CH; k++) {
-                        float dot = group_sum<G>(live ? dot4(v0, r0.row[k]) : 0.f, FULL);
+                        float dot = group_sum<G>(dot4(v0, r0.row[k]), FULL);
                         float g = 0.f;
                         const bool upd = sgns_g(dot, 0.f, alpha, s_exp, E, idx_scale, g) && r0.tg[k] >= 0;
                         if (!upd) g = 0.f;
                         axpy4(neu, g, r0.row[k]);
-                        if (upd && live)
+                        if (upd && live && !(a.dbg & 1))
                             red_add4(reinterpret_cast<float4 *>(a.syn1neg + (int64_t)r0.tg[k] * a.stride) + slot, scale4(g, v0));
                     }
                     for (int k0 = SGNS_CH; k0 < K; k0 += SGNS_CH) { // negative > 5: further chunks, not pipelined
@@ -525,23 +539,23 @@ k_sgns_items_pipe(const sgns_args a) {
                         for (int k = 0; k < SGNS_CH; k++) tg[k] = __shfl_sync(FULL, mine, k, G);
 #pragma unroll
                         for (int k = 0; k < SGNS_CH; k++)
-                            vk[k] = __ldcg(reinterpret_cast<const float4 *>(a.syn1neg + (int64_t)(tg[k] < 0 ? 0 : tg[k]) * a.stride) + slot);
+                            vk[k] = ldcg4_if(reinterpret_cast<const float4 *>(a.syn1neg + (int64_t)(tg[k] < 0 ? 0 : tg[k]) * a.stride) + slot, tg[k] >= 0 && live);
 #pragma unroll
                         for (int k = 0; k < SGNS_CH; k++) {
-                            float dot = group_sum<G>(live ? dot4(v0, vk[k]) : 0.f, FULL);
+                            float dot = group_sum<G>(dot4(v0, vk[k]), FULL);
                             float g = 0.f;
                             const bool upd = sgns_g(dot, 0.f, alpha, s_exp, E, idx_scale, g) && tg[k] >= 0;
                             if (!upd) g = 0.f;
                             axpy4(neu, g, vk[k]);
-                            if (upd && live)
+                            if (upd && live && !(a.dbg & 1))
                                 red_add4(reinterpret_cast<float4 *>(a.syn1neg + (int64_t)tg[k] * a.stride) + slot, scale4(g, v0));
                         }
                     }
-                    if (r0.act && live) red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)r0.last * a.stride) + slot, neu);
+                    if (r0.act && live && !(a.dbg & 1)) red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)r0.last * a.stride) + slot, neu);
                 }
                 r0 = rn;
             }
-            if (valid && live) red_add4(pw + slot, d1);
+            if (valid && live && !(a.dbg & 1)) red_add4(pw + slot, d1);
         }
     }
     if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
@@ -730,6 +744,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         a.V = V; a.dim = p->dim; a.stride = stride; a.window = p->window; a.negative = p->negative; a.epochs = p->epochs;
         a.neg_table_size = p->neg_table_size; a.exp_table_size = p->exp_table_size; a.Lmax = Lmax;
         a.lr = p->lr; a.min_lr = p->min_lr; a.seed = p->seed; a.pairs = d_pairs;
+        a.dbg = getenv("DGE_SGNS_DEBUG") ? atoi(getenv("DGE_SGNS_DEBUG")) : 0;
 
         // ---- schedule
         //  concurrency 1            : kernel A, one group: the oracle's sequential order (parity tests)
