@@ -80,9 +80,9 @@ def main():
                dict(wall_s=wall, groups=ctx.phase_ms("sgns_groups")))
 
     gpu("gpu_items_auto")
-    for c in (16, 64, 256, 1024, 4096, 16384, 65536):
+    for c in (64, 256, 512, 1024, 2048, 4096, 16384):
         gpu("gpu_items_c%d" % c, concurrency=c)
-    for c in (8, 64, 1024, 0):
+    for c in (1024, 0):
         gpu("gpu_sentence_c%d" % c, concurrency=c, schedule=abi.SCHEDULE_SENTENCE)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "quality_%s.json" % level), "w") as f:
