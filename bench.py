@@ -304,7 +304,8 @@ def run_gpu_arm(args, w, rank, world, dist):
     G.free()
     if S is not None:
         S.free()
-    for it in range(args.warmup + args.steps):
+    d2h_sgns = 0
+    for it in range(0 if args.no_e2e else args.warmup + args.steps):
         if it == args.warmup:
             sync_all()
         t0 = time.perf_counter()
@@ -338,6 +339,8 @@ def run_gpu_arm(args, w, rank, world, dist):
             S.free()
     sync_all()
     per_step_steps = sum(walk_steps) / len(walk_steps)        # same expected count per step
+    if args.no_e2e:
+        e_walk_ms, e_sg_ms, e_pairs = [float("nan")], [float("nan")], [0]
     e_t_walk = max_over_ranks(sum(e_walk_ms) / 1e3)
     e_t_sgns = max_over_ranks(sum(e_sg_ms) / 1e3)
     e_tot_steps = sum_over_ranks(per_step_steps * args.steps)
@@ -405,6 +408,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="tract24")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: device-resident loop only")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
