@@ -1,0 +1,43 @@
+package embedding;
+
+/**
+ * JNI declarations over libdge.so (include/dge.h).  Source only: this image has no JDK (SURVEY F6), so the
+ * class is not compiled or tested here; tests drive the same C ABI through ctypes (embedding_b200/abi.py).
+ *
+ * Handles are opaque native pointers carried as long.  Every array argument is a plain Java array; the glue
+ * (java/jni/dge_jni.c) pins it with Get/ReleasePrimitiveArrayCritical for the duration of the call only, so no
+ * Java object is retained across calls (SURVEY 8(b) "Ownership").  A non-zero status becomes a RuntimeException
+ * carrying dge_last_error().
+ */
+public final class DgeNative {
+    static { System.loadLibrary("dge_jni"); }   // libdge_jni.so links against libdge.so
+
+    private DgeNative() {}
+
+    public static native long create(int device);
+    public static native void destroy(long ctx);
+
+    /** LayeredGraph.addEdge / addSourceVertex / initiateAliasTables -> dge_graph_build. */
+    public static native long graphBuild(long ctx, int nVertices, int[] src, int[] dst, double[] w, int[] sources,
+                                         double[] outDegreeOrNull, double[] sourceWeightSumOrNull);
+    /** Vertex.probTable / aliasTable / outDegree and LayeredGraph.probTable / aliasTable -> dge_graph_tables. */
+    public static native void graphTables(long graph, long[] rowPtr, int[] col, double[] w, double[] prob, int[] alias,
+                                          double[] outDegree, double[] srcProb, int[] srcAlias, double[] sourceWeightSum);
+    /** Vertex.sampleNextVertex(double x) -> dge_graph_sample_next. */
+    public static native void graphSampleNext(long graph, int[] v, double[] x, int sampler, int[] out);
+    public static native void graphFree(long graph);
+
+    /** the loop of CrossTimeGraph.sampleSequenceHelper / SpatialGraph.outputSampleSequence -> dge_walk. */
+    public static native long walk(long graph, long nWalks, long firstWalkId, int numLayer, long seed, int sampler);
+    public static native void corpusTokens(long corpus, int[] tokensOut);
+    public static native void corpusRelabel(long corpus, int[] idMap, int newNIds, int positionStride);
+    public static native void corpusWriteSeq(long corpus, int[] labelLayer, int[] labelRegion, boolean positionPrefix,
+                                             String path, boolean append);
+    public static native void corpusFree(long corpus);
+
+    /** Word2Vec.Builder()...build().fit() -> dge_sgns_train; writeWordVectors -> dge_model_write_vec. */
+    public static native long sgnsTrain(long ctx, long[] corpora, int dim, int window, int negative, int minCount,
+                                        int epochs, float lr, float minLr, long seed);
+    public static native void modelWriteVec(long model, int[] labelLayer, int[] labelRegion, String path);
+    public static native void modelFree(long model);
+}

@@ -1,0 +1,70 @@
+/*
+ * dge_jni.c -- JNI glue between java/embedding/DgeNative.java and libdge.so (include/dge.h).
+ * Source only: jni.h does not exist in the build image; compiled by the maintainer with
+ *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -Iinclude java/jni/dge_jni.c \
+ *       -Lembedding_b200 -ldge -o libdge_jni.so
+ * Only the graph / walk / train entry points are shown in full; the remaining ones follow the same pattern.
+ */
+#if defined(__has_include)
+#if __has_include(<jni.h>)
+#include <jni.h>
+#include "dge.h"
+
+static void throw_dge(JNIEnv *env, dge_ctx *ctx) {
+    jclass cls = (*env)->FindClass(env, "java/lang/RuntimeException");
+    (*env)->ThrowNew(env, cls, dge_last_error(ctx));
+}
+
+JNIEXPORT jlong JNICALL Java_embedding_DgeNative_create(JNIEnv *env, jclass c, jint device) {
+    dge_ctx *ctx = NULL;
+    if (dge_create(device, &ctx) != DGE_OK) { throw_dge(env, NULL); return 0; }
+    return (jlong)(intptr_t)ctx;
+}
+
+JNIEXPORT jlong JNICALL Java_embedding_DgeNative_graphBuild(JNIEnv *env, jclass c, jlong jctx, jint nv, jintArray jsrc,
+        jintArray jdst, jdoubleArray jw, jintArray jsources, jdoubleArray jod, jdoubleArray jsws) {
+    dge_ctx *ctx = (dge_ctx *)(intptr_t)jctx;
+    jsize ne = (*env)->GetArrayLength(env, jsrc), ns = (*env)->GetArrayLength(env, jsources);
+    jint *src = (*env)->GetPrimitiveArrayCritical(env, jsrc, NULL);
+    jint *dst = (*env)->GetPrimitiveArrayCritical(env, jdst, NULL);
+    jdouble *w = (*env)->GetPrimitiveArrayCritical(env, jw, NULL);
+    jint *sources = (*env)->GetPrimitiveArrayCritical(env, jsources, NULL);
+    jdouble *od = jod ? (*env)->GetPrimitiveArrayCritical(env, jod, NULL) : NULL;
+    jdouble *sws = jsws ? (*env)->GetPrimitiveArrayCritical(env, jsws, NULL) : NULL;
+    dge_graph *g = NULL;
+    int rc = dge_graph_build(ctx, nv, ne, (const int32_t *)src, (const int32_t *)dst, w, ns, (const int32_t *)sources, od, sws, &g);
+    if (sws) (*env)->ReleasePrimitiveArrayCritical(env, jsws, sws, JNI_ABORT);
+    if (od) (*env)->ReleasePrimitiveArrayCritical(env, jod, od, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, jsources, sources, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, jw, w, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, jdst, dst, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, jsrc, src, JNI_ABORT);
+    if (rc != DGE_OK) { throw_dge(env, ctx); return 0; }
+    return (jlong)(intptr_t)g;
+}
+
+JNIEXPORT jlong JNICALL Java_embedding_DgeNative_walk(JNIEnv *env, jclass c, jlong jg, jlong n, jlong first, jint L,
+        jlong seed, jint sampler) {
+    dge_corpus *corpus = NULL;
+    if (dge_walk((dge_graph *)(intptr_t)jg, n, first, L, (uint64_t)seed, sampler, &corpus) != DGE_OK) { throw_dge(env, NULL); return 0; }
+    return (jlong)(intptr_t)corpus;
+}
+
+JNIEXPORT jlong JNICALL Java_embedding_DgeNative_sgnsTrain(JNIEnv *env, jclass c, jlong jctx, jlongArray jcorp, jint dim,
+        jint window, jint negative, jint minCount, jint epochs, jfloat lr, jfloat minLr, jlong seed) {
+    dge_ctx *ctx = (dge_ctx *)(intptr_t)jctx;
+    jsize n = (*env)->GetArrayLength(env, jcorp);
+    jlong *h = (*env)->GetLongArrayElements(env, jcorp, NULL);
+    const dge_corpus *corp[4];
+    for (jsize i = 0; i < n && i < 4; i++) corp[i] = (const dge_corpus *)(intptr_t)h[i];
+    (*env)->ReleaseLongArrayElements(env, jcorp, h, JNI_ABORT);
+    dge_sgns_params p;
+    dge_sgns_default_params(&p);
+    p.dim = dim; p.window = window; p.negative = negative; p.min_count = minCount; p.epochs = epochs;
+    p.lr = lr; p.min_lr = minLr; p.seed = (uint64_t)seed;
+    dge_model *m = NULL;
+    if (dge_sgns_train(ctx, corp, n, &p, &m) != DGE_OK) { throw_dge(env, ctx); return 0; }
+    return (jlong)(intptr_t)m;
+}
+#endif
+#endif
