@@ -92,12 +92,12 @@ def make_workload(name, rank=0):
                       % (name, n, L, n_flow, n_spatial, dim, L))
     elif name == "synth100k":
         n_regions, L = 100_000, 24
-        gsyn = synth.powerlaw_flow_graph(n_regions, L=L, seed=100000 + rank)
+        gsyn = synth.powerlaw_flow_graph(n_regions, L=L, seed=100000)   # replicated on every rank
         w.update(L=L, dim=128, window=10, negative=5, n_regions=n_regions,
                  flow=dict(nv=gsyn["n_vertices"], src=gsyn["src"], dst=gsyn["dst"], w=gsyn["w"], sources=gsyn["sources"],
-                           n_walks=20_000_000, v_layer=gsyn["v_layer"], v_region=gsyn["v_region"], id_map=None),
+                           n_walks=4_000_000, v_layer=gsyn["v_layer"], v_region=gsyn["v_region"], id_map=None),
                  spatial=None, n_ids=gsyn["n_vertices"],
-                 desc="synth100k: 100K regions x 24 slices, %d edges, 20M walks x 24, D=128 window=10 K=5" % len(gsyn["src"]))
+                 desc="synth100k: 100K regions x 24 slices, %d edges, 4M walks x 24 per GPU, D=128 window=10 K=5" % len(gsyn["src"]))
     else:
         raise SystemExit("unknown workload %r" % name)
     return w
@@ -202,6 +202,11 @@ def run_gpu_arm(args, w, rank, world, dist):
     from embedding_b200 import abi
     local = int(os.environ.get("LOCAL_RANK", "0"))
     ctx = abi.Context(local)
+    data_parallel = dist is not None and w["name"].startswith("synth")
+    if data_parallel:      # stage 2 exchanges embedding deltas over NCCL only where the vocabulary is large
+        import torch
+        from embedding_b200 import parallel
+        parallel.init_comm(ctx, dist, torch.device("cuda", local))
     L, dim, neg = w["L"], w["dim"], w["negative"]
     f, sp = w["flow"], w["spatial"]
     peak, peak_src = measured_peak_gbs()
@@ -268,18 +273,19 @@ def run_gpu_arm(args, w, rank, world, dist):
             sync_all()
             clocks.start()
             launches0 = ctx.kernel_launches()
-        t0 = time.perf_counter()
+        # device time of each stage: CUDA events on the ctx stream (the stream every libdge kernel runs on)
+        ctx.timer_start()
         c1, c2, kms = walk(G, S, seed=1000 + it)
-        t1 = time.perf_counter()
+        ev_walk = ctx.timer_stop()
+        ctx.timer_start()
         corpora = relabel(c1, c2)
-        t2 = time.perf_counter()
         m = abi.Model.train(ctx, corpora, params)
-        t3 = time.perf_counter()
+        ev_sgns = ctx.timer_stop()
         if it >= args.warmup:
-            walk_ms.append((t1 - t0) * 1e3)
+            walk_ms.append(ev_walk)
             walk_kernel_ms.append(kms)
             walk_steps.append(sum(c.count_tokens() for c in corpora))
-            sg_ms.append((t3 - t2) * 1e3)
+            sg_ms.append(ev_sgns)
             sg_kernel_ms.append(ctx.phase_ms("sgns"))
             sg_pairs.append(m.pairs)
         for c in corpora:
@@ -379,7 +385,8 @@ def run_gpu_arm(args, w, rank, world, dist):
                                 note=resident_note),
                   cpu_baseline=cpu["walk"] if cpu else None),
         sgns=dict(value=tot_pairs / t_sgns, unit="pairs/s", ms_per_step=t_sgns / args.steps * 1e3, kernel="k_sgns_items",
-                  kernel_ms=sk_ms, groups_in_flight=ctx.phase_ms("sgns_groups"),
+                  kernel_ms=sk_ms, groups_in_flight=ctx.phase_ms("sgns_groups"), sync_rounds=ctx.phase_ms("sgns_rounds"),
+                  sync_ms=ctx.phase_ms("sgns_sync"),
                   e2e=dict(value=e_tot_pairs / e_t_sgns, unit="pairs/s", h2d_bytes_per_step=int(d2h_walk), d2h_bytes_per_step=int(d2h_sgns),
                            includes="dge_corpus_from_tokens from pinned host + dge_sgns_train + dge_model_vectors to host"),
                   roofline=dict(bound="hbm", achieved=sgns_ach, peak=peak, unit="GB/s", frac=sgns_ach / peak,
@@ -391,7 +398,9 @@ def run_gpu_arm(args, w, rank, world, dist):
                 warmup=args.warmup, ms_per_step=(t_walk + t_sgns) / args.steps * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f64 (alias tables, walk draws) / f32 (SGNS)", data="synthetic",
                 config=dict(workload=w["desc"], l2="inputs of a step (>= 1.5 GB of tokens) exceed the 126 MB L2; every step uses a new seed",
-                            parallelism="walk ids sharded by rank, no collective; SGNS replicas only" if world > 1 else "1 GPU"),
+                            parallelism=("1 GPU" if world == 1 else "walk ids sharded by rank, no collective; SGNS data-parallel, NCCL all-reduce of summed embedding deltas"
+                                         if data_parallel else "walk ids sharded by rank, no collective; SGNS replicas only"),
+                            timing="CUDA events on the library stream per stage (dge_timer_start/stop), max over ranks"),
                 e2e=stages["walk"]["e2e"], roofline=stages["walk"]["roofline"], cpu_baseline=stages["walk"]["cpu_baseline"],
                 clocks=clk, gpu_launches=int(launches), stages=stages,
                 dominant_kernel=dict(name="k_sgns_items", share_of_step_kernel_time=share),

@@ -5,6 +5,7 @@ GPU; `lib()` fails loudly if libdge.so has not been built, `Context()` fails lou
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -13,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libdge.so")
 
 SAMPLER_ALIAS, SAMPLER_CDF = 0, 1
 SCHEDULE_ITEMS, SCHEDULE_SENTENCE = 0, 1
+COMM_ID_BYTES = 128
 
 class DgeError(RuntimeError):
     def __init__(self, code, msg):
@@ -23,7 +25,7 @@ class DgeError(RuntimeError):
 class SgnsParams(C.Structure):
     _fields_ = [("dim", C.c_int32), ("window", C.c_int32), ("negative", C.c_int32), ("min_count", C.c_int32),
                 ("epochs", C.c_int32), ("neg_table_size", C.c_int32), ("exp_table_size", C.c_int32),
-                ("concurrency", C.c_int32), ("schedule", C.c_int32), ("lr", C.c_float), ("min_lr", C.c_float), ("seed", C.c_uint64)]
+                ("concurrency", C.c_int32), ("schedule", C.c_int32), ("sync_rounds", C.c_int32), ("lr", C.c_float), ("min_lr", C.c_float), ("seed", C.c_uint64)]
 
 
 _lib = None
@@ -76,13 +78,14 @@ def lib():
     L.dge_model_write_vec.argtypes = [vp, pi32, pi32, C.c_char_p]
     L.dge_model_free.argtypes = [vp]
     L.dge_model_free.restype = None
-    if hasattr(L, "dge_comm_init"):
-        L.dge_comm_unique_id.argtypes = [vp, C.c_char_p]
-        L.dge_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
-        L.dge_comm_destroy.argtypes = [vp]
-        L.dge_walk_shard.argtypes = [i64, C.c_int, C.c_int, pi64, pi64]
-        L.dge_model_allreduce_mean.argtypes = [vp, vp]
-        L.dge_sgns_train_dp.argtypes = [vp, P(vp), i32, P(SgnsParams), i32, P(vp)]
+    L.dge_timer_start.argtypes = [vp]
+    L.dge_timer_stop.argtypes = [vp, P(C.c_float)]
+    L.dge_comm_unique_id.argtypes = [vp, C.c_size_t]
+    L.dge_comm_init.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t]
+    L.dge_comm_shape.argtypes = [vp, P(C.c_int), P(C.c_int)]
+    L.dge_comm_destroy.argtypes = [vp]
+    L.dge_comm_destroy.restype = None
+    L.dge_comm_nccl_version.restype = C.c_int
     _lib = L
     return L
 
@@ -132,9 +135,16 @@ class Context:
             _check(rc, None)
         self._h = h
         self.device = int(device)
+        self._children = weakref.WeakSet()   # graphs / corpora / models: released before the ctx (dge.h: handles
+                                             # must be freed before dge_destroy)
+
+    def _adopt(self, child):
+        self._children.add(child)
 
     def close(self):
         if getattr(self, "_h", None):
+            for ch in list(self._children):
+                ch.free()
             lib().dge_destroy(self._h)
             self._h = None
 
@@ -148,6 +158,34 @@ class Context:
 
     def kernel_launches(self):
         return int(lib().dge_kernel_launches(self._h))
+
+    def timer_start(self):
+        _check(lib().dge_timer_start(self._h), self._h)
+
+    def timer_stop(self):
+        """ms between timer_start() and now, from CUDA events on the ctx stream."""
+        ms = C.c_float()
+        _check(lib().dge_timer_stop(self._h, C.byref(ms)), self._h)
+        return float(ms.value)
+
+    # ---- multi-GPU (one process per GPU): the host carries the opaque NCCL id from rank 0 to the others
+    @staticmethod
+    def comm_unique_id():
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        _check(lib().dge_comm_unique_id(C.cast(buf, C.c_void_p), COMM_ID_BYTES), None)
+        return buf.raw
+
+    def comm_init(self, rank, world, unique_id):
+        if len(unique_id) != COMM_ID_BYTES:
+            raise ValueError("unique_id must be %d bytes" % COMM_ID_BYTES)
+        buf = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        _check(lib().dge_comm_init(self._h, int(rank), int(world), C.cast(buf, C.c_void_p), COMM_ID_BYTES), self._h)
+        self.rank, self.world = int(rank), int(world)
+
+    def comm_shape(self):
+        r, w = C.c_int(), C.c_int()
+        _check(lib().dge_comm_shape(self._h, C.byref(r), C.byref(w)), self._h)
+        return r.value, w.value
 
 
 class Graph:
@@ -170,6 +208,7 @@ class Graph:
                                      _ptr(w, C.c_double), len(sources), _ptr(sources, C.c_int32),
                                      _ptr(od, C.c_double), _ptr(sws, C.c_double), C.byref(h)), ctx._h)
         self._h = h
+        ctx._adopt(self)
         self.nv, self.ne, self.ns = int(n_vertices), len(src), len(sources)
 
     def free(self):
@@ -215,6 +254,7 @@ class Corpus:
     def __init__(self, ctx, handle):
         self.ctx = ctx
         self._h = handle
+        ctx._adopt(self)
         n, L, ids = C.c_int64(), C.c_int32(), C.c_int32()
         _check(lib().dge_corpus_shape(handle, C.byref(n), C.byref(L), C.byref(ids)), ctx._h)
         self.n_walks, self.L, self.n_ids = n.value, L.value, ids.value
@@ -281,6 +321,7 @@ class Model:
     def __init__(self, ctx, handle):
         self.ctx = ctx
         self._h = handle
+        ctx._adopt(self)
         V, d, pairs = C.c_int32(), C.c_int32(), C.c_int64()
         _check(lib().dge_model_shape(handle, C.byref(V), C.byref(d), C.byref(pairs)), ctx._h)
         self.V, self.dim, self.pairs = V.value, d.value, pairs.value

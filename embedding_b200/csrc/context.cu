@@ -38,9 +38,16 @@ int dge_create(int device, dge_ctx **out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaEventCreate(&ctx->tev0) != cudaSuccess || cudaEventCreate(&ctx->tev1) != cudaSuccess) {
         delete ctx;
         return dge_fail(nullptr, DGE_E_CUDA, "dge_create: stream/event creation failed");
+    }
+    // stream-ordered allocator: keep freed blocks in the pool (no trim at synchronisation points)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     *out = ctx;
     return DGE_OK;
@@ -48,10 +55,14 @@ int dge_create(int device, dge_ctx **out) {
 
 void dge_destroy(dge_ctx *ctx) {
     if (!ctx) return;
+    dge_comm_destroy(ctx);
     cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->tev0) cudaEventDestroy(ctx->tev0);
+    if (ctx->tev1) cudaEventDestroy(ctx->tev1);
     delete ctx;
 }
 
@@ -75,5 +86,22 @@ int dge_phase_ms(const dge_ctx *ctx, const char *phase, float *ms) {
 }
 
 int64_t dge_kernel_launches(const dge_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int dge_timer_start(dge_ctx *ctx) {
+    if (!ctx) return DGE_E_INVALID;
+    DGE_CUDA(ctx, cudaSetDevice(ctx->device));
+    DGE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    DGE_CUDA(ctx, cudaEventRecord(ctx->tev0, ctx->stream));
+    return DGE_OK;
+}
+
+int dge_timer_stop(dge_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return DGE_E_INVALID;
+    DGE_CUDA(ctx, cudaSetDevice(ctx->device));
+    DGE_CUDA(ctx, cudaEventRecord(ctx->tev1, ctx->stream));
+    DGE_CUDA(ctx, cudaEventSynchronize(ctx->tev1));
+    DGE_CUDA(ctx, cudaEventElapsedTime(ms, ctx->tev0, ctx->tev1));
+    return DGE_OK;
+}
 
 } // extern "C"

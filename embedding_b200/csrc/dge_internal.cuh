@@ -13,7 +13,10 @@ struct dge_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // phase timers
+    cudaEvent_t tev0 = nullptr, tev1 = nullptr; // dge_timer_start / dge_timer_stop (bench.py's timed region)
+    void *comm = nullptr;                       // ncclComm_t when dge_comm_init was called (comm.cu)
+    int rank = 0, world = 1;
     std::string err;
     std::map<std::string, float> phase_ms;
     int64_t launches = 0;
@@ -70,6 +73,11 @@ struct dge_model {
     int32_t *id_of_word = nullptr;             // device [V]
 };
 
+// ---- multi-GPU (comm.cu); no-ops without a communicator
+int dge_comm_allreduce_sum_f32(dge_ctx *ctx, float *buf, size_t n);
+int dge_comm_allreduce_sum_u64(dge_ctx *ctx, unsigned long long *buf, size_t n);
+int dge_comm_allreduce_max_u64(dge_ctx *ctx, unsigned long long *buf, size_t n);
+
 // ---- error plumbing
 void dge_set_error(dge_ctx *ctx, const std::string &msg);
 int dge_fail(dge_ctx *ctx, int code, const std::string &msg);
@@ -101,9 +109,15 @@ struct dge_phase_timer {
     }
 };
 
+// Device memory comes from the device's stream-ordered pool on the ctx stream (context.cu sets the release
+// threshold to "never"): the multi-GB token / scratch buffers of one step are reused by the next step without a
+// round trip to the driver.  Frees are stream-ordered too, so they never synchronise the device.
 template <typename T>
-static inline cudaError_t dge_malloc(T **p, size_t n) {
-    return cudaMalloc((void **)p, (n ? n : 1) * sizeof(T));
+static inline cudaError_t dge_malloc(dge_ctx *ctx, T **p, size_t n) {
+    return cudaMallocAsync((void **)p, (n ? n : 1) * sizeof(T), ctx->stream);
+}
+static inline void dge_free(dge_ctx *ctx, void *p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
 }
 
 // ---- Philox4x32-10 (Salmon et al., SC'11).  Same stream definition as oracle/dge_oracle.c.

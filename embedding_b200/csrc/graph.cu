@@ -538,9 +538,11 @@ __global__ void k_big_sizes(const int64_t *__restrict__ row_ptr, const int32_t *
     if (i < n_big) k_out[i] = row_ptr[big_rows[i] + 1] - row_ptr[big_rows[i]];
 }
 
-struct dev_tmp { // device scratch freed on scope exit
+struct dev_tmp { // device scratch returned to the ctx pool on scope exit
+    dge_ctx *ctx;
     void *p = nullptr;
-    ~dev_tmp() { if (p) cudaFree(p); }
+    explicit dev_tmp(dge_ctx *c) : ctx(c) {}
+    ~dev_tmp() { if (p) dge_free(ctx, p); }
 };
 
 static int grid_for(int64_t n, int threads, int sm_count, int per_sm = 8) {
@@ -557,8 +559,8 @@ static int run_alias(dge_ctx *ctx, const int64_t *d_row_ptr, int32_t n_rows, int
     if (n_rows == 0 || n_entries == 0) return DGE_OK;
     int32_t *d_big = nullptr, *d_nbig = nullptr;
     int64_t max_big = n_entries / (ALIAS_SMALL_MAX + 1) + 1;
-    DGE_CUDA(ctx, dge_malloc(&d_big, (size_t)max_big));
-    DGE_CUDA(ctx, dge_malloc(&d_nbig, 1));
+    DGE_CUDA(ctx, dge_malloc(ctx, &d_big, (size_t)max_big));
+    DGE_CUDA(ctx, dge_malloc(ctx, &d_nbig, 1));
     DGE_CUDA(ctx, cudaMemsetAsync(d_nbig, 0, sizeof(int32_t), ctx->stream));
     int threads = 256;
     int64_t warps_needed = n_rows;
@@ -574,8 +576,8 @@ static int run_alias(dge_ctx *ctx, const int64_t *d_row_ptr, int32_t n_rows, int
         DGE_CUDA(ctx, cudaMemcpy(big.data(), d_big, sizeof(int32_t) * n_big, cudaMemcpyDeviceToHost));
         std::sort(big.begin(), big.end());
         // sizes of the big rows in one transfer
-        dev_tmp t_k;
-        DGE_CUDA(ctx, dge_malloc((int64_t **)&t_k.p, (size_t)n_big));
+        dev_tmp t_k(ctx);
+        DGE_CUDA(ctx, dge_malloc(ctx, (int64_t **)&t_k.p, (size_t)n_big));
         DGE_CUDA(ctx, cudaMemcpyAsync(d_big, big.data(), sizeof(int32_t) * n_big, cudaMemcpyHostToDevice, ctx->stream));
         k_big_sizes<<<(n_big + 255) / 256, 256, 0, ctx->stream>>>(d_row_ptr, d_big, n_big, (int64_t *)t_k.p);
         DGE_LAUNCH_CHECK(ctx);
@@ -592,27 +594,27 @@ static int run_alias(dge_ctx *ctx, const int64_t *d_row_ptr, int32_t n_rows, int
         if (rc == DGE_OK) {
             unsigned long long *d_scratch = nullptr;
             int64_t *d_off = nullptr;
-            DGE_CUDA(ctx, dge_malloc(&d_scratch, (size_t)total));
-            DGE_CUDA(ctx, dge_malloc(&d_off, (size_t)n_big));
+            DGE_CUDA(ctx, dge_malloc(ctx, &d_scratch, (size_t)total));
+            DGE_CUDA(ctx, dge_malloc(ctx, &d_off, (size_t)n_big));
             DGE_CUDA(ctx, cudaMemsetAsync(d_scratch, 0, sizeof(unsigned long long) * (size_t)total, ctx->stream));
             DGE_CUDA(ctx, cudaMemcpyAsync(d_off, off.data(), sizeof(int64_t) * n_big, cudaMemcpyHostToDevice, ctx->stream));
             k_alias_big<<<n_big, 32, 0, ctx->stream>>>(d_row_ptr, d_big, n_big, d_off, d_scratch, d_prob, d_alias);
             DGE_LAUNCH_CHECK(ctx);
             DGE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            cudaFree(d_scratch);
-            cudaFree(d_off);
+            dge_free(ctx, d_scratch);
+            dge_free(ctx, d_off);
         }
     }
-    cudaFree(d_big);
-    cudaFree(d_nbig);
+    dge_free(ctx, d_big);
+    dge_free(ctx, d_nbig);
     return rc;
 }
 
 static void graph_release(dge_graph *g) {
     if (!g) return;
-    cudaFree(g->row_ptr); cudaFree(g->col); cudaFree(g->w); cudaFree(g->prob); cudaFree(g->alias);
-    cudaFree(g->out_degree); cudaFree(g->sources); cudaFree(g->src_w); cudaFree(g->src_prob);
-    cudaFree(g->src_alias); cudaFree(g->sws); cudaFree(g->rec); cudaFree(g->srec);
+    dge_free(g->ctx, g->row_ptr); dge_free(g->ctx, g->col); dge_free(g->ctx, g->w); dge_free(g->ctx, g->prob); dge_free(g->ctx, g->alias);
+    dge_free(g->ctx, g->out_degree); dge_free(g->ctx, g->sources); dge_free(g->ctx, g->src_w); dge_free(g->ctx, g->src_prob);
+    dge_free(g->ctx, g->src_alias); dge_free(g->ctx, g->sws); dge_free(g->ctx, g->rec); dge_free(g->ctx, g->srec);
     delete g;
 }
 
@@ -641,31 +643,31 @@ int dge_graph_build(dge_ctx *ctx, int32_t nv, int64_t ne, const int32_t *src, co
     g->ctx = ctx; g->nv = nv; g->ne = ne; g->ns = ns;
 
     dge_phase_timer t_csr(ctx, "csr");
-    DGE_CUDA(ctx, dge_malloc(&g->row_ptr, (size_t)nv + 1));
-    DGE_CUDA(ctx, dge_malloc(&g->col, (size_t)ne));
-    DGE_CUDA(ctx, dge_malloc(&g->w, (size_t)ne));
-    DGE_CUDA(ctx, dge_malloc(&g->prob, (size_t)ne));
-    DGE_CUDA(ctx, dge_malloc(&g->alias, (size_t)ne));
-    DGE_CUDA(ctx, dge_malloc(&g->out_degree, (size_t)nv));
-    DGE_CUDA(ctx, dge_malloc(&g->sources, (size_t)ns));
-    DGE_CUDA(ctx, dge_malloc(&g->src_w, (size_t)ns));
-    DGE_CUDA(ctx, dge_malloc(&g->src_prob, (size_t)ns));
-    DGE_CUDA(ctx, dge_malloc(&g->src_alias, (size_t)ns));
-    DGE_CUDA(ctx, dge_malloc(&g->sws, 1));
-    DGE_CUDA(ctx, dge_malloc(&g->rec, (size_t)ne));
-    DGE_CUDA(ctx, dge_malloc(&g->srec, (size_t)ns));
+    DGE_CUDA(ctx, dge_malloc(ctx, &g->row_ptr, (size_t)nv + 1));
+    DGE_CUDA(ctx, dge_malloc(ctx, &g->col, (size_t)ne));
+    DGE_CUDA(ctx, dge_malloc(ctx, &g->w, (size_t)ne));
+    DGE_CUDA(ctx, dge_malloc(ctx, &g->prob, (size_t)ne));
+    DGE_CUDA(ctx, dge_malloc(ctx, &g->alias, (size_t)ne));
+    DGE_CUDA(ctx, dge_malloc(ctx, &g->out_degree, (size_t)nv));
+    DGE_CUDA(ctx, dge_malloc(ctx, &g->sources, (size_t)ns));
+    DGE_CUDA(ctx, dge_malloc(ctx, &g->src_w, (size_t)ns));
+    DGE_CUDA(ctx, dge_malloc(ctx, &g->src_prob, (size_t)ns));
+    DGE_CUDA(ctx, dge_malloc(ctx, &g->src_alias, (size_t)ns));
+    DGE_CUDA(ctx, dge_malloc(ctx, &g->sws, 1));
+    DGE_CUDA(ctx, dge_malloc(ctx, &g->rec, (size_t)ne));
+    DGE_CUDA(ctx, dge_malloc(ctx, &g->srec, (size_t)ns));
 
-    dev_tmp t_src, t_dst, t_w, t_deg, t_first, t_misc, t_tiles, t_perm;
+    dev_tmp t_src(ctx), t_dst(ctx), t_w(ctx), t_deg(ctx), t_first(ctx), t_misc(ctx), t_tiles(ctx), t_perm(ctx);
     int32_t *d_src, *d_dst, *d_deg;
     double *d_w;
     int64_t *d_first;
-    DGE_CUDA(ctx, dge_malloc((int32_t **)&t_src.p, (size_t)ne)); d_src = (int32_t *)t_src.p;
-    DGE_CUDA(ctx, dge_malloc((int32_t **)&t_dst.p, (size_t)ne)); d_dst = (int32_t *)t_dst.p;
-    DGE_CUDA(ctx, dge_malloc((double **)&t_w.p, (size_t)ne)); d_w = (double *)t_w.p;
-    DGE_CUDA(ctx, dge_malloc((int32_t **)&t_deg.p, (size_t)nv + 1)); d_deg = (int32_t *)t_deg.p;
-    DGE_CUDA(ctx, dge_malloc((int64_t **)&t_first.p, (size_t)nv)); d_first = (int64_t *)t_first.p;
+    DGE_CUDA(ctx, dge_malloc(ctx, (int32_t **)&t_src.p, (size_t)ne)); d_src = (int32_t *)t_src.p;
+    DGE_CUDA(ctx, dge_malloc(ctx, (int32_t **)&t_dst.p, (size_t)ne)); d_dst = (int32_t *)t_dst.p;
+    DGE_CUDA(ctx, dge_malloc(ctx, (double **)&t_w.p, (size_t)ne)); d_w = (double *)t_w.p;
+    DGE_CUDA(ctx, dge_malloc(ctx, (int32_t **)&t_deg.p, (size_t)nv + 1)); d_deg = (int32_t *)t_deg.p;
+    DGE_CUDA(ctx, dge_malloc(ctx, (int64_t **)&t_first.p, (size_t)nv)); d_first = (int64_t *)t_first.p;
     // misc: [0] runs (u64), [1] bad (int), [2] nonempty (int)
-    DGE_CUDA(ctx, dge_malloc((unsigned long long **)&t_misc.p, 4));
+    DGE_CUDA(ctx, dge_malloc(ctx, (unsigned long long **)&t_misc.p, 4));
     unsigned long long *d_runs = (unsigned long long *)t_misc.p;
     int *d_bad = (int *)(d_runs + 1);
     int32_t *d_nonempty = (int32_t *)(d_runs + 2);
@@ -687,7 +689,7 @@ int dge_graph_build(dge_ctx *ctx, int32_t nv, int64_t ne, const int32_t *src, co
     int32_t n_tiles = (int32_t)(((int64_t)nv + SCAN_TILE - 1) / SCAN_TILE);
     if (n_tiles < 1) n_tiles = 1;
     int64_t *d_tiles;
-    DGE_CUDA(ctx, dge_malloc((int64_t **)&t_tiles.p, (size_t)n_tiles)); d_tiles = (int64_t *)t_tiles.p;
+    DGE_CUDA(ctx, dge_malloc(ctx, (int64_t **)&t_tiles.p, (size_t)n_tiles)); d_tiles = (int64_t *)t_tiles.p;
     if (nv > 0) {
         k_scan_tile_sums<<<n_tiles, SCAN_THREADS, 0, st>>>(d_deg, nv, d_tiles, d_nonempty);
         DGE_LAUNCH_CHECK(ctx);
@@ -710,7 +712,7 @@ int dge_graph_build(dge_ctx *ctx, int32_t nv, int64_t ne, const int32_t *src, co
             DGE_LAUNCH_CHECK(ctx);
         } else {
             int32_t *d_perm;
-            DGE_CUDA(ctx, dge_malloc((int32_t **)&t_perm.p, (size_t)ne)); d_perm = (int32_t *)t_perm.p;
+            DGE_CUDA(ctx, dge_malloc(ctx, (int32_t **)&t_perm.p, (size_t)ne)); d_perm = (int32_t *)t_perm.p;
             DGE_CUDA(ctx, cudaMemsetAsync(d_deg, 0, sizeof(int32_t) * ((size_t)nv + 1), st)); // reuse as cursor
             k_place_atomic<<<grid_for(ne, T, ctx->sm_count, 16), T, 0, st>>>(d_src, ne, g->row_ptr, d_deg, d_perm);
             DGE_LAUNCH_CHECK(ctx);
@@ -751,8 +753,8 @@ int dge_graph_build(dge_ctx *ctx, int32_t nv, int64_t ne, const int32_t *src, co
         }
         DGE_CUDA(ctx, cudaMemcpyAsync(&g->source_weight_sum, g->sws, sizeof(double), cudaMemcpyDeviceToHost, st));
         int64_t h_rp[2] = {0, ns};
-        dev_tmp t_rp;
-        DGE_CUDA(ctx, dge_malloc((int64_t **)&t_rp.p, 2));
+        dev_tmp t_rp(ctx);
+        DGE_CUDA(ctx, dge_malloc(ctx, (int64_t **)&t_rp.p, 2));
         DGE_CUDA(ctx, cudaMemcpyAsync(t_rp.p, h_rp, sizeof(h_rp), cudaMemcpyHostToDevice, st));
         rc = run_alias(ctx, (const int64_t *)t_rp.p, 1, ns, g->src_w, g->sws, g->src_prob, g->src_alias);
         if (rc != DGE_OK) return rc;
@@ -815,10 +817,10 @@ int dge_graph_sample_next(const dge_graph *g, int64_t n, const int32_t *v, const
     if (n == 0) return DGE_OK;
     DGE_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    dev_tmp tv, tx, to;
-    DGE_CUDA(ctx, dge_malloc((int32_t **)&tv.p, (size_t)n));
-    DGE_CUDA(ctx, dge_malloc((double **)&tx.p, (size_t)n));
-    DGE_CUDA(ctx, dge_malloc((int32_t **)&to.p, (size_t)n));
+    dev_tmp tv(ctx), tx(ctx), to(ctx);
+    DGE_CUDA(ctx, dge_malloc(ctx, (int32_t **)&tv.p, (size_t)n));
+    DGE_CUDA(ctx, dge_malloc(ctx, (double **)&tx.p, (size_t)n));
+    DGE_CUDA(ctx, dge_malloc(ctx, (int32_t **)&to.p, (size_t)n));
     DGE_CUDA(ctx, cudaMemcpyAsync(tv.p, v, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
     DGE_CUDA(ctx, cudaMemcpyAsync(tx.p, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
     k_sample_next<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g->rec, g->srec, g->ns, g->nv, g->row_ptr, g->col, g->w,

@@ -37,6 +37,8 @@ struct sgns_args {
     uint64_t seed;
     unsigned long long *pairs;
     int64_t n_groups;
+    int32_t ep_lo, ep_hi;     // epochs [ep_lo, ep_hi) and sentences [s_lo, s_hi) of this launch (multi-GPU rounds
+    int64_t s_lo, s_hi;       // launch one slice at a time; a single-GPU run is one launch over everything)
     uint64_t lcg_a[SGNS_MAX_NEG], lcg_c[SGNS_MAX_NEG]; // (k+1)-step jump of the negative-sampling LCG
     int32_t dbg;
 };
@@ -63,12 +65,12 @@ __device__ __forceinline__ float sgns_alpha(const sgns_args &a, int ep, int64_t 
     return alpha < a.min_lr ? a.min_lr : alpha;
 }
 
-__global__ void k_hist(const int32_t *__restrict__ tok, int64_t total, unsigned int *__restrict__ cnt) {
+__global__ void k_hist(const int32_t *__restrict__ tok, int64_t total, unsigned long long *__restrict__ cnt) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < total; i += stride) {
         int32_t t = tok[i];
-        if (t >= 0) atomicAdd(&cnt[t], 1u);
+        if (t >= 0) atomicAdd(&cnt[t], 1ULL);
     }
 }
 
@@ -170,8 +172,8 @@ k_sgns_seq(const sgns_args a) {
     const int win = a.window;
     const int64_t N = a.n_sent;
     unsigned long long pairs = 0;
-    for (int ep = 0; ep < a.epochs; ep++) {
-        for (int64_t s = gid; s < N; s += a.n_groups) {
+    for (int ep = a.ep_lo; ep < a.ep_hi; ep++) {
+        for (int64_t s = a.s_lo + gid; s < a.s_hi; s += a.n_groups) {
             int n = 0;
             while (n < a.Lmax && a.wtok[(int64_t)n * N + s] >= 0) n++;
             const float alpha = sgns_alpha(a, ep, s);
@@ -283,7 +285,7 @@ k_sgns_items(const sgns_args a) {
     const float idx_scale = (float)E / SGNS_MAX_EXP / 2.0f;
     const int win = a.window;
     const int64_t N = a.n_sent;
-    const int64_t n_items = N * a.Lmax;
+    const int64_t item_lo = a.s_lo * a.Lmax, n_items = a.s_hi * a.Lmax; // items [item_lo, n_items) of this launch
     const double inv_total = 1.0 / (double)((int64_t)a.epochs * N);
     const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
     const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
@@ -299,8 +301,8 @@ k_sgns_items(const sgns_args a) {
 #pragma unroll
     for (int v = 0; v < VPL; v++) { live[v] = lane + v * G < n4; slot[v] = live[v] ? lane + v * G : 0; }
     unsigned long long pairs = 0;
-    for (int ep = 0; ep < a.epochs; ep++) {
-        for (int64_t base = warp_id * GPW; base < n_items; base += a.n_groups) { // warp-uniform trip count
+    for (int ep = a.ep_lo; ep < a.ep_hi; ep++) {
+        for (int64_t base = item_lo + warp_id * GPW; base < n_items; base += a.n_groups) { // warp-uniform trip count
             const int64_t item = base + gw;
             bool valid = item < n_items;
             const int64_t s = valid ? item / a.Lmax : 0;
@@ -435,7 +437,7 @@ k_sgns_items_pipe(const sgns_args a) {
     const int win = a.window;
     const int64_t N = a.n_sent;
     const int Lmax = a.Lmax;
-    const int64_t n_items = N * Lmax;
+    const int64_t item_lo = a.s_lo * Lmax, n_items = a.s_hi * Lmax; // items [item_lo, n_items) of this launch
     const double inv_total = 1.0 / (double)((int64_t)a.epochs * N);
     const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
     const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
@@ -451,8 +453,8 @@ k_sgns_items_pipe(const sgns_args a) {
     struct stage_t { int32_t last; bool act; uint64_t ns0, nsk; int32_t traw; };
     struct stage_r { int32_t last; bool act; uint64_t ns0; int32_t tg[SGNS_CH]; float4 row[SGNS_CH]; float4 v0; };
 
-    for (int ep = 0; ep < a.epochs; ep++) {
-        for (int64_t base = warp_id * GPW; base < n_items; base += a.n_groups) { // warp-uniform trip count
+    for (int ep = a.ep_lo; ep < a.ep_hi; ep++) {
+        for (int64_t base = item_lo + warp_id * GPW; base < n_items; base += a.n_groups) { // warp-uniform trip count
             const int64_t item = base + gw;
             bool valid = item < n_items;
             const int64_t s = valid ? item / Lmax : 0;
@@ -561,6 +563,30 @@ k_sgns_items_pipe(const sgns_args a) {
     if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
 }
 
+// multi-GPU delta exchange (see dge_sgns_train): cur -= base  ...all-reduce(cur)...  base += cur; cur = base
+__global__ void k_delta_begin(float *__restrict__ c0, const float *__restrict__ b0, float *__restrict__ c1,
+                              const float *__restrict__ b1, size_t n) {
+    size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4, stride = (size_t)gridDim.x * blockDim.x * 4;
+    for (; i < n; i += stride) { // n is a multiple of 4 (rows are whole float4 slots)
+        float4 x = *reinterpret_cast<float4 *>(c0 + i), y = *reinterpret_cast<const float4 *>(b0 + i);
+        *reinterpret_cast<float4 *>(c0 + i) = make_float4(x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w);
+        x = *reinterpret_cast<float4 *>(c1 + i); y = *reinterpret_cast<const float4 *>(b1 + i);
+        *reinterpret_cast<float4 *>(c1 + i) = make_float4(x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w);
+    }
+}
+__global__ void k_delta_end(float *__restrict__ c0, float *__restrict__ b0, float *__restrict__ c1, float *__restrict__ b1,
+                            size_t n) {
+    size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4, stride = (size_t)gridDim.x * blockDim.x * 4;
+    for (; i < n; i += stride) {
+        float4 x = *reinterpret_cast<float4 *>(c0 + i), y = *reinterpret_cast<float4 *>(b0 + i);
+        y = make_float4(y.x + x.x, y.y + x.y, y.z + x.z, y.w + x.w);
+        *reinterpret_cast<float4 *>(b0 + i) = y; *reinterpret_cast<float4 *>(c0 + i) = y;
+        x = *reinterpret_cast<float4 *>(c1 + i); y = *reinterpret_cast<float4 *>(b1 + i);
+        y = make_float4(y.x + x.x, y.y + x.y, y.z + x.z, y.w + x.w);
+        *reinterpret_cast<float4 *>(b1 + i) = y; *reinterpret_cast<float4 *>(c1 + i) = y;
+    }
+}
+
 typedef void (*sgns_kernel_t)(const sgns_args);
 struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq, items; };
 
@@ -598,7 +624,7 @@ static bool pick_variant(int n4, sgns_variant *out) {
 
 static void model_release(dge_model *m) {
     if (!m) return;
-    cudaFree(m->syn0); cudaFree(m->syn1neg); cudaFree(m->id_of_word);
+    dge_free(m->ctx, m->syn0); dge_free(m->ctx, m->syn1neg); dge_free(m->ctx, m->id_of_word);
     delete m;
 }
 
@@ -608,6 +634,7 @@ void dge_sgns_default_params(dge_sgns_params *p) {
     if (!p) return;
     p->dim = 20; p->window = 8; p->negative = 5; p->min_count = 2; p->epochs = 1;
     p->neg_table_size = 100000; p->exp_table_size = 1000; p->concurrency = 0; p->schedule = DGE_SCHEDULE_ITEMS;
+    p->sync_rounds = 0;
     p->lr = 0.025f; p->min_lr = 1e-4f; p->seed = 1;
 }
 
@@ -620,7 +647,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         return dge_fail(ctx, DGE_E_INVALID, "dge_sgns_train: need 1..4 corpora and params");
     if (p->negative > SGNS_MAX_NEG) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: negative must be <= 32");
     if (p->dim < 1 || p->window < 1 || p->negative < 0 || p->epochs < 1 || p->neg_table_size < 1 ||
-        p->exp_table_size < 2 || p->min_count < 0 || p->concurrency < 0 ||
+        p->exp_table_size < 2 || p->min_count < 0 || p->concurrency < 0 || p->sync_rounds < 0 ||
         (p->schedule != DGE_SCHEDULE_ITEMS && p->schedule != DGE_SCHEDULE_SENTENCE))
         return dge_fail(ctx, DGE_E_INVALID, "dge_sgns_train: invalid hyper-parameter");
     int32_t n_ids = corpora[0] ? corpora[0]->n_ids : 0;
@@ -642,9 +669,9 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
 
     // ---- vocabulary: device histogram, host ranking (descending count, ties ascending id)
     dge_phase_timer t_vocab(ctx, "vocab");
-    unsigned int *d_cnt = nullptr;
-    DGE_CUDA(ctx, dge_malloc(&d_cnt, (size_t)n_ids));
-    cudaMemsetAsync(d_cnt, 0, sizeof(unsigned int) * (size_t)(n_ids ? n_ids : 1), st);
+    unsigned long long *d_cnt = nullptr;
+    DGE_CUDA(ctx, dge_malloc(ctx, &d_cnt, (size_t)n_ids + 2));
+    cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * ((size_t)n_ids + 2), st);
     for (int i = 0; i < n_corpora; i++) {
         int64_t total = corpora[i]->n * (int64_t)corpora[i]->L;
         if (total) {
@@ -652,15 +679,29 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             ctx->launches++;
         }
     }
-    std::vector<unsigned int> cnt((size_t)n_ids + 1);
-    cudaError_t ce = cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(unsigned int) * (size_t)n_ids, cudaMemcpyDeviceToHost, st);
+    // multi-GPU: every rank holds a shard of the corpus; the vocabulary is built from the global counts so that all
+    // ranks index the same words identically.  Slot n_ids carries max(local sentences) (rounds must agree).
+    const bool multi = ctx->comm != nullptr && ctx->world > 1;
+    int64_t max_sent = n_sent;
+    if (multi) {
+        int rc = dge_comm_allreduce_sum_u64(ctx, d_cnt, (size_t)n_ids);
+        unsigned long long h_ns = (unsigned long long)n_sent;
+        if (rc == DGE_OK) {
+            cudaMemcpyAsync(d_cnt + n_ids, &h_ns, sizeof(h_ns), cudaMemcpyHostToDevice, st);
+            rc = dge_comm_allreduce_max_u64(ctx, d_cnt + n_ids, 1);
+        }
+        if (rc != DGE_OK) { dge_free(ctx, d_cnt); return rc; }
+    }
+    std::vector<unsigned long long> cnt((size_t)n_ids + 2);
+    cudaError_t ce = cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(unsigned long long) * ((size_t)n_ids + 1), cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-    cudaFree(d_cnt);
+    dge_free(ctx, d_cnt);
     if (ce != cudaSuccess) return dge_fail(ctx, DGE_E_CUDA, std::string("dge_sgns_train: histogram: ") + cudaGetErrorString(ce));
+    if (multi) max_sent = (int64_t)cnt[n_ids];
     std::vector<int32_t> order;
     order.reserve(n_ids);
     for (int32_t i = 0; i < n_ids; i++)
-        if (cnt[i] > 0 && (int64_t)cnt[i] >= p->min_count) order.push_back(i);
+        if (cnt[i] > 0 && cnt[i] >= (unsigned long long)p->min_count) order.push_back(i);
     std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
         if (cnt[x] != cnt[y]) return cnt[x] > cnt[y];
         return x < y;
@@ -695,17 +736,17 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
     int32_t *d_word_of_id = nullptr, *d_table = nullptr;
     float *d_exp = nullptr;
     unsigned long long *d_pairs = nullptr;
-    auto cleanup = [&]() { cudaFree(d_word_of_id); cudaFree(d_table); cudaFree(d_exp); cudaFree(d_pairs); };
+    auto cleanup = [&]() { dge_free(ctx, d_word_of_id); dge_free(ctx, d_table); dge_free(ctx, d_exp); dge_free(ctx, d_pairs); };
     auto fail = [&](const std::string &msg) {
         cleanup();
         model_release(m);
         return dge_fail(ctx, DGE_E_CUDA, msg);
     };
     size_t nel = (size_t)(V ? V : 1) * (size_t)stride;
-    if (dge_malloc(&m->syn0, nel) != cudaSuccess || dge_malloc(&m->syn1neg, nel) != cudaSuccess ||
-        dge_malloc(&m->id_of_word, (size_t)V) != cudaSuccess || dge_malloc(&d_word_of_id, (size_t)n_ids) != cudaSuccess ||
-        dge_malloc(&d_table, (size_t)p->neg_table_size) != cudaSuccess ||
-        dge_malloc(&d_exp, (size_t)p->exp_table_size) != cudaSuccess || dge_malloc(&d_pairs, 2) != cudaSuccess)
+    if (dge_malloc(ctx, &m->syn0, nel) != cudaSuccess || dge_malloc(ctx, &m->syn1neg, nel) != cudaSuccess ||
+        dge_malloc(ctx, &m->id_of_word, (size_t)V) != cudaSuccess || dge_malloc(ctx, &d_word_of_id, (size_t)n_ids) != cudaSuccess ||
+        dge_malloc(ctx, &d_table, (size_t)p->neg_table_size) != cudaSuccess ||
+        dge_malloc(ctx, &d_exp, (size_t)p->exp_table_size) != cudaSuccess || dge_malloc(ctx, &d_pairs, 2) != cudaSuccess)
         return fail("dge_sgns_train: cudaMalloc failed");
     cudaMemsetAsync(m->syn0, 0, nel * sizeof(float), st);
     cudaMemsetAsync(m->syn1neg, 0, nel * sizeof(float), st);
@@ -721,10 +762,10 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
     }
 
     int32_t *d_wtok = nullptr;
-    if (V > 0 && n_sent > 0) {
+    if (V > 0 && (n_sent > 0 || multi)) {
         // ---- compacted corpus in vocabulary indices (position-major, all corpora concatenated)
         dge_phase_timer t_prep(ctx, "compact");
-        if (dge_malloc(&d_wtok, (size_t)n_sent * (size_t)Lmax) != cudaSuccess) return fail("dge_sgns_train: cudaMalloc corpus failed");
+        if (dge_malloc(ctx, &d_wtok, (size_t)n_sent * (size_t)Lmax) != cudaSuccess) return fail("dge_sgns_train: cudaMalloc corpus failed");
         int64_t first = 0;
         for (int i = 0; i < n_corpora; i++) {
             if (corpora[i]->n > 0) {
@@ -783,20 +824,74 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         int blocks = (int)((want + gpb - 1) / gpb);
         a.n_groups = (int64_t)blocks * gpb;
         ctx->phase_ms["sgns_groups"] = (float)a.n_groups;
+        // ---- launches.  Single GPU: one launch over all epochs and sentences.  Data-parallel (ctx has a communicator,
+        // or sync_rounds > 0): each epoch is cut into `rounds` slices of sentences; after every slice the ranks
+        // exchange the SUM of their embedding deltas (cur - base) with one NCCL all-reduce per table over NVLink and
+        // all continue from base + sum.  All updates of all ranks are applied (the multi-GPU analogue of Hogwild
+        // threads); averaging the parameters instead would divide the learning rate by the world size.
+        int rounds = 1;
+        if (multi || p->sync_rounds > 0) {
+            rounds = p->sync_rounds > 0 ? p->sync_rounds : (int)std::max<int64_t>(4, (max_sent + (1 << 20) - 1) >> 20);
+            rounds = (int)std::min<int64_t>(rounds, std::max<int64_t>(1, max_sent));
+        }
+        float *base0 = nullptr, *base1 = nullptr;
+        if (rounds > 1 || multi) {
+            if (dge_malloc(ctx, &base0, nel) != cudaSuccess || dge_malloc(ctx, &base1, nel) != cudaSuccess) {
+                dge_free(ctx, base0); dge_free(ctx, d_wtok);
+                return fail("dge_sgns_train: cudaMalloc of the delta base failed");
+            }
+            cudaMemcpyAsync(base0, m->syn0, nel * sizeof(float), cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync(base1, m->syn1neg, nel * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        }
+        ctx->phase_ms["sgns_rounds"] = (float)rounds;
+        float sync_ms = 0.f;
+        int comm_rc = DGE_OK;
         dge_phase_timer t_sgns(ctx, "sgns");
         smem = smem_for(threads);
-        fn<<<blocks, threads, smem, st>>>(a);
-        ctx->launches++;
+        if (rounds == 1 && !multi) {
+            a.ep_lo = 0; a.ep_hi = p->epochs; a.s_lo = 0; a.s_hi = n_sent;
+            fn<<<blocks, threads, smem, st>>>(a);
+            ctx->launches++;
+        } else {
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            const int grid_e = ctx->sm_count * 8;
+            for (int ep = 0; ep < p->epochs && comm_rc == DGE_OK; ep++) {
+                for (int r = 0; r < rounds && comm_rc == DGE_OK; r++) {
+                    a.ep_lo = ep; a.ep_hi = ep + 1;
+                    a.s_lo = n_sent * r / rounds; a.s_hi = n_sent * (r + 1) / rounds;
+                    if (a.s_hi > a.s_lo) {
+                        fn<<<blocks, threads, smem, st>>>(a);
+                        ctx->launches++;
+                    }
+                    cudaEventRecord(e0, st);
+                    k_delta_begin<<<grid_e, 256, 0, st>>>(m->syn0, base0, m->syn1neg, base1, nel);
+                    comm_rc = dge_comm_allreduce_sum_f32(ctx, m->syn0, nel);
+                    if (comm_rc == DGE_OK) comm_rc = dge_comm_allreduce_sum_f32(ctx, m->syn1neg, nel);
+                    k_delta_end<<<grid_e, 256, 0, st>>>(m->syn0, base0, m->syn1neg, base1, nel);
+                    ctx->launches += 2;
+                    cudaEventRecord(e1, st);
+                    cudaEventSynchronize(e1);
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    sync_ms += ms;
+                }
+            }
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+        }
         t_sgns.stop();
+        ctx->phase_ms["sgns_sync"] = sync_ms;
+        dge_free(ctx, base0); dge_free(ctx, base1);
+        if (comm_rc != DGE_OK) { dge_free(ctx, d_wtok); cleanup(); model_release(m); return comm_rc; }
         ce = cudaGetLastError();
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-        if (ce != cudaSuccess) { cudaFree(d_wtok); return fail(std::string("dge_sgns_train: kernel: ") + cudaGetErrorString(ce)); }
+        if (ce != cudaSuccess) { dge_free(ctx, d_wtok); return fail(std::string("dge_sgns_train: kernel: ") + cudaGetErrorString(ce)); }
         unsigned long long h_pairs[2] = {0, 0};
         cudaMemcpy(h_pairs, d_pairs, sizeof(h_pairs), cudaMemcpyDeviceToHost);
         m->pairs = (int64_t)h_pairs[0];
         m->words = (int64_t)h_pairs[1];
     }
-    cudaFree(d_wtok);
+    dge_free(ctx, d_wtok);
     ce = cudaStreamSynchronize(st);
     if (ce != cudaSuccess) return fail(std::string("dge_sgns_train: ") + cudaGetErrorString(ce));
     cleanup();

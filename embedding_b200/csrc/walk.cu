@@ -173,8 +173,8 @@ int dge_corpus_relabel(dge_corpus *c, const int32_t *id_map, int32_t new_n_ids, 
     DGE_CUDA(ctx, cudaSetDevice(ctx->device));
     int32_t *d_map = nullptr;
     int *d_bad = nullptr;
-    DGE_CUDA(ctx, dge_malloc(&d_map, (size_t)c->n_ids));
-    if (dge_malloc(&d_bad, 1) != cudaSuccess) { cudaFree(d_map); return dge_fail(ctx, DGE_E_CUDA, "dge_corpus_relabel: cudaMalloc"); }
+    DGE_CUDA(ctx, dge_malloc(ctx, &d_map, (size_t)c->n_ids));
+    if (dge_malloc(ctx, &d_bad, 1) != cudaSuccess) { dge_free(ctx, d_map); return dge_fail(ctx, DGE_E_CUDA, "dge_corpus_relabel: cudaMalloc"); }
     cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream);
     if (c->n_ids) cudaMemcpyAsync(d_map, id_map, sizeof(int32_t) * (size_t)c->n_ids, cudaMemcpyHostToDevice, ctx->stream);
     if (c->n * c->L > 0) {
@@ -185,7 +185,7 @@ int dge_corpus_relabel(dge_corpus *c, const int32_t *id_map, int32_t new_n_ids, 
     cudaError_t e = cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
-    cudaFree(d_map); cudaFree(d_bad);
+    dge_free(ctx, d_map); dge_free(ctx, d_bad);
     if (e != cudaSuccess) return dge_fail(ctx, DGE_E_CUDA, std::string("dge_corpus_relabel: ") + cudaGetErrorString(e));
     if (h_bad) return dge_fail(ctx, DGE_E_INVALID, "dge_corpus_relabel: mapped id outside [0, new_n_ids) (corpus is now partially relabelled)");
     c->n_ids = new_n_ids;
@@ -204,7 +204,7 @@ int dge_walk(const dge_graph *g, int64_t n_walks, int64_t first_walk_id, int32_t
     DGE_CUDA(ctx, cudaSetDevice(ctx->device));
     dge_corpus *c = new dge_corpus();
     c->ctx = ctx; c->n = n_walks; c->L = L; c->n_ids = g->nv;
-    cudaError_t e = dge_malloc(&c->tok, (size_t)n_walks * (size_t)L);
+    cudaError_t e = dge_malloc(ctx, &c->tok, (size_t)n_walks * (size_t)L);
     if (e != cudaSuccess) {
         delete c;
         return dge_fail(ctx, DGE_E_CUDA, std::string("dge_walk: cudaMalloc tokens: ") + cudaGetErrorString(e));
@@ -223,7 +223,7 @@ int dge_walk(const dge_graph *g, int64_t n_walks, int64_t first_walk_id, int32_t
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {
-            cudaFree(c->tok);
+            dge_free(ctx, c->tok);
             delete c;
             return dge_fail(ctx, DGE_E_CUDA, std::string("dge_walk: ") + cudaGetErrorString(e));
         }
@@ -247,12 +247,12 @@ int dge_corpus_from_tokens(dge_ctx *ctx, const int32_t *tokens, int64_t n_walks,
     unsigned long long *d_cnt = nullptr;
     int rc = DGE_OK;
     auto fail = [&](const std::string &m, int code) {
-        cudaFree(c->tok); cudaFree(stage); cudaFree(d_cnt);
+        dge_free(ctx, c->tok); dge_free(ctx, stage); dge_free(ctx, d_cnt);
         delete c;
         return dge_fail(ctx, code, m);
     };
-    if (dge_malloc(&c->tok, total) != cudaSuccess || dge_malloc(&stage, total) != cudaSuccess ||
-        dge_malloc(&d_cnt, 2) != cudaSuccess)
+    if (dge_malloc(ctx, &c->tok, total) != cudaSuccess || dge_malloc(ctx, &stage, total) != cudaSuccess ||
+        dge_malloc(ctx, &d_cnt, 2) != cudaSuccess)
         return fail("dge_corpus_from_tokens: cudaMalloc failed", DGE_E_CUDA);
     if (total) {
         dge_phase_timer t(ctx, "tokens_h2d");
@@ -270,7 +270,7 @@ int dge_corpus_from_tokens(dge_ctx *ctx, const int32_t *tokens, int64_t n_walks,
         if (e != cudaSuccess) return fail(std::string("dge_corpus_from_tokens: ") + cudaGetErrorString(e), DGE_E_CUDA);
         if (h_bad) return fail("dge_corpus_from_tokens: token id outside [-1, n_ids)", DGE_E_INVALID);
     }
-    cudaFree(stage); cudaFree(d_cnt);
+    dge_free(ctx, stage); dge_free(ctx, d_cnt);
     *out = c;
     return rc;
 }
@@ -291,7 +291,7 @@ int dge_corpus_tokens(const dge_corpus *c, int32_t *tokens) {
     if (!tokens) return dge_fail(ctx, DGE_E_INVALID, "dge_corpus_tokens: tokens is NULL");
     DGE_CUDA(ctx, cudaSetDevice(ctx->device));
     int32_t *stage = nullptr;
-    DGE_CUDA(ctx, dge_malloc(&stage, total));
+    DGE_CUDA(ctx, dge_malloc(ctx, &stage, total));
     dge_phase_timer t(ctx, "tokens_d2h");
     dim3 grid((unsigned)((c->n + 31) / 32), (unsigned)((c->L + 31) / 32)), block(32, 8);
     k_tokens_to_walk_major<<<grid, block, 0, ctx->stream>>>(c->tok, c->n, c->L, stage);
@@ -300,7 +300,7 @@ int dge_corpus_tokens(const dge_corpus *c, int32_t *tokens) {
     t.stop();
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
-    cudaFree(stage);
+    dge_free(ctx, stage);
     if (e != cudaSuccess) return dge_fail(ctx, DGE_E_CUDA, std::string("dge_corpus_tokens: ") + cudaGetErrorString(e));
     return DGE_OK;
 }
@@ -310,7 +310,7 @@ int dge_corpus_count_tokens(const dge_corpus *c, int64_t *n_tokens) {
     dge_ctx *ctx = c->ctx;
     DGE_CUDA(ctx, cudaSetDevice(ctx->device));
     unsigned long long *d_cnt = nullptr;
-    DGE_CUDA(ctx, dge_malloc(&d_cnt, 2));
+    DGE_CUDA(ctx, dge_malloc(ctx, &d_cnt, 2));
     cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), ctx->stream);
     int64_t total = c->n * (int64_t)c->L;
     if (total) {
@@ -320,7 +320,7 @@ int dge_corpus_count_tokens(const dge_corpus *c, int64_t *n_tokens) {
     unsigned long long h = 0;
     cudaError_t e = cudaMemcpyAsync(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_cnt);
+    dge_free(ctx, d_cnt);
     if (e != cudaSuccess) return dge_fail(ctx, DGE_E_CUDA, std::string("dge_corpus_count_tokens: ") + cudaGetErrorString(e));
     *n_tokens = (int64_t)h;
     return DGE_OK;
@@ -329,7 +329,7 @@ int dge_corpus_count_tokens(const dge_corpus *c, int64_t *n_tokens) {
 void dge_corpus_free(dge_corpus *c) {
     if (!c) return;
     cudaSetDevice(c->ctx->device);
-    cudaFree(c->tok);
+    dge_free(c->ctx, c->tok);
     delete c;
 }
 

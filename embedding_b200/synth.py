@@ -43,12 +43,16 @@ def spatial_weights(n, seed=2013, extent=0.25):
     return np.exp(-d * 100.0)
 
 
-def powerlaw_flow_graph(n_regions, L=24, seed=100000, mean_degree=42, cap=4096, zipf_a=1.6):
+def powerlaw_flow_graph(n_regions, L=24, seed=100000, mean_degree=42, cap=4096, zipf_a=1.6, pop_s=0.8):
     """Time-sliced synthetic flow graph: node (h, r) has id h*n_regions + r (first-appearance order of a
     host that walks layers then regions), edges (h, r) -> ((h+1)%L, r') grouped by source.
 
     out-degree ~ Zipf(zipf_a) rescaled to `mean_degree`, capped at `cap`; destinations by preferential
-    attachment over regions (popularity ~ Zipf); weights floor(Pareto(1.2)) + 1.
+    attachment over regions: region popularity follows a rank-Zipf law, p(rank r) ~ (r+1)^-pop_s with pop_s = 0.8
+    (the busiest 1 % of the regions attract ~40 % of the edges), assigned to region ids by a random permutation;
+    weights floor(Pareto(1.2)) + 1.  (An unbounded Zipf *sample* as popularity lets one or two regions swallow the
+    whole graph, which makes every walk and every embedding row cache-resident -- not the HBM-bound shape the
+    100K / 1M-region configs are meant to exercise.)
     Returns dict(n_vertices, src, dst, w, sources, v_layer, v_region)."""
     rng = np.random.default_rng(seed)
     nv = n_regions * L
@@ -58,7 +62,7 @@ def powerlaw_flow_graph(n_regions, L=24, seed=100000, mean_degree=42, cap=4096, 
     deg = np.minimum(deg, n_regions)
     ne = int(deg.sum())
     src = np.repeat(np.arange(nv, dtype=np.int32), deg)
-    pop = rng.zipf(1.3, size=n_regions).astype(np.float64)
+    pop = (1.0 / np.arange(1, n_regions + 1, dtype=np.float64) ** pop_s)[rng.permutation(n_regions)]
     cdf = np.cumsum(pop / pop.sum())
     dst_region = np.searchsorted(cdf, rng.random(ne)).astype(np.int64)
     np.minimum(dst_region, n_regions - 1, out=dst_region)

@@ -11,7 +11,8 @@
  * Conventions
  *   - plain C types only; every buffer in a signature is HOST memory owned by the caller
  *     (device memory never crosses the ABI);
- *   - opaque handles are library-owned and released only by the matching *_free;
+ *   - opaque handles are library-owned and released only by the matching *_free, which must happen before the
+ *     dge_destroy of the ctx they were created on;
  *   - every call is blocking; a ctx (one per GPU / process) is used by one thread at a time;
  *   - return 0 on success, a negative dge_status otherwise; dge_last_error() has the text;
  *   - there is NO CPU fallback: without a usable sm_100 device dge_create fails with DGE_E_NO_DEVICE.
@@ -59,6 +60,24 @@ void dge_host_free(void *p);
 int dge_phase_ms(const dge_ctx *ctx, const char *phase, float *ms);
 /* Number of library kernels launched since dge_create (for bench.py's gpu_launches). */
 int64_t dge_kernel_launches(const dge_ctx *ctx);
+/* Device-side stopwatch: CUDA events recorded on the ctx stream (the stream every library kernel is launched on)
+ * around whatever calls the host makes in between.  Replaces the System.currentTimeMillis() prints of
+ * CrossTimeGraph.java:128,146-147 / SpatialGraph.java:98,119-120. */
+int dge_timer_start(dge_ctx *ctx);
+int dge_timer_stop(dge_ctx *ctx, float *ms);
+
+/* ------------------------------------------------------------------ multi-GPU (one process per GPU)
+ * The reference is single-device (only a commented-out hint, DeepWalk.java:43).  Walks shard by walk id with no
+ * collective (first_walk_id of dge_walk).  Stage 2 becomes data-parallel when the ctx carries a communicator:
+ * every rank trains on its own corpora and dge_sgns_train exchanges the sum of the embedding deltas with NCCL
+ * all-reduces over NVLink (sync_rounds per epoch).  The host moves the opaque id from rank 0 to the other ranks
+ * by any means it has (a file, a socket, MPI, torch.distributed). */
+#define DGE_COMM_ID_BYTES 128
+int dge_comm_unique_id(void *id, size_t bytes);
+int dge_comm_init(dge_ctx *ctx, int rank, int world, const void *id, size_t bytes);
+int dge_comm_shape(const dge_ctx *ctx, int *rank, int *world);
+void dge_comm_destroy(dge_ctx *ctx); /* also done by dge_destroy */
+int dge_comm_nccl_version(void);     /* 0 when NCCL cannot be loaded */
 
 /* ------------------------------------------------------------------ stage 1a: graph + alias tables
  * Stands under LayeredGraph.addEdge :157-174, addSourceVertex :180-189, initiateAliasTables :195-226
@@ -133,6 +152,8 @@ typedef struct {
                                the vocabulary size); 1 = one sentence at a time in the oracle's
                                exact order (parity tests); N = N sentences in flight */
     int32_t schedule;       /* DGE_SCHEDULE_ITEMS (default) or DGE_SCHEDULE_SENTENCE */
+    int32_t sync_rounds;    /* multi-GPU only: delta all-reduces per epoch; 0 = automatic (one per ~2^20 local
+                               sentences, at least 4).  Ignored without a communicator of world > 1. */
     float lr;               /* 0.025 */
     float min_lr;           /* 1e-4 */
     uint64_t seed;

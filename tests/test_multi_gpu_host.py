@@ -58,6 +58,28 @@ def test_walk_shards_union_equals_single_run(oracle, tmp_path):
     assert int(np.load(tmp_path / "steps.npy")[0]) == int((whole >= 0).sum())
 
 
+def _bcast_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from embedding_b200 import parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    payload = bytes(range(128)) if rank == 0 else b""
+    got = parallel.broadcast_bytes(dist, payload, 128)
+    with open(os.path.join(out_dir, "id%d.bin" % rank), "wb") as f:
+        f.write(got)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_comm_id_broadcast_reaches_every_rank(tmp_path):
+    """The host's only job for dge_comm_init: carry the opaque 128-byte id from rank 0 to all ranks."""
+    mp.spawn(_bcast_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert open(tmp_path / ("id%d.bin" % r), "rb").read() == bytes(range(128))
+
+
 def test_shard_arithmetic():
     from embedding_b200 import parallel
     for n in (0, 1, 7, 8, 15_600_000):
