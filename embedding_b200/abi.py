@@ -68,6 +68,7 @@ def lib():
     L.dge_corpus_count_tokens.argtypes = [vp, pi64]
     L.dge_corpus_relabel.argtypes = [vp, pi32, i32, i32]
     L.dge_corpus_write_seq.argtypes = [vp, pi32, pi32, C.c_int, C.c_char_p, C.c_int]
+    L.dge_corpus_read_seq.argtypes = [vp, C.c_char_p, pi32, pi32, i32, C.c_int, P(vp)]
     L.dge_corpus_free.argtypes = [vp]
     L.dge_corpus_free.restype = None
     L.dge_sgns_default_params.argtypes = [P(SgnsParams)]
@@ -78,6 +79,13 @@ def lib():
     L.dge_model_write_vec.argtypes = [vp, pi32, pi32, C.c_char_p]
     L.dge_model_free.argtypes = [vp]
     L.dge_model_free.restype = None
+    L.dge_flows_create.argtypes = [vp, i32, pi32, P(vp)]
+    L.dge_flows_add_trips.argtypes = [vp, i64, pi32, pi32, pi32]
+    L.dge_flows_tensor.argtypes = [vp, pi32]
+    L.dge_flows_free.argtypes = [vp]
+    L.dge_flows_free.restype = None
+    L.dge_crosstime_graph_build.argtypes = [vp, pi32, i32, C.c_int, pi32, P(vp)]
+    L.dge_graph_labels.argtypes = [vp, pi32, pi32, pi32]
     L.dge_timer_start.argtypes = [vp]
     L.dge_timer_stop.argtypes = [vp, P(C.c_float)]
     L.dge_comm_unique_id.argtypes = [vp, C.c_size_t]
@@ -188,8 +196,74 @@ class Context:
         return r.value, w.value
 
 
+class Flows:
+    """dge_flows: the hourly flow counts F[src][hour][dst] on the device."""
+
+    def __init__(self, ctx, n_regions, F=None):
+        self.ctx, self.n = ctx, int(n_regions)
+        if F is not None:
+            F = np.ascontiguousarray(F, np.int32)
+            if F.shape != (self.n, 24, self.n):
+                raise ValueError("F must be [n_regions, 24, n_regions]")
+        h = C.c_void_p()
+        _check(lib().dge_flows_create(ctx._h, self.n, _ptr(F, C.c_int32), C.byref(h)), ctx._h)
+        self._h = h
+        ctx._adopt(self)
+
+    def add_trips(self, src_region, dst_region, start_hour):
+        s = np.ascontiguousarray(src_region, np.int32)
+        d = np.ascontiguousarray(dst_region, np.int32)
+        h = np.ascontiguousarray(start_hour, np.int32)
+        if not (len(s) == len(d) == len(h)):
+            raise ValueError("trip arrays must have equal length")
+        _check(lib().dge_flows_add_trips(self._h, len(s), _ptr(s, C.c_int32), _ptr(d, C.c_int32), _ptr(h, C.c_int32)),
+               self.ctx._h)
+
+    def tensor(self):
+        F = np.empty((self.n, 24, self.n), np.int32)
+        _check(lib().dge_flows_tensor(self._h, _ptr(F, C.c_int32)), self.ctx._h)
+        return F
+
+    def crosstime_graph(self, order, num_layer, mode, intervals=None):
+        """mode 0 = constructGraph_CA(intervals), mode 1 = constructGraph_tract(); returns a Graph with labels."""
+        o = np.ascontiguousarray(order, np.int32)
+        if len(o) != self.n:
+            raise ValueError("order must have n_regions entries")
+        iv = None if intervals is None else np.ascontiguousarray(intervals, np.int32)
+        if iv is not None and len(iv) != num_layer + 1:
+            raise ValueError("intervals must have num_layer + 1 entries")
+        h = C.c_void_p()
+        _check(lib().dge_crosstime_graph_build(self._h, _ptr(o, C.c_int32), int(num_layer), int(mode), _ptr(iv, C.c_int32),
+                                               C.byref(h)), self.ctx._h)
+        return Graph._from_handle(self.ctx, h)
+
+    def free(self):
+        if getattr(self, "_h", None):
+            lib().dge_flows_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.free()
+
+
 class Graph:
     """dge_graph: CSR + alias tables + packed walk records on the device."""
+
+    @classmethod
+    def _from_handle(cls, ctx, h):
+        g = cls.__new__(cls)
+        g.ctx, g._h = ctx, h
+        ctx._adopt(g)
+        nv, ne, ns = C.c_int32(), C.c_int64(), C.c_int32()
+        _check(lib().dge_graph_sizes(h, C.byref(nv), C.byref(ne), C.byref(ns)), ctx._h)
+        g.nv, g.ne, g.ns = nv.value, ne.value, ns.value
+        return g
+
+    def labels(self):
+        """(v_layer, v_region_index, sources) of a graph built from flows on the device."""
+        vl, vr, so = np.empty(self.nv, np.int32), np.empty(self.nv, np.int32), np.empty(self.ns, np.int32)
+        _check(lib().dge_graph_labels(self._h, _ptr(vl, C.c_int32), _ptr(vr, C.c_int32), _ptr(so, C.c_int32)), self.ctx._h)
+        return vl, vr, so
 
     def __init__(self, ctx, n_vertices, src, dst, w, sources, out_degree=None, source_weight_sum=None):
         self.ctx = ctx
@@ -267,6 +341,15 @@ class Corpus:
         h = C.c_void_p()
         _check(lib().dge_corpus_from_tokens(ctx._h, _ptr(tokens, C.c_int32), tokens.shape[0], tokens.shape[1],
                                             int(n_ids), C.byref(h)), ctx._h)
+        return cls(ctx, h)
+
+    @classmethod
+    def read_seq(cls, ctx, path, label_region, label_layer=None, position_prefix=False):
+        lr = np.ascontiguousarray(label_region, np.int32)
+        ll = None if label_layer is None else np.ascontiguousarray(label_layer, np.int32)
+        h = C.c_void_p()
+        _check(lib().dge_corpus_read_seq(ctx._h, os.fsencode(path), _ptr(ll, C.c_int32), _ptr(lr, C.c_int32), len(lr),
+                                         1 if position_prefix else 0, C.byref(h)), ctx._h)
         return cls(ctx, h)
 
     def free(self):

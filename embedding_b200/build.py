@@ -25,6 +25,7 @@ SOURCES = {
     "io.cu": [],
     "sgns.cu": [],
     "comm.cu": [],
+    "flows.cu": [],
 }
 
 

@@ -54,7 +54,22 @@ struct dge_graph {
     double source_weight_sum = 0;
     dge_edge_rec *rec = nullptr;  // [ne]
     dge_edge_rec *srec = nullptr; // [ns]
+    int32_t *v_layer = nullptr;   // [nv] labels by vertex id, only for graphs built by dge_crosstime_graph_build
+    int32_t *v_region = nullptr;  // [nv] region INDEX (position in the host's region-id array)
 };
+
+struct dge_flows {
+    dge_ctx *ctx = nullptr;
+    int32_t n = 0;           // regions
+    int32_t *F = nullptr;    // dense trip counts [n][24][n] (src, hour of day, dst)
+    int64_t trips = 0;       // records added with dge_flows_add_trips
+};
+
+int dge_graph_build_device(dge_ctx *ctx, int32_t nv, int64_t ne, const int32_t *d_src, const int32_t *d_dst,
+                           const double *d_w, int32_t ns, const int32_t *sources, const double *out_degree,
+                           const double *source_weight_sum, dge_graph **out);
+// exclusive scan of int32 flags into int64 positions (graph.cu); pos has n+1 entries
+int dge_scan_i32(dge_ctx *ctx, const int32_t *d_in, int32_t n, int64_t *d_pos);
 
 struct dge_corpus {
     dge_ctx *ctx = nullptr;

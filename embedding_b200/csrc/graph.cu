@@ -545,6 +545,26 @@ struct dev_tmp { // device scratch returned to the ctx pool on scope exit
     ~dev_tmp() { if (p) dge_free(ctx, p); }
 };
 
+int dge_scan_i32(dge_ctx *ctx, const int32_t *d_in, int32_t n, int64_t *d_pos) {
+    cudaStream_t st = ctx->stream;
+    if (n <= 0) {
+        DGE_CUDA(ctx, cudaMemsetAsync(d_pos, 0, sizeof(int64_t), st));
+        return DGE_OK;
+    }
+    int32_t n_tiles = (int32_t)(((int64_t)n + SCAN_TILE - 1) / SCAN_TILE);
+    dev_tmp t_tiles(ctx), t_cnt(ctx);
+    DGE_CUDA(ctx, dge_malloc(ctx, (int64_t **)&t_tiles.p, (size_t)n_tiles));
+    DGE_CUDA(ctx, dge_malloc(ctx, (int32_t **)&t_cnt.p, 1));
+    DGE_CUDA(ctx, cudaMemsetAsync(t_cnt.p, 0, sizeof(int32_t), st));
+    k_scan_tile_sums<<<n_tiles, SCAN_THREADS, 0, st>>>(d_in, n, (int64_t *)t_tiles.p, (int32_t *)t_cnt.p);
+    DGE_LAUNCH_CHECK(ctx);
+    k_scan_sums<<<1, 1024, 0, st>>>((int64_t *)t_tiles.p, n_tiles);
+    DGE_LAUNCH_CHECK(ctx);
+    k_scan_apply<<<n_tiles, SCAN_THREADS, 0, st>>>(d_in, n, (const int64_t *)t_tiles.p, d_pos);
+    DGE_LAUNCH_CHECK(ctx);
+    return DGE_OK;
+}
+
 static int grid_for(int64_t n, int threads, int sm_count, int per_sm = 8) {
     int64_t g = (n + threads - 1) / threads;
     int64_t cap = (int64_t)sm_count * per_sm;
@@ -615,6 +635,7 @@ static void graph_release(dge_graph *g) {
     dge_free(g->ctx, g->row_ptr); dge_free(g->ctx, g->col); dge_free(g->ctx, g->w); dge_free(g->ctx, g->prob); dge_free(g->ctx, g->alias);
     dge_free(g->ctx, g->out_degree); dge_free(g->ctx, g->sources); dge_free(g->ctx, g->src_w); dge_free(g->ctx, g->src_prob);
     dge_free(g->ctx, g->src_alias); dge_free(g->ctx, g->sws); dge_free(g->ctx, g->rec); dge_free(g->ctx, g->srec);
+    dge_free(g->ctx, g->v_layer); dge_free(g->ctx, g->v_region);
     delete g;
 }
 
@@ -622,17 +643,12 @@ struct graph_guard { // frees a half-built graph on an early error return
     dge_graph *g;
     ~graph_guard() { if (g) graph_release(g); }
 };
-extern "C" {
-
-int dge_graph_build(dge_ctx *ctx, int32_t nv, int64_t ne, const int32_t *src, const int32_t *dst, const double *w,
-                    int32_t ns, const int32_t *sources, const double *out_degree, const double *source_weight_sum,
-                    dge_graph **out) {
-    if (!ctx) return dge_fail(nullptr, DGE_E_INVALID, "dge_graph_build: ctx is NULL");
-    if (!out) return dge_fail(ctx, DGE_E_INVALID, "dge_graph_build: out is NULL");
+// Core of dge_graph_build over a DEVICE COO (d_src / d_dst / d_w stay owned by the caller; sources, out_degree and
+// source_weight_sum are host pointers).  Also used by flows.cu, which enumerates the CrossTimeGraph edges on device.
+int dge_graph_build_device(dge_ctx *ctx, int32_t nv, int64_t ne, const int32_t *d_src, const int32_t *d_dst,
+                           const double *d_w, int32_t ns, const int32_t *sources, const double *out_degree,
+                           const double *source_weight_sum, dge_graph **out) {
     *out = nullptr;
-    if (nv < 0 || ne < 0 || ns < 0) return dge_fail(ctx, DGE_E_INVALID, "dge_graph_build: negative size");
-    if (ne > 0 && (!src || !dst || !w)) return dge_fail(ctx, DGE_E_INVALID, "dge_graph_build: NULL edge arrays");
-    if (ns > 0 && !sources) return dge_fail(ctx, DGE_E_INVALID, "dge_graph_build: NULL source list");
     if (ne >= (int64_t)1 << 31) return dge_fail(ctx, DGE_E_LIMIT, "dge_graph_build: n_edges must be < 2^31");
     if (ne > 0 && nv == 0) return dge_fail(ctx, DGE_E_INVALID, "dge_graph_build: edges but no vertices");
     if (ns > ALIAS_BIG_MAX) return dge_fail(ctx, DGE_E_LIMIT, "dge_graph_build: more than 2^25 source vertices");
@@ -657,13 +673,9 @@ int dge_graph_build(dge_ctx *ctx, int32_t nv, int64_t ne, const int32_t *src, co
     DGE_CUDA(ctx, dge_malloc(ctx, &g->rec, (size_t)ne));
     DGE_CUDA(ctx, dge_malloc(ctx, &g->srec, (size_t)ns));
 
-    dev_tmp t_src(ctx), t_dst(ctx), t_w(ctx), t_deg(ctx), t_first(ctx), t_misc(ctx), t_tiles(ctx), t_perm(ctx);
-    int32_t *d_src, *d_dst, *d_deg;
-    double *d_w;
+    dev_tmp t_deg(ctx), t_first(ctx), t_misc(ctx), t_tiles(ctx), t_perm(ctx);
+    int32_t *d_deg;
     int64_t *d_first;
-    DGE_CUDA(ctx, dge_malloc(ctx, (int32_t **)&t_src.p, (size_t)ne)); d_src = (int32_t *)t_src.p;
-    DGE_CUDA(ctx, dge_malloc(ctx, (int32_t **)&t_dst.p, (size_t)ne)); d_dst = (int32_t *)t_dst.p;
-    DGE_CUDA(ctx, dge_malloc(ctx, (double **)&t_w.p, (size_t)ne)); d_w = (double *)t_w.p;
     DGE_CUDA(ctx, dge_malloc(ctx, (int32_t **)&t_deg.p, (size_t)nv + 1)); d_deg = (int32_t *)t_deg.p;
     DGE_CUDA(ctx, dge_malloc(ctx, (int64_t **)&t_first.p, (size_t)nv)); d_first = (int64_t *)t_first.p;
     // misc: [0] runs (u64), [1] bad (int), [2] nonempty (int)
@@ -673,13 +685,7 @@ int dge_graph_build(dge_ctx *ctx, int32_t nv, int64_t ne, const int32_t *src, co
     int32_t *d_nonempty = (int32_t *)(d_runs + 2);
     DGE_CUDA(ctx, cudaMemsetAsync(t_misc.p, 0, 4 * sizeof(unsigned long long), st));
     DGE_CUDA(ctx, cudaMemsetAsync(d_deg, 0, sizeof(int32_t) * ((size_t)nv + 1), st));
-    if (ne) {
-        DGE_CUDA(ctx, cudaMemcpyAsync(d_src, src, sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice, st));
-        DGE_CUDA(ctx, cudaMemcpyAsync(d_dst, dst, sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice, st));
-        DGE_CUDA(ctx, cudaMemcpyAsync(d_w, w, sizeof(double) * (size_t)ne, cudaMemcpyHostToDevice, st));
-    }
     if (ns) DGE_CUDA(ctx, cudaMemcpyAsync(g->sources, sources, sizeof(int32_t) * (size_t)ns, cudaMemcpyHostToDevice, st));
-
     const int T = 256;
     if (ne) {
         k_count<<<grid_for(ne, T, ctx->sm_count, 16), T, 0, st>>>(d_src, d_dst, ne, nv, d_deg, d_first, d_runs, d_bad);
@@ -776,6 +782,35 @@ int dge_graph_build(dge_ctx *ctx, int32_t nv, int64_t ne, const int32_t *src, co
     guard.g = nullptr;
     *out = g;
     return DGE_OK;
+}
+
+extern "C" {
+
+int dge_graph_build(dge_ctx *ctx, int32_t nv, int64_t ne, const int32_t *src, const int32_t *dst, const double *w,
+                    int32_t ns, const int32_t *sources, const double *out_degree, const double *source_weight_sum,
+                    dge_graph **out) {
+    if (!ctx) return dge_fail(nullptr, DGE_E_INVALID, "dge_graph_build: ctx is NULL");
+    if (!out) return dge_fail(ctx, DGE_E_INVALID, "dge_graph_build: out is NULL");
+    *out = nullptr;
+    if (nv < 0 || ne < 0 || ns < 0) return dge_fail(ctx, DGE_E_INVALID, "dge_graph_build: negative size");
+    if (ne > 0 && (!src || !dst || !w)) return dge_fail(ctx, DGE_E_INVALID, "dge_graph_build: NULL edge arrays");
+    if (ns > 0 && !sources) return dge_fail(ctx, DGE_E_INVALID, "dge_graph_build: NULL source list");
+    if (ne >= (int64_t)1 << 31) return dge_fail(ctx, DGE_E_LIMIT, "dge_graph_build: n_edges must be < 2^31");
+    DGE_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    dev_tmp t_src(ctx), t_dst(ctx), t_w(ctx);
+    DGE_CUDA(ctx, dge_malloc(ctx, (int32_t **)&t_src.p, (size_t)ne));
+    DGE_CUDA(ctx, dge_malloc(ctx, (int32_t **)&t_dst.p, (size_t)ne));
+    DGE_CUDA(ctx, dge_malloc(ctx, (double **)&t_w.p, (size_t)ne));
+    if (ne) {
+        dge_phase_timer t_h2d(ctx, "coo_h2d");
+        DGE_CUDA(ctx, cudaMemcpyAsync(t_src.p, src, sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice, st));
+        DGE_CUDA(ctx, cudaMemcpyAsync(t_dst.p, dst, sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice, st));
+        DGE_CUDA(ctx, cudaMemcpyAsync(t_w.p, w, sizeof(double) * (size_t)ne, cudaMemcpyHostToDevice, st));
+        t_h2d.stop();
+    }
+    return dge_graph_build_device(ctx, nv, ne, (const int32_t *)t_src.p, (const int32_t *)t_dst.p, (const double *)t_w.p, ns,
+                                  sources, out_degree, source_weight_sum, out);
 }
 
 int dge_graph_sizes(const dge_graph *g, int32_t *nv, int64_t *ne, int32_t *ns) {

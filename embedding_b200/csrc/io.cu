@@ -82,6 +82,77 @@ int dge_corpus_write_seq(const dge_corpus *c, const int32_t *label_layer, const 
     return DGE_OK;
 }
 
+// `.seq` reader: what FileSentenceIterator / LineSentenceIterator + DefaultTokenizerFactory hand to Word2Vec
+// (DeepWalk.java:47-59,70) when the corpus files already exist (checkInputFile :86-87,99-100 skips generation).
+int dge_corpus_read_seq(dge_ctx *ctx, const char *path, const int32_t *label_layer, const int32_t *label_region,
+                        int32_t n_ids, int position_prefix, dge_corpus **out) {
+    if (!ctx) return dge_fail(nullptr, DGE_E_INVALID, "dge_corpus_read_seq: ctx is NULL");
+    if (!out) return dge_fail(ctx, DGE_E_INVALID, "dge_corpus_read_seq: out is NULL");
+    *out = nullptr;
+    if (!path || n_ids < 0 || (n_ids > 0 && (!label_region || (!position_prefix && !label_layer))))
+        return dge_fail(ctx, DGE_E_INVALID, "dge_corpus_read_seq: NULL argument");
+    FILE *f = fopen(path, "rb");
+    if (!f) return dge_fail(ctx, DGE_E_IO, std::string("dge_corpus_read_seq: cannot open ") + path);
+    std::vector<char> buf;
+    {
+        char chunk[1 << 16];
+        size_t got;
+        while ((got = fread(chunk, 1, sizeof(chunk), f)) > 0) buf.insert(buf.end(), chunk, chunk + got);
+    }
+    bool read_ok = !ferror(f);
+    fclose(f);
+    if (!read_ok) return dge_fail(ctx, DGE_E_IO, std::string("dge_corpus_read_seq: read failed: ") + path);
+    // (layer, region) -> id; in position-prefix mode the first number of a token is the walk position, not a label
+    std::map<std::pair<int32_t, int32_t>, int32_t> ids;
+    for (int32_t i = 0; i < n_ids; i++) {
+        auto key = std::make_pair(position_prefix ? 0 : label_layer[i], label_region[i]);
+        if (!ids.emplace(key, i).second)
+            return dge_fail(ctx, DGE_E_INVALID, "dge_corpus_read_seq: duplicate label");
+    }
+    // pass 1: lines and the longest line
+    int64_t n_lines = 0;
+    int32_t L = 0, cur = 0;
+    bool in_tok = false;
+    for (size_t i = 0; i <= buf.size(); i++) {
+        char ch = i < buf.size() ? buf[i] : '\n';
+        if (ch == ' ' || ch == '\t' || ch == '\r' || ch == '\n') {
+            if (in_tok) { cur++; in_tok = false; }
+            if (ch == '\n') {
+                if (i < buf.size() || cur > 0) { n_lines++; if (cur > L) L = cur; }
+                cur = 0;
+            }
+        } else in_tok = true;
+    }
+    std::vector<int32_t> tok((size_t)n_lines * (size_t)L + 1, -1);
+    // pass 2: parse "<a>-<b>"
+    int64_t line = 0;
+    int32_t pos = 0;
+    size_t i = 0;
+    const size_t n = buf.size();
+    auto parse_int = [&](int32_t &v) -> bool {
+        bool neg = false;
+        if (i < n && buf[i] == '-') { neg = true; i++; }
+        if (i >= n || buf[i] < '0' || buf[i] > '9') return false;
+        int64_t x = 0;
+        while (i < n && buf[i] >= '0' && buf[i] <= '9') { x = x * 10 + (buf[i] - '0'); if (x > 2147483647LL) return false; i++; }
+        v = (int32_t)(neg ? -x : x);
+        return true;
+    };
+    while (i < n && line < n_lines) {
+        char ch = buf[i];
+        if (ch == '\n') { line++; pos = 0; i++; continue; }
+        if (ch == ' ' || ch == '\t' || ch == '\r') { i++; continue; }
+        int32_t a, b;
+        if (!parse_int(a) || i >= n || buf[i] != '-') return dge_fail(ctx, DGE_E_INVALID, "dge_corpus_read_seq: malformed token at line " + std::to_string(line + 1));
+        i++;
+        if (!parse_int(b)) return dge_fail(ctx, DGE_E_INVALID, "dge_corpus_read_seq: malformed token at line " + std::to_string(line + 1));
+        auto it = ids.find(std::make_pair(position_prefix ? 0 : a, b));
+        if (it == ids.end()) return dge_fail(ctx, DGE_E_INVALID, "dge_corpus_read_seq: unknown label at line " + std::to_string(line + 1));
+        tok[(size_t)line * L + pos++] = it->second;
+    }
+    return dge_corpus_from_tokens(ctx, tok.data(), n_lines, L, n_ids, out);
+}
+
 int dge_model_write_vec(const dge_model *m, const int32_t *label_layer, const int32_t *label_region, const char *path) {
     if (!m) return dge_fail(nullptr, DGE_E_INVALID, "dge_model_write_vec: model is NULL");
     dge_ctx *ctx = m->ctx;

@@ -57,6 +57,25 @@ class Flows:
             order = [pos[k] for k in java_hashmap_order(self.region_ids)]
         self.order = np.asarray(order, np.int32)
 
+    @classmethod
+    def from_trips(cls, region_ids, src_index, dst_index, start_hour, ctx=None, order=None):
+        """CommunityAreas.mapTripsIntoCommunities :55-103 / Tracts.mapTripsIntoTracts :71-102 after the host's
+        point-in-polygon lookup: the trips are counted into F on the device (dge_flows_add_trips)."""
+        ctx = ctx or default_context()
+        n = len(region_ids)
+        dev = abi.Flows(ctx, n)
+        dev.add_trips(src_index, dst_index, start_hour)
+        fl = cls(region_ids, dev.tensor(), order)
+        fl._dev = (ctx, dev)
+        return fl
+
+    def device(self, ctx):
+        """The same counts as a device tensor (uploaded once per ctx)."""
+        cached = getattr(self, "_dev", None)
+        if cached is None or cached[0] is not ctx or cached[1]._h is None:
+            self._dev = (ctx, abi.Flows(ctx, len(self.region_ids), self.F))
+        return self._dev[1]
+
     def slot_weights_ca(self, lo, hi):
         """CommunityArea.getFlowTo(dst, lo, hi) for all (src, dst): circular half-open [lo, hi)."""
         W = np.zeros(self.F.shape[::2], np.int64)
@@ -184,10 +203,14 @@ class LayeredGraph:
 
     @property
     def n_vertices(self):
+        if getattr(self, "_device_built", False):
+            return self._graph.nv
         return self._bulk[0] if self._bulk is not None else len(self._names)
 
     def initiateAliasTables(self):
         """LayeredGraph.initiateAliasTables :195-226 -> dge_graph_build (CSR + all alias tables on the GPU)."""
+        if getattr(self, "_device_built", False) and self._graph is not None:
+            return self                      # dge_crosstime_graph_build already built the tables
         if self._bulk is not None:
             nv, src, dst, w = self._bulk
         else:
@@ -296,14 +319,34 @@ class CrossTimeGraph(LayeredGraph):
         return g
 
     @classmethod
-    def constructGraph_tract(cls, flows, ctx=None):
-        """CrossTimeGraph.constructGraph_tract :25-52 (window [h, h+timeStep-1] inclusive)."""
+    def _construct_device(cls, flows, L, mode, intervals, ctx):
+        """Same graph, enumerated on the GPU from the device-resident flow tensor (dge_crosstime_graph_build):
+        slot sums, edges with w > 0 in (h, src, dst) order, first-appearance vertex ids, sources, CSR and alias
+        tables in one call -- nothing but names is produced on the host."""
+        ctx = ctx or default_context()
+        g = cls(ctx)
+        g._graph = flows.device(ctx).crosstime_graph(flows.order, L, mode, intervals)
+        vl, vr, so = g._graph.labels()
+        g.v_layer, g.v_region = vl, flows.region_ids[vr].astype(np.int32)
+        g._names = ["%d-%d" % (l, r) for l, r in zip(g.v_layer, g.v_region)]
+        g._ids = {nm: i for i, nm in enumerate(g._names)}
+        g.sourceVertices = [int(x) for x in so]
+        g._device_built = True
+        return g
+
+    @classmethod
+    def constructGraph_tract(cls, flows, ctx=None, on_device=False):
+        """CrossTimeGraph.constructGraph_tract :25-52 (window [h, h+timeStep-1] inclusive).
+        on_device=False enumerates the COO on the host (what a Java host would pass to dge_graph_build);
+        on_device=True leaves the whole construction to the GPU."""
         L = cls.numLayer
         time_step = 24 // L
+        if on_device:
+            return cls._construct_device(flows, L, 1, None, ctx)
         return cls._construct(flows, lambda h: flows.slot_weights_tract(h, h + time_step - 1), L, ctx)
 
     @classmethod
-    def constructGraph_CA(cls, flows, timeIntervals=None, ctx=None):
+    def constructGraph_CA(cls, flows, timeIntervals=None, ctx=None, on_device=False):
         """CrossTimeGraph.constructGraph_CA() :54-61 and constructGraph_CA(int[]) :68-95."""
         if timeIntervals is None:
             L = cls.numLayer
@@ -313,6 +356,8 @@ class CrossTimeGraph(LayeredGraph):
                 timeIntervals[i] = (i * time_step) % L
         cls.numLayer = len(timeIntervals) - 1           # :71
         ti = list(timeIntervals)
+        if on_device:
+            return cls._construct_device(flows, cls.numLayer, 0, ti, ctx)
         return cls._construct(flows, lambda h: flows.slot_weights_ca(ti[h], ti[h + 1]), cls.numLayer, ctx)
 
     @classmethod
@@ -321,9 +366,9 @@ class CrossTimeGraph(LayeredGraph):
         and returns (graph, device corpus) for the in-memory hand-off to DeepWalk."""
         LayeredGraph.numLayer = cls.numLayer             # :104 / :116
         if regionLevel == "tract":
-            g = cls.constructGraph_tract(flows, ctx)
+            g = cls.constructGraph_tract(flows, ctx, on_device=True)
         else:
-            g = cls.constructGraph_CA(flows, timeIntervals, ctx)
+            g = cls.constructGraph_CA(flows, timeIntervals, ctx, on_device=True)
         g.initiateAliasTables()
         corpus = g.sample(cls.numSamples, abi.SAMPLER_ALIAS, LayeredGraph.numLayer)
         if path is not None:

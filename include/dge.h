@@ -30,6 +30,7 @@ typedef struct dge_ctx dge_ctx;
 typedef struct dge_graph dge_graph;
 typedef struct dge_corpus dge_corpus;
 typedef struct dge_model dge_model;
+typedef struct dge_flows dge_flows;
 
 typedef enum {
     DGE_OK = 0,
@@ -78,6 +79,33 @@ int dge_comm_init(dge_ctx *ctx, int rank, int world, const void *id, size_t byte
 int dge_comm_shape(const dge_ctx *ctx, int *rank, int *world);
 void dge_comm_destroy(dge_ctx *ctx); /* also done by dge_destroy */
 int dge_comm_nccl_version(void);     /* 0 when NCCL cannot be loaded */
+
+/* ------------------------------------------------------------------ stage 0: flow records -> CrossTimeGraph
+ * The hourly flow counts of every region: the dense tensor F[src][hour 0..23][dst] int32 stands for the reference's
+ * per-region `taxiFlows: List<Map<dst, count>>` (CommunityAreas.java:220, Tracts.java:459).  Region INDICES
+ * (0..n_regions-1) are positions in the host's region-id array; the host keeps the ids and the geometry.
+ * F != NULL uploads counts (the deserialised CA-serialize-<year>.seq / tracts-serialize-<year>.seq maps,
+ * CommunityAreas.java:115-124, Tracts.java:115-125); F == NULL starts from zero.  Limit: n_regions <= 8192. */
+int dge_flows_create(dge_ctx *ctx, int32_t n_regions, const int32_t *F, dge_flows **out);
+/* Counting of CommunityAreas.mapTripsIntoCommunities :55-103 / Tracts.mapTripsIntoTracts :71-102 after the host's
+ * point-in-polygon lookup: per trip F[src][start hour][dst] += 1.  A trip with src or dst == -1 (outside every
+ * region) is ignored as in the reference. */
+int dge_flows_add_trips(dge_flows *f, int64_t n_trips, const int32_t *src_region, const int32_t *dst_region,
+                        const int32_t *start_hour);
+int dge_flows_tensor(const dge_flows *f, int32_t *F /* [n][24][n] */);
+void dge_flows_free(dge_flows *f);
+/* CrossTimeGraph.constructGraph_CA(int[]) :68-95 (mode 0; intervals[num_layer+1], slot h = circular half-open
+ * [intervals[h], intervals[h+1]) of CommunityArea.getFlowTo :240-245) and constructGraph_tract() :25-52 (mode 1;
+ * slot h = hours [h, h + 24/num_layer - 1] inclusive of Tract.getFlowTo Tracts.java:477-482), followed by
+ * initiateAliasTables :195-226, entirely on device: slot sums, the (h, src, dst) edge enumeration with w > 0, vertex
+ * ids by first appearance (LayeredGraph.addEdge :159-170), the layer-0 source list, CSR and alias tables.
+ * order[n_regions] = region indices in the host's HashMap iteration order (it defines edge and id order).
+ * The result is bit-identical to dge_graph_build on the COO the Java loops would produce. */
+int dge_crosstime_graph_build(const dge_flows *f, const int32_t *order, int32_t num_layer, int mode,
+                              const int32_t *intervals, dge_graph **out);
+/* Labels by vertex id of a graph built by dge_crosstime_graph_build: layer h and region index of "<h>-<region>";
+ * sources[n_sources] works for every graph.  Any pointer may be NULL. */
+int dge_graph_labels(const dge_graph *g, int32_t *v_layer, int32_t *v_region_index, int32_t *sources);
 
 /* ------------------------------------------------------------------ stage 1a: graph + alias tables
  * Stands under LayeredGraph.addEdge :157-174, addSourceVertex :180-189, initiateAliasTables :195-226
@@ -133,6 +161,13 @@ int dge_corpus_count_tokens(const dge_corpus *c, int64_t *n_tokens);
  * mode) and ignores label_layer.  append != 0 appends to an existing file. */
 int dge_corpus_write_seq(const dge_corpus *c, const int32_t *label_layer, const int32_t *label_region,
                          int position_prefix, const char *path, int append);
+/* Reads a `.seq` file back into a device corpus: what FileSentenceIterator / LineSentenceIterator +
+ * DefaultTokenizerFactory feed to Word2Vec when the corpus files already exist (DeepWalk.java:47-59,70; generation
+ * is skipped by checkInputFile :86-87,99-100).  Tokens "<layer>-<region>" are mapped to the id whose labels match;
+ * with position_prefix != 0 the first number is the walk position (spatial corpus) and only the region is matched.
+ * L = the longest line; shorter lines are -1 padded.  An unknown or malformed token is DGE_E_INVALID. */
+int dge_corpus_read_seq(dge_ctx *ctx, const char *path, const int32_t *label_layer, const int32_t *label_region,
+                        int32_t n_ids, int position_prefix, dge_corpus **out);
 void dge_corpus_free(dge_corpus *c);
 
 /* ------------------------------------------------------------------ stage 2: skip-gram

@@ -99,7 +99,7 @@ def test_two_rank_data_parallel_skipgram(dge_lib, tmp_path):
     s0, ids = m.vectors()
     assert np.array_equal(ids, r0["ids"])
     assert abs(int(r0["pairs"]) + int(r1["pairs"]) - m.pairs) < 0.02 * m.pairs
-    zeros = np.zeros(len(ids), np.int32)
+    zeros = np.zeros(nv, np.int32)
     la = ev.layers_from_model(s0, ids, zeros, np.arange(nv, dtype=np.int32))
     lb = ev.layers_from_model(r0["syn0"], r0["ids"], zeros, np.arange(nv, dtype=np.int32))
     lc = {0: (np.random.default_rng(0).standard_normal(s0.shape), la[0][1])}

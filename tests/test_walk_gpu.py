@@ -122,6 +122,17 @@ def test_corpus_roundtrip_relabel_and_seq_format(dge_lib, ctx, tmp_path):
     l2 = p2.read_text().split("\n")
     for row, line in zip(tok[:200], l2):
         assert line == " ".join("%d-%d" % (j, region[t]) for j, t in enumerate(row) if t >= 0)  # SpatialGraph.java:105-108
+    # read both files back (DeepWalk.learnEmbedding on existing .seq files, DeepWalk.java:47-59)
+    back = dge_lib.Corpus.read_seq(ctx, str(p), region, layer)
+    assert (back.n_walks, back.L, back.n_ids) == (1000, 7, 50) and np.array_equal(back.tokens(), tok)
+    back2 = dge_lib.Corpus.read_seq(ctx, str(p2), region, position_prefix=True)
+    assert np.array_equal(back2.tokens(), tok)
+    bad = tmp_path / "bad.seq"
+    bad.write_text("0-1000 3-9999\n")
+    with pytest.raises(dge_lib.DgeError):
+        dge_lib.Corpus.read_seq(ctx, str(bad), region, layer)          # unknown label
+    with pytest.raises(dge_lib.DgeError):
+        dge_lib.Corpus.read_seq(ctx, str(tmp_path / "missing.seq"), region, layer)
     # relabel into a (position, region-index) space
     c.relabel(np.arange(50, dtype=np.int32), 50 * 7, position_stride=50)
     got = c.tokens()
