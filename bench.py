@@ -45,12 +45,13 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kernel):
-    """dram bytes per launch from the committed ncu summary (profiles/traffic.json), or None."""
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` at this workload's launch size, from the
+    committed ncu capture (profiles/traffic.json: {workload: {kernel: {"bytes": ..., "source": ...}}}), or None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(kernel)
+            return json.load(open(p)).get(workload, {}).get(kernel, {}).get("bytes")
         except Exception:
             return None
     return None
@@ -381,7 +382,7 @@ def run_gpu_arm(args, w, rank, world, dist):
                   e2e=dict(value=e_tot_steps / e_t_walk, unit="steps/s", h2d_bytes_per_step=int(h2d_walk), d2h_bytes_per_step=int(d2h_walk),
                            includes="dge_graph_build from host COO + dge_walk + dge_corpus_tokens to pinned host"),
                   roofline=dict(bound="hbm", achieved=walk_ach, peak=peak, unit="GB/s", frac=walk_ach / peak,
-                                traffic=ncu_traffic("k_walk_alias"), bytes_per_unit=WALK_BYTES_PER_STEP, peak_source=peak_src,
+                                traffic=ncu_traffic(w["name"], "k_walk_alias"), bytes_per_unit=WALK_BYTES_PER_STEP, peak_source=peak_src,
                                 note=resident_note),
                   cpu_baseline=cpu["walk"] if cpu else None),
         sgns=dict(value=tot_pairs / t_sgns, unit="pairs/s", ms_per_step=t_sgns / args.steps * 1e3, kernel="k_sgns_items",
@@ -390,7 +391,7 @@ def run_gpu_arm(args, w, rank, world, dist):
                   e2e=dict(value=e_tot_pairs / e_t_sgns, unit="pairs/s", h2d_bytes_per_step=int(d2h_walk), d2h_bytes_per_step=int(d2h_sgns),
                            includes="dge_corpus_from_tokens from pinned host + dge_sgns_train + dge_model_vectors to host"),
                   roofline=dict(bound="hbm", achieved=sgns_ach, peak=peak, unit="GB/s", frac=sgns_ach / peak,
-                                traffic=ncu_traffic("k_sgns_items"), bytes_per_unit=sgns_bytes_per_pair(dim, neg),
+                                traffic=ncu_traffic(w["name"], "k_sgns_items"), bytes_per_unit=sgns_bytes_per_pair(dim, neg),
                                 peak_source=peak_src, note=resident_note),
                   cpu_baseline=cpu["sgns"] if cpu else None))
     share = sk_ms / (sk_ms + wk_ms)
@@ -401,7 +402,12 @@ def run_gpu_arm(args, w, rank, world, dist):
                             parallelism=("1 GPU" if world == 1 else "walk ids sharded by rank, no collective; SGNS data-parallel, NCCL all-reduce of summed embedding deltas"
                                          if data_parallel else "walk ids sharded by rank, no collective; SGNS replicas only"),
                             timing="CUDA events on the library stream per stage (dge_timer_start/stop), max over ranks"),
-                e2e=stages["walk"]["e2e"], roofline=stages["walk"]["roofline"], cpu_baseline=stages["walk"]["cpu_baseline"],
+                e2e=stages["walk"]["e2e"],
+                # roofline of the DOMINANT kernel of the step (the skip-gram item kernel, `share` of the step's kernel
+                # time); the walk kernel's own roofline is stages.walk.roofline
+                roofline=dict(stages["sgns"]["roofline"], kernel="k_sgns_items", share_of_step_kernel_time=share,
+                              units="SGNS pairs; the top-level value counts walk steps, see stages"),
+                cpu_baseline=stages["walk"]["cpu_baseline"],
                 clocks=clk, gpu_launches=int(launches), stages=stages,
                 dominant_kernel=dict(name="k_sgns_items", share_of_step_kernel_time=share),
                 published=dict(note="reference publishes walk wall times only (python/running_time.py:16-20; other hardware, includes "

@@ -82,6 +82,9 @@ def lib():
     L.dge_flows_create.argtypes = [vp, i32, pi32, P(vp)]
     L.dge_flows_add_trips.argtypes = [vp, i64, pi32, pi32, pi32]
     L.dge_flows_tensor.argtypes = [vp, pi32]
+    L.dge_flows_slot_weights.argtypes = [vp, C.c_int, i32, i32, pi32]
+    L.dge_flows_write_matrix.argtypes = [vp, C.c_int, i32, i32, pi32, i32, pi32, i32, C.c_char, C.c_char_p]
+    L.dge_flows_write_od.argtypes = [vp, C.c_int, i32, i32, pi32, i32, pi32, i32, pi32, C.c_int, i32, C.c_char_p]
     L.dge_flows_free.argtypes = [vp]
     L.dge_flows_free.restype = None
     L.dge_crosstime_graph_build.argtypes = [vp, pi32, i32, C.c_int, pi32, P(vp)]
@@ -223,6 +226,26 @@ class Flows:
         F = np.empty((self.n, 24, self.n), np.int32)
         _check(lib().dge_flows_tensor(self._h, _ptr(F, C.c_int32)), self.ctx._h)
         return F
+
+    def slot_weights(self, mode, lo, hi):
+        """W[src, dst] = getFlowTo(dst, lo, hi): mode 0 CA (circular, half-open), mode 1 tract (inclusive)."""
+        W = np.empty((self.n, self.n), np.int32)
+        _check(lib().dge_flows_slot_weights(self._h, int(mode), int(lo), int(hi), _ptr(W, C.c_int32)), self.ctx._h)
+        return W
+
+    def write_matrix(self, mode, lo, hi, rows, cols, sep, path):
+        r, c = np.ascontiguousarray(rows, np.int32), np.ascontiguousarray(cols, np.int32)
+        _check(lib().dge_flows_write_matrix(self._h, int(mode), int(lo), int(hi), _ptr(r, C.c_int32), len(r),
+                                            _ptr(c, C.c_int32), len(c), sep.encode(), os.fsencode(path)), self.ctx._h)
+
+    def write_od(self, mode, lo, hi, rows, cols, region_ids, path, keep_zero=False, presence_hour=-1):
+        r, c = np.ascontiguousarray(rows, np.int32), np.ascontiguousarray(cols, np.int32)
+        ids = np.ascontiguousarray(region_ids, np.int32)
+        if len(ids) != self.n:
+            raise ValueError("region_ids must have n_regions entries")
+        _check(lib().dge_flows_write_od(self._h, int(mode), int(lo), int(hi), _ptr(r, C.c_int32), len(r), _ptr(c, C.c_int32),
+                                        len(c), _ptr(ids, C.c_int32), int(bool(keep_zero)), int(presence_hour),
+                                        os.fsencode(path)), self.ctx._h)
 
     def crosstime_graph(self, order, num_layer, mode, intervals=None):
         """mode 0 = constructGraph_CA(intervals), mode 1 = constructGraph_tract(); returns a Graph with labels."""

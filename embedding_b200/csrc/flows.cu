@@ -101,6 +101,19 @@ __global__ void k_keys_to_ids(int32_t *__restrict__ skey, int32_t *__restrict__ 
     dkey[e] = vid[dkey[e]];
 }
 
+// W[a][b] = getFlowTo(b, lo, hi) of region a for all pairs (static exports); b fastest => coalesced.
+__global__ void k_slot_matrix(const int32_t *__restrict__ F, int32_t n, int mode, int32_t lo, int32_t hi,
+                              int32_t *__restrict__ W) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n * n) return;
+    int32_t b = (int32_t)(t % n), a = (int32_t)(t / n);
+    const int32_t *row = F + (int64_t)a * 24 * n + b;
+    int32_t cnt = 0;
+    if (mode == 0) for (int32_t x = lo; x != hi; x = (x + 1) % 24) cnt += row[(int64_t)x * n];
+    else for (int32_t x = lo; x <= hi; x++) cnt += row[(int64_t)x * n];
+    W[t] = cnt;
+}
+
 struct flows_tmp {
     dge_ctx *ctx;
     void *p = nullptr;
@@ -173,6 +186,26 @@ int dge_flows_tensor(const dge_flows *f, int32_t *F) {
     DGE_CUDA(ctx, cudaSetDevice(ctx->device));
     size_t total = (size_t)f->n * 24 * (size_t)f->n;
     if (total) DGE_CUDA(ctx, cudaMemcpyAsync(F, f->F, total * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    DGE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DGE_OK;
+}
+
+int dge_flows_slot_weights(const dge_flows *f, int mode, int32_t lo, int32_t hi, int32_t *W) {
+    if (!f) return dge_fail(nullptr, DGE_E_INVALID, "dge_flows_slot_weights: flows is NULL");
+    dge_ctx *ctx = f->ctx;
+    if (!W && f->n) return dge_fail(ctx, DGE_E_INVALID, "dge_flows_slot_weights: W is NULL");
+    if ((mode != 0 && mode != 1) || lo < 0 || lo > 23 || hi < 0 || hi > 23)
+        return dge_fail(ctx, DGE_E_INVALID, "dge_flows_slot_weights: mode must be 0 or 1 and the hours must lie in 0..23");
+    const int64_t cells = (int64_t)f->n * f->n;
+    if (!cells) return DGE_OK;
+    DGE_CUDA(ctx, cudaSetDevice(ctx->device));
+    flows_tmp t_W(ctx);
+    DGE_CUDA(ctx, dge_malloc(ctx, (int32_t **)&t_W.p, (size_t)cells));
+    dge_phase_timer t(ctx, "slot_weights");
+    k_slot_matrix<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(f->F, f->n, mode, lo, hi, (int32_t *)t_W.p);
+    DGE_LAUNCH_CHECK(ctx);
+    t.stop();
+    DGE_CUDA(ctx, cudaMemcpyAsync(W, t_W.p, sizeof(int32_t) * (size_t)cells, cudaMemcpyDeviceToHost, ctx->stream));
     DGE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return DGE_OK;
 }

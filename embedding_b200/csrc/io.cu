@@ -176,4 +176,83 @@ int dge_model_write_vec(const dge_model *m, const int32_t *label_layer, const in
     return DGE_OK;
 }
 
+// ---- static flow-graph exports for the LINE / matrix-factorisation baselines.  The slot sums are
+// computed on the device (dge_flows_slot_weights); formatting is the host's part, as in the Java loops.
+static int flows_export_args(const dge_flows *f, const int32_t *rows, int32_t n_rows, const int32_t *cols, int32_t n_cols,
+                             const char *path, const char *who) {
+    if (!f) return dge_fail(nullptr, DGE_E_INVALID, std::string(who) + ": flows is NULL");
+    if (!path || n_rows < 0 || n_cols < 0 || (n_rows && !rows) || (n_cols && !cols))
+        return dge_fail(f->ctx, DGE_E_INVALID, std::string(who) + ": NULL argument");
+    for (int32_t i = 0; i < n_rows; i++)
+        if (rows[i] < 0 || rows[i] >= f->n) return dge_fail(f->ctx, DGE_E_INVALID, std::string(who) + ": row index out of range");
+    for (int32_t i = 0; i < n_cols; i++)
+        if (cols[i] < 0 || cols[i] >= f->n) return dge_fail(f->ctx, DGE_E_INVALID, std::string(who) + ": column index out of range");
+    return DGE_OK;
+}
+
+int dge_flows_write_matrix(const dge_flows *f, int mode, int32_t lo, int32_t hi, const int32_t *rows, int32_t n_rows,
+                           const int32_t *cols, int32_t n_cols, char sep, const char *path) {
+    int rc = flows_export_args(f, rows, n_rows, cols, n_cols, path, "dge_flows_write_matrix");
+    if (rc != DGE_OK) return rc;
+    dge_ctx *ctx = f->ctx;
+    std::vector<int32_t> W((size_t)f->n * f->n + 1);
+    rc = dge_flows_slot_weights(f, mode, lo, hi, W.data());
+    if (rc != DGE_OK) return rc;
+    FILE *out = fopen(path, "wb");
+    if (!out) return dge_fail(ctx, DGE_E_IO, std::string("dge_flows_write_matrix: cannot open ") + path);
+    std::vector<char> line((size_t)n_cols * 12 + 2);
+    bool ok = true;
+    for (int32_t a = 0; a < n_rows && ok; a++) {
+        char *p = line.data();
+        const int32_t *w = W.data() + (size_t)rows[a] * f->n;
+        for (int32_t b = 0; b < n_cols; b++) {
+            if (b) *p++ = sep;
+            p = put_int(p, w[cols[b]]);
+        }
+        *p++ = '\n';
+        ok = fwrite(line.data(), 1, (size_t)(p - line.data()), out) == (size_t)(p - line.data());
+    }
+    if (fclose(out) != 0) ok = false;
+    if (!ok) return dge_fail(ctx, DGE_E_IO, std::string("dge_flows_write_matrix: write failed: ") + path);
+    return DGE_OK;
+}
+
+int dge_flows_write_od(const dge_flows *f, int mode, int32_t lo, int32_t hi, const int32_t *rows, int32_t n_rows,
+                       const int32_t *cols, int32_t n_cols, const int32_t *region_ids, int keep_zero,
+                       int32_t presence_hour, const char *path) {
+    int rc = flows_export_args(f, rows, n_rows, cols, n_cols, path, "dge_flows_write_od");
+    if (rc != DGE_OK) return rc;
+    dge_ctx *ctx = f->ctx;
+    if (!region_ids && f->n) return dge_fail(ctx, DGE_E_INVALID, "dge_flows_write_od: region_ids is NULL");
+    if (presence_hour > 23) return dge_fail(ctx, DGE_E_INVALID, "dge_flows_write_od: presence_hour must be < 24");
+    std::vector<int32_t> W((size_t)f->n * f->n + 1), P;
+    rc = dge_flows_slot_weights(f, mode, lo, hi, W.data());
+    if (rc == DGE_OK && presence_hour >= 0) {
+        P.resize((size_t)f->n * f->n + 1);
+        rc = dge_flows_slot_weights(f, 1, presence_hour, presence_hour, P.data());
+    }
+    if (rc != DGE_OK) return rc;
+    FILE *out = fopen(path, "wb");
+    if (!out) return dge_fail(ctx, DGE_E_IO, std::string("dge_flows_write_od: cannot open ") + path);
+    std::vector<char> buf((size_t)n_cols * 40 + 2);
+    bool ok = true;
+    for (int32_t a = 0; a < n_rows && ok; a++) {
+        char *p = buf.data();
+        const size_t base = (size_t)rows[a] * f->n;
+        for (int32_t b = 0; b < n_cols; b++) {
+            const int32_t w = W[base + cols[b]];
+            if (presence_hour >= 0 && P[base + cols[b]] <= 0) continue;
+            if (w <= 0 && !keep_zero) continue;
+            p = put_int(p, region_ids[rows[a]]); *p++ = ' ';
+            p = put_int(p, region_ids[cols[b]]); *p++ = ' ';
+            p = put_int(p, w); *p++ = '\n';
+        }
+        const size_t len = (size_t)(p - buf.data());
+        if (len) ok = fwrite(buf.data(), 1, len, out) == len;
+    }
+    if (fclose(out) != 0) ok = false;
+    if (!ok) return dge_fail(ctx, DGE_E_IO, std::string("dge_flows_write_od: write failed: ") + path);
+    return DGE_OK;
+}
+
 } // extern "C"

@@ -32,7 +32,9 @@ struct sgns_args {
     const int32_t *neg_table;
     const float *exp_table;
     float *syn0, *syn1neg;
-    int32_t V, dim, stride, window, negative, epochs, neg_table_size, exp_table_size, Lmax;
+    int32_t V, dim, stride, n4, window, negative, epochs, neg_table_size, exp_table_size, Lmax;
+    // stride = row pitch in floats, a multiple of 8 (rows start on 32-byte sector boundaries); n4 = ceil(dim/4)
+    // float4 slots carry data, the pad up to the pitch is never read or written
     float lr, min_lr;
     uint64_t seed;
     unsigned long long *pairs;
@@ -166,7 +168,7 @@ k_sgns_seq(const sgns_args a) {
     for (int i = threadIdx.x; i < a.exp_table_size; i += blockDim.x) s_exp[i] = a.exp_table[i];
     __syncthreads();
     const int64_t gid = (int64_t)blockIdx.x * gpb + gl;
-    const int n4 = a.stride >> 2;
+    const int n4 = a.n4;
     const int E = a.exp_table_size;
     const float idx_scale = (float)E / SGNS_MAX_EXP / 2.0f;
     const int win = a.window;
@@ -252,12 +254,14 @@ k_sgns_seq(const sgns_args a) {
 // contract without its failure mode on small vocabularies (DESIGN.md "SGNS schedule").
 // Items are taken in corpus order by a grid-stride loop, so n_groups bounds the sentences in flight.
 
-// x mod m for x < 2^48, m < 2^31, exact: one double multiply + fix-up instead of a 64-bit division
+// x mod m for x < 2^48, m < 2^30, exact: one double multiply + fix-up instead of a 64-bit division
 __device__ __forceinline__ uint32_t mod48(uint64_t x, uint32_t m, double inv_m) {
-    uint64_t q = (uint64_t)((double)x * inv_m);
-    int64_t r = (int64_t)(x - q * (uint64_t)m);
-    if (r < 0) r += m;
-    else if (r >= (int64_t)m) r -= m;
+    // q is floor(x/m) or one off (x < 2^48 is exact in a double, the product is off by < 1), so the remainder lies
+    // in (-m, 2m): for m < 2^30 the low 32 bits are enough
+    const uint64_t q = (uint64_t)((double)x * inv_m);
+    int32_t r = (int32_t)((uint32_t)x - (uint32_t)q * m);
+    if (r < 0) r += (int32_t)m;
+    else if (r >= (int32_t)m) r -= (int32_t)m;
     return (uint32_t)r;
 }
 // full 64-bit x mod m through three 48-bit steps
@@ -295,7 +299,7 @@ k_sgns_items(const sgns_args a) {
     // sector, no extra traffic) and its dot-product term is dropped; invalid work is cancelled through g = 0.
     // Loaded values are never masked or predicated: that makes ptxas consume each load before issuing the next,
     // whereas plain back-to-back loads keep K+1 rows in flight per lane.
-    const int n4 = a.stride >> 2;
+    const int n4 = a.n4;
     int slot[VPL];
     bool live[VPL];
 #pragma unroll
@@ -443,7 +447,7 @@ k_sgns_items_pipe(const sgns_args a) {
     const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const int K = a.V >= 2 ? a.negative : 0;
-    const int n4 = a.stride >> 2;
+    const int n4 = a.n4;
     const bool live = lane < n4;
     const int slot = live ? lane : 0;
     const bool drawer = lane < SGNS_CH && lane < K;
@@ -563,6 +567,211 @@ k_sgns_items_pipe(const sgns_args a) {
     if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Kernel C: the item kernel rebuilt around its measured limit.  ncu on the tract x 24 workload
+// (profiles/r1s3_sgns_tract24.json) showed k_sgns_items_pipe issue-bound (58 % issue slots busy, no memory stall):
+// ~600 warp instructions per 4 pairs, most of them integer / control overhead.  Same work decomposition, same
+// draws, same arithmetic per pair; what changed:
+//   * the K+1 dot products of a pair are reduced with ONE transposed butterfly (7 shuffles for up to 8 values over
+//     8 lanes, lane L ends with the total of value L) instead of K+1 separate butterflies (3 shuffles each);
+//   * lane L alone turns total L into its gradient scale g_L (one branch-free sigmoid-table lookup per lane instead
+//     of K+1 per lane) and the six g are broadcast back;
+//   * the per-pair hash of the negative stream is computed for G context positions at once (lane l: position
+//     c0 + l) and broadcast per pair, instead of G times redundantly per pair;
+//   * row addresses are 32-bit slot offsets from a per-lane base pointer (one IMAD.WIDE each);
+//   * the pipeline registers are ping-ponged by an unroll-by-two (no register rotation);
+//   * negatives > 5 are pipelined as further 5-wide chunks of the same pair (MULTI) instead of a serial tail;
+//   * a reduction whose g is exactly 0 (saturated sigmoid) is not sent.
+// Rows sit on a sector-aligned pitch (args.stride, multiple of 8 floats), so a row of D floats touches
+// ceil(D/8) sectors instead of one more on every other row.
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src, int width) {
+    uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src, width);
+    uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src, width);
+    return ((uint64_t)hi << 32) | lo;
+}
+// address of float4 slot `base` (a per-lane pointer into row 0) in row `row`: one 32 x 32 + 64-bit multiply-add
+__device__ __forceinline__ uint64_t row_addr(const char *base, uint32_t row, uint32_t pitch) {
+    uint64_t p;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(row), "r"(pitch), "l"(base));
+    return p;
+}
+// predicated 128-bit L2 reduction / load as single PTX statements (no branch around them).  The load keeps the
+// previous register contents where pred is false: the callers make stale (finite) values harmless through g = 0.
+__device__ __forceinline__ void red_add4_if(uint64_t p, const float4 &v, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+                 ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void ldcg4_into(float4 &r, uint64_t p, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+                 : "+f"(r.x), "+f"(r.y), "+f"(r.z), "+f"(r.w)
+                 : "l"(p), "r"((int)pred));
+}
+
+template <int G, bool MULTI, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_sgns_items_v2(const sgns_args a) {
+    static_assert(G == 8 || G == 16 || G == 32, "lane groups of 8, 16 or 32");
+    extern __shared__ int32_t smem[];
+    float *s_exp = reinterpret_cast<float *>(smem);
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int GPW = 32 / G;
+    const int lane = threadIdx.x % G;
+    const int gw = (threadIdx.x & 31) / G;
+    int32_t *mytok = smem + a.exp_table_size + (threadIdx.x / G) * a.Lmax;
+    for (int i = threadIdx.x; i < a.exp_table_size; i += blockDim.x) s_exp[i] = a.exp_table[i];
+    __syncthreads();
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int E = a.exp_table_size;
+    const float idx_scale = (float)E / SGNS_MAX_EXP / 2.0f;
+    const int win = a.window;
+    const int64_t N = a.n_sent;
+    const int Lmax = a.Lmax;
+    const int64_t item_lo = a.s_lo * Lmax, n_items = a.s_hi * Lmax; // items [item_lo, n_items) of this launch
+    const double inv_total = 1.0 / (double)((int64_t)a.epochs * N);
+    const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
+    const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int K = a.V >= 2 ? a.negative : 0;
+    const int NCH = MULTI ? max(1, (K + SGNS_CH - 1) / SGNS_CH) : 1; // 5-wide chunks of negatives per pair
+    const bool live = lane < a.n4;
+    const uint32_t pitch = (uint32_t)a.stride * 4u;           // bytes; V * pitch < 2^32 * 16 is checked by the host
+    const char *base0 = reinterpret_cast<const char *>(a.syn0) + (live ? lane : 0) * 16;
+    const char *base1 = reinterpret_cast<const char *>(a.syn1neg) + (live ? lane : 0) * 16;
+    // value index owned by this lane after the transposed reduction: negatives 0..4 of the chunk, 5 = positive
+    const int L8 = lane & 7;
+    const bool up4 = (lane & 4) != 0, up2 = (lane & 2) != 0, up1 = (lane & 1) != 0;
+    const float my_label = L8 == SGNS_CH ? 1.f : 0.f;
+    unsigned long long pairs = 0;
+
+    struct stage_t { int32_t last; bool act; uint64_t nsk; int32_t traw; int j; };
+    struct stage_r { int32_t last; bool act; int j; int32_t mine; int32_t tg[SGNS_CH]; float4 row[SGNS_CH]; float4 v0; };
+
+    for (int ep = a.ep_lo; ep < a.ep_hi; ep++) {
+        for (int64_t base = item_lo + warp_id * GPW; base < n_items; base += a.n_groups) { // warp-uniform trip count
+            const int64_t item = base + gw;
+            bool valid = item < n_items;
+            const int64_t s = valid ? item / Lmax : 0;
+            const int i = valid ? (int)(item - s * Lmax) : 0;
+            __syncwarp();
+            for (int j = lane; j < Lmax; j += G) mytok[j] = a.wtok[(int64_t)j * N + s];
+            __syncwarp();
+            const int32_t w1 = mytok[i];
+            valid = valid && w1 >= 0;
+            if (!__any_sync(FULL, valid)) continue;
+            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * N + s) * inv_total);
+            if (alpha < a.min_lr) alpha = a.min_lr;
+            const float g_hi = (my_label - 1.f) * alpha, g_lo = my_label * alpha; // saturated sigmoid: dot > 6, dot < -6
+            const uint64_t S = sgns_sentence_rng(a.seed, ep, s);
+            const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
+            // inclusive context range (SkipGram.skipGram); an invalid item gets the empty range
+            const int lo = valid ? i - win + b : 1, hi = valid ? i + win - b : 0;
+            float4 cur = zero4, d1 = zero4, neu = zero4, v0p = zero4;
+            ldcg4_into(cur, row_addr(base1, (uint32_t)w1, pitch), valid && live); // private copy of syn1neg[w1]
+            int npairs = 0;
+            int cT = 0, jT = 0;    // (context position, chunk) of the next unit the T stage hands out
+            uint64_t hc = 0;       // pair hash of context position (cT rounded down to G) + lane
+
+            auto stageT = [&]() { // which (pair, chunk) comes next; request its negatives' table entries
+                stage_t t;
+                t.j = jT;
+                t.last = cT < Lmax ? mytok[cT] : -1;
+                t.act = cT >= lo && cT <= hi && cT != i && t.last >= 0 && t.last != w1;
+                if ((cT & (G - 1)) == 0 && jT == 0) hc = sgns_pair_rng(S, i, cT + lane); // warp-uniform condition
+                const uint64_t ns0 = shfl64(hc, cT & (G - 1), G);
+                const int kk = jT * SGNS_CH + lane;      // this lane's negative of the pair (lanes 0..4 draw)
+                const bool drawer = lane < SGNS_CH && kk < K;
+                const int kc = drawer ? kk : 0;
+                t.nsk = a.lcg_a[kc] * ns0 + a.lcg_c[kc]; // the LCG is affine: state after kk+1 steps
+                t.traw = -2;                             // "draws nothing"
+                if (drawer && t.act) t.traw = a.neg_table[mod48(t.nsk >> 16, tsize, inv_tsize)];
+                if (MULTI) { if (++jT == NCH) { jT = 0; cT++; } }
+                else cT++;
+                return t;
+            };
+            auto stageR = [&](const stage_t &t, stage_r &r) { // resolve the negatives, request all rows of the unit
+                r.last = t.last; r.act = t.act; r.j = t.j;
+                int32_t tt = t.traw;
+                const bool redraw = tt != -2 && (tt <= 0 || tt >= a.V); // DL4J: target = r % (V-1) + 1
+                if (__any_sync(FULL, redraw)) {
+                    if (redraw) tt = (int32_t)mod64(t.nsk, vm1, inv_vm1) + 1;
+                }
+                r.mine = (tt != -2 && tt != w1) ? tt : -1;
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) r.tg[k] = __shfl_sync(FULL, r.mine, k, G);
+                if (!MULTI || t.j == 0) ldcg4_into(r.v0, row_addr(base0, (uint32_t)t.last, pitch), t.act && live);
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) ldcg4_into(r.row[k], row_addr(base1, (uint32_t)r.tg[k], pitch), r.tg[k] >= 0 && live);
+            };
+            auto compute = [&](const stage_r &r) {
+                if (!__any_sync(FULL, r.act)) return;
+                const bool first = !MULTI || r.j == 0;
+                if (first) { npairs += r.act; neu = zero4; }
+                if (MULTI && first) v0p = r.v0;
+                const float4 v0 = MULTI ? v0p : r.v0;
+                // ---- K+1 dot products, transposed reduction: lane L8 ends with the group total of value L8
+                float d0 = dot4(v0, r.row[0]), d1v = dot4(v0, r.row[1]), d2 = dot4(v0, r.row[2]), d3 = dot4(v0, r.row[3]);
+                float d4 = dot4(v0, r.row[4]), d5 = first ? dot4(v0, cur) : 0.f;
+                // offset 4: lanes with bit 2 clear keep values 0..3, the others keep 4..7 (6, 7 are empty)
+                float e0 = (up4 ? d4 : d0) + __shfl_xor_sync(FULL, up4 ? d0 : d4, 4);
+                float e1 = (up4 ? d5 : d1v) + __shfl_xor_sync(FULL, up4 ? d1v : d5, 4);
+                float e2 = (up4 ? 0.f : d2) + __shfl_xor_sync(FULL, up4 ? d2 : 0.f, 4);
+                float e3 = (up4 ? 0.f : d3) + __shfl_xor_sync(FULL, up4 ? d3 : 0.f, 4);
+                // offset 2: bit 1 clear keeps the lower two of its four
+                float f0 = (up2 ? e2 : e0) + __shfl_xor_sync(FULL, up2 ? e0 : e2, 2);
+                float f1 = (up2 ? e3 : e1) + __shfl_xor_sync(FULL, up2 ? e1 : e3, 2);
+                // offset 1
+                float tot = (up1 ? f1 : f0) + __shfl_xor_sync(FULL, up1 ? f0 : f1, 1);
+                if (G >= 16) tot += __shfl_xor_sync(FULL, tot, 8);
+                if (G >= 32) tot += __shfl_xor_sync(FULL, tot, 16);
+                // ---- lane L8 owns target L8: its gradient scale (libnd4j NegativeSampling, expTable sigmoid)
+                float g;
+                {
+                    const float f = (tot + SGNS_MAX_EXP) * idx_scale;
+                    const int idx = (int)f;
+                    const float sg = s_exp[min(max(idx, 0), E - 1)];
+                    g = (my_label - sg) * alpha;
+                    if (idx < 0 || idx >= E) g = 0.f;          // table index out of range: the aggregate skips the target
+                    if (tot > SGNS_MAX_EXP) g = g_hi;
+                    else if (tot < -SGNS_MAX_EXP) g = g_lo;
+                    const bool mine_ok = L8 < SGNS_CH ? r.mine >= 0 : (L8 == SGNS_CH && r.act && first);
+                    if (!mine_ok) g = 0.f;                      // lanes >= 8 of a wide group are never read
+                }
+                float gk[SGNS_CH + 1];
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) gk[k] = __shfl_sync(FULL, g, k, G);
+                gk[SGNS_CH] = first ? __shfl_sync(FULL, g, SGNS_CH, G) : 0.f;
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) {
+                    axpy4(neu, gk[k], r.row[k]);
+                    red_add4_if(row_addr(base1, (uint32_t)r.tg[k], pitch), scale4(gk[k], v0), gk[k] != 0.f && live && !(a.dbg & 1));
+                }
+                if (first) { // positive target: the item's private, always-current copy of syn1neg[w1]
+                    axpy4(neu, gk[SGNS_CH], cur);
+                    axpy4(d1, gk[SGNS_CH], v0);
+                    axpy4(cur, gk[SGNS_CH], v0);
+                }
+                red_add4_if(row_addr(base0, (uint32_t)r.last, pitch), neu, (!MULTI || r.j == NCH - 1) && r.act && live && !(a.dbg & 1));
+            };
+
+            stage_r rA, rB; // rows not (re)loaded keep stale finite values, cancelled by g = 0; start from zeros
+            rA.v0 = rB.v0 = zero4;
+#pragma unroll
+            for (int k = 0; k < SGNS_CH; k++) rA.row[k] = rB.row[k] = zero4;
+            stage_t t1 = stageT();
+            stageR(t1, rA);
+            t1 = stageT();
+            const int U = Lmax * NCH;
+            for (int u = 0; u < U; u += 2) { // ping-pong: no register rotation
+                stageR(t1, rB); t1 = stageT(); compute(rA);
+                stageR(t1, rA); t1 = stageT(); compute(rB);
+            }
+            red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, valid && live && !(a.dbg & 1));
+            pairs += (unsigned)npairs;
+        }
+    }
+    if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
+}
+
 // multi-GPU delta exchange (see dge_sgns_train): cur -= base  ...all-reduce(cur)...  base += cur; cur = base
 __global__ void k_delta_begin(float *__restrict__ c0, const float *__restrict__ b0, float *__restrict__ c1,
                               const float *__restrict__ b1, size_t n) {
@@ -593,7 +802,7 @@ struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq,
 // Kernel A (exact order): rows of up to 8 float4 slots are held by ONE thread; wider rows give each lane of a
 // 16- or 32-lane group one 128-bit slot (2 or 4 for rows wider than 32 slots).
 // Kernel B (items): groups of 8 / 16 / 32 lanes, one slot per lane (2 or 4 beyond 32 slots).
-static bool pick_variant(int n4, sgns_variant *out) {
+static bool pick_variant(int n4, int negative, bool legacy_items, bool occ3, sgns_variant *out) {
     if (n4 > 128) return false;
     sgns_kernel_t seq = nullptr, items = nullptr;
     int Gs = 1, Vs = 1;
@@ -612,9 +821,10 @@ static bool pick_variant(int n4, sgns_variant *out) {
         default: seq = k_sgns_seq<32, 4>; Gs = 32; Vs = 4; break;
     }
     int Gi, Vi = 1;
-    if (n4 <= 8) { Gi = 8; items = k_sgns_items_pipe<8>; }
-    else if (n4 <= 16) { Gi = 16; items = k_sgns_items_pipe<16>; }
-    else if (n4 <= 32) { Gi = 32; items = k_sgns_items_pipe<32>; }
+    const bool multi = negative > SGNS_CH; // more than one 5-wide chunk of negatives per pair
+    if (n4 <= 8) { Gi = 8; items = legacy_items ? k_sgns_items_pipe<8> : multi ? (occ3 ? k_sgns_items_v2<8, true, 3> : k_sgns_items_v2<8, true, 4>) : (occ3 ? k_sgns_items_v2<8, false, 3> : k_sgns_items_v2<8, false, 4>); }
+    else if (n4 <= 16) { Gi = 16; items = legacy_items ? k_sgns_items_pipe<16> : multi ? (occ3 ? k_sgns_items_v2<16, true, 3> : k_sgns_items_v2<16, true, 4>) : (occ3 ? k_sgns_items_v2<16, false, 3> : k_sgns_items_v2<16, false, 4>); }
+    else if (n4 <= 32) { Gi = 32; items = legacy_items ? k_sgns_items_pipe<32> : multi ? (occ3 ? k_sgns_items_v2<32, true, 3> : k_sgns_items_v2<32, true, 4>) : (occ3 ? k_sgns_items_v2<32, false, 3> : k_sgns_items_v2<32, false, 4>); }
     else if (n4 <= 64) { Gi = 32; Vi = 2; items = k_sgns_items<32, 2>; }
     else { Gi = 32; Vi = 4; items = k_sgns_items<32, 4>; }
     out->G_seq = Gs; out->VPL_seq = Vs; out->seq = seq;
@@ -660,10 +870,12 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         Lmax = std::max(Lmax, corpora[i]->L);
         n_sent += corpora[i]->n;
     }
-    const int32_t n4 = (p->dim + 3) / 4;   // rows are zero-padded to whole float4 slots
-    const int32_t stride = n4 * 4;
+    const int32_t n4 = (p->dim + 3) / 4;        // float4 slots that carry data (zero-padded to whole slots)
+    const int32_t stride = ((p->dim + 7) / 8) * 8; // row pitch in floats: rows start on 32-byte sector boundaries
+    const int dbg = getenv("DGE_SGNS_DEBUG") ? atoi(getenv("DGE_SGNS_DEBUG")) : 0; // 1: no reductions, 2: previous item kernel, 4: 3 blocks/SM build, 8: item kernel on ONE warp (tests)
     sgns_variant var;
-    if (!pick_variant(n4, &var)) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: dim must be <= 512");
+    if (!pick_variant(n4, p->negative, (dbg & 2) != 0, (dbg & 4) != 0, &var)) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: dim must be <= 512");
+    if (p->neg_table_size >= (1 << 30)) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: neg_table_size must be < 2^30");
     DGE_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
 
@@ -782,10 +994,10 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         a.wtok = d_wtok; a.n_sent = n_sent;
         a.neg_table = d_table; a.exp_table = d_exp;
         a.syn0 = m->syn0; a.syn1neg = m->syn1neg;
-        a.V = V; a.dim = p->dim; a.stride = stride; a.window = p->window; a.negative = p->negative; a.epochs = p->epochs;
+        a.V = V; a.dim = p->dim; a.stride = stride; a.n4 = n4; a.window = p->window; a.negative = p->negative; a.epochs = p->epochs;
         a.neg_table_size = p->neg_table_size; a.exp_table_size = p->exp_table_size; a.Lmax = Lmax;
         a.lr = p->lr; a.min_lr = p->min_lr; a.seed = p->seed; a.pairs = d_pairs;
-        a.dbg = getenv("DGE_SGNS_DEBUG") ? atoi(getenv("DGE_SGNS_DEBUG")) : 0;
+        a.dbg = dbg;
 
         // ---- schedule
         //  concurrency 1            : kernel A, one group: the oracle's sequential order (parity tests)
@@ -818,6 +1030,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         if (p->concurrency > 0) want = sequential ? (int64_t)p->concurrency : (int64_t)p->concurrency * Lmax;
         else if (sequential) want = full_groups;
         else want = std::min<int64_t>(full_groups, std::max<int64_t>(gpb, (int64_t)SGNS_STALE_BOUND * V / (p->negative + 1)));
+        if (!sequential && (dbg & 8)) want = 1; // one warp: items strictly in corpus order (arithmetic check against the oracle)
         want = std::max<int64_t>(1, std::min(want, units));
         while (threads > 32 && threads > G && want < (int64_t)ctx->sm_count * gpb) { threads >>= 1; gpb = threads / G; }
         if (sequential && want < gpb) { gpb = (int)want; threads = gpb * G; } // kernel B keeps whole warps

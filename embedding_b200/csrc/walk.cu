@@ -8,19 +8,21 @@
 // The unseeded shared java.util.Random (:14) is replaced by a counter-based Philox4x32-10 stream
 // per walk, so output is reproducible and independent of how walks are split over GPUs.
 //
-// Layout: one thread per walk; a step is ONE dependent 32-byte load (dge_edge_rec, a full DRAM
+// Layout: one thread per walk; a step is ONE dependent 32-byte (256-bit) load (dge_edge_rec, a full DRAM
 // sector) because the record carries the CSR row of both possible destinations.  Tokens are
 // stored position-major [L][n] so every store instruction of a warp is one 128 B line.
 #include "dge_internal.cuh"
 
 __device__ __forceinline__ dge_edge_rec ld_rec(const dge_edge_rec *p) {
-    // two 128-bit read-only loads of the same sector
-    const uint4 *q = reinterpret_cast<const uint4 *>(p);
-    uint4 a = __ldg(q), b = __ldg(q + 1);
+    // ONE 256-bit read-only load of the record's sector (sm_100 LDG.256): the L2-resident configs are bound by L1
+    // request throughput (ncu: l1tex 97 % busy with two 128-bit requests per step), so one request per step it is.
+    // Records are 32 bytes and 32-byte aligned (dge_edge_rec, arrays from the pool are 256-byte aligned).
+    unsigned long long a, b, c, d;
+    asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
     dge_edge_rec r;
-    r.prob = __hiloint2double((int)a.y, (int)a.x);
-    r.dst = (int32_t)a.z; r.adst = (int32_t)a.w;
-    r.start0 = b.x; r.deg0 = b.y; r.start1 = b.z; r.deg1 = b.w;
+    r.prob = __longlong_as_double((long long)a);
+    r.dst = (int32_t)(uint32_t)b; r.adst = (int32_t)(uint32_t)(b >> 32);
+    r.start0 = (uint32_t)c; r.deg0 = (uint32_t)(c >> 32); r.start1 = (uint32_t)d; r.deg1 = (uint32_t)(d >> 32);
     return r;
 }
 

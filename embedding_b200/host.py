@@ -90,6 +90,61 @@ class Flows:
         return self.F[:, lo:hi + 1, :].sum(axis=1, dtype=np.int64)
 
 
+    # ---- static flow-graph exports for the LINE / matrix baselines.  `out_dir` stands for the
+    # reference's "../miscs/<year>"; file names, separators, loop bounds and the hour ranges are the Java ones.
+    # The slot sums run on the device (dge_flows_slot_weights); ctx defaults to default_context().
+
+    def _by_id(self, ids):
+        pos = {int(r): i for i, r in enumerate(self.region_ids)}
+        return np.array([pos[int(i)] for i in ids], np.int32)
+
+    def outputStaticFlowGraph(self, out_dir, ctx=None):
+        """CommunityAreas.outputStaticFlowGraph :127-145: taxi-CA-static.matrix (',' joined) and taxi-CA-static.od
+        (w > 0) over ids 1..n with getFlowTo(j, 0, 23) -- circular half-open, i.e. hours 0..22 as in the reference."""
+        dev = self.device(ctx or default_context())
+        idx = self._by_id(range(1, len(self.region_ids) + 1))
+        dev.write_matrix(0, 0, 23, idx, idx, ",", os.path.join(out_dir, "taxi-CA-static.matrix"))
+        dev.write_od(0, 0, 23, idx, idx, self.region_ids, os.path.join(out_dir, "taxi-CA-static.od"))
+
+    def outputAdjacencyMatrix_CA(self, out_dir, ctx=None):
+        """CommunityAreas.outputAdjacencyMatrix :147-164: taxi-CA-h<hour>.matrix, ' ' joined, single-hour flows."""
+        dev = self.device(ctx or default_context())
+        idx = self._by_id(range(1, len(self.region_ids) + 1))
+        for hour in range(24):
+            dev.write_matrix(1, hour, hour, idx, idx, " ", os.path.join(out_dir, "taxi-CA-h%d.matrix" % hour))
+
+    def outputEdgeGraph_LINE(self, out_dir, ctx=None):
+        """CommunityAreas.outputEdgeGraph_LINE :169-184: taxi-CA-h<hour>.od with every (i, j) pair, zeros included;
+        the Java inner loop runs `j < communities.size()`, so the last destination id is never written."""
+        dev = self.device(ctx or default_context())
+        n = len(self.region_ids)
+        idx = self._by_id(range(1, n + 1))
+        for hour in range(24):
+            dev.write_od(1, hour, hour, idx, idx[:n - 1], self.region_ids, os.path.join(out_dir, "taxi-CA-h%d.od" % hour),
+                         keep_zero=True)
+
+    def outputEdgeFile(self, out_dir, numTimeSlot=8, ctx=None):
+        """Tracts.outputEdgeFile :236-260: taxi-h<h>.od per time slot (sources in HashMap iteration order, destinations
+        = those with a trip in hour h itself, weight = getFlowTo(dst, h, h+timeStep-1) > 0) and taxi-all.od (hours
+        0..23).  Destinations of one source are written in the host's region iteration order; the reference uses the
+        per-hour HashMap<Integer,Integer> key order, which depends on trip arrival order (consumers are order-free)."""
+        dev = self.device(ctx or default_context())
+        timeStep = 24 // numTimeSlot
+        for h in range(numTimeSlot):
+            dev.write_od(1, h, h + timeStep - 1, self.order, self.order, self.region_ids,
+                         os.path.join(out_dir, "taxi-h%d.od" % h), presence_hour=h)
+        dev.write_od(1, 0, 23, self.order, self.order, self.region_ids, os.path.join(out_dir, "taxi-all.od"))
+
+    def outputAdjacencyMatrix_tract(self, out_dir, numTimeSlot=8, ctx=None):
+        """Tracts.outputAdjacencyMatrix :265-301: taxi-h<h>.matrix per slot and taxi-all.matrix, ids sorted, ',' joined."""
+        dev = self.device(ctx or default_context())
+        idx = self._by_id(sorted(int(r) for r in self.region_ids))
+        timeStep = 24 // numTimeSlot
+        for h in range(numTimeSlot):
+            dev.write_matrix(1, h, h + timeStep - 1, idx, idx, ",", os.path.join(out_dir, "taxi-h%d.matrix" % h))
+        dev.write_matrix(1, 0, 23, idx, idx, ",", os.path.join(out_dir, "taxi-all.matrix"))
+
+
 class Vertex:
     """View of LayeredGraph.Vertex (LayeredGraph.java:29-133) after initiateAliasTables()."""
 

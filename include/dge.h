@@ -94,6 +94,27 @@ int dge_flows_add_trips(dge_flows *f, int64_t n_trips, const int32_t *src_region
                         const int32_t *start_hour);
 int dge_flows_tensor(const dge_flows *f, int32_t *F /* [n][24][n] */);
 void dge_flows_free(dge_flows *f);
+/* Slot weights of every (src, dst) pair: W[src * n + dst] = getFlowTo(dst, lo, hi) of region src, by region index.
+ * mode 0 = CommunityArea.getFlowTo CommunityAreas.java:240-245 (hours lo, lo+1, ... circular, stopping BEFORE hi: the
+ * call getFlowTo(j, 0, 23) of outputStaticFlowGraph :133 therefore leaves hour 23 out, as the reference does);
+ * mode 1 = Tract.getFlowTo Tracts.java:477-482 (hours lo..hi inclusive; lo == hi is the single-hour
+ * getFlowTo(dst, hour) :236 / Tracts.java:474). */
+int dge_flows_slot_weights(const dge_flows *f, int mode, int32_t lo, int32_t hi, int32_t *W);
+/* The static-graph exports that feed the LINE / matrix-factorisation baselines.  Rows / sources
+ * are visited in rows[0..n_rows), columns / destinations in cols[0..n_cols) (region indices; the host passes ids
+ * 1..77, the sorted tract ids or its HashMap iteration order as the Java loops do).
+ *   dge_flows_write_matrix: one line per row, the weights joined by `sep` -- CommunityAreas.outputStaticFlowGraph
+ *     :129-144 (','), outputAdjacencyMatrix :147-164 (' '), Tracts.outputAdjacencyMatrix :265-301 (',').
+ *   dge_flows_write_od: one line "<src id> <dst id> <w>" per pair -- CommunityAreas.outputStaticFlowGraph :130,136-137
+ *     (w > 0 only), outputEdgeGraph_LINE :169-184 (keep_zero != 0, and the Java loop's `j < size` drops the last
+ *     column: the host passes n_cols = 76), Tracts.outputEdgeFile :236-260.  presence_hour >= 0 visits only the
+ *     destinations with a trip in that single hour (Tracts.java:243 iterates taxiFlows.get(h).keySet()).
+ *     region_ids[n] are the printed ids. */
+int dge_flows_write_matrix(const dge_flows *f, int mode, int32_t lo, int32_t hi, const int32_t *rows, int32_t n_rows,
+                           const int32_t *cols, int32_t n_cols, char sep, const char *path);
+int dge_flows_write_od(const dge_flows *f, int mode, int32_t lo, int32_t hi, const int32_t *rows, int32_t n_rows,
+                       const int32_t *cols, int32_t n_cols, const int32_t *region_ids, int keep_zero,
+                       int32_t presence_hour, const char *path);
 /* CrossTimeGraph.constructGraph_CA(int[]) :68-95 (mode 0; intervals[num_layer+1], slot h = circular half-open
  * [intervals[h], intervals[h+1]) of CommunityArea.getFlowTo :240-245) and constructGraph_tract() :25-52 (mode 1;
  * slot h = hours [h, h + 24/num_layer - 1] inclusive of Tract.getFlowTo Tracts.java:477-482), followed by

@@ -203,6 +203,18 @@ def java8_stream_sum(v):
     return lib().ora_java8_stream_sum(_p(v, C.c_double), len(v))
 
 
+def flow_ca(F, src, dst, lo, hi):
+    """CommunityArea.getFlowTo(dst, lo, hi) CommunityAreas.java:240-245 over the dense F[n, 24, n]."""
+    F = np.ascontiguousarray(F, np.int32)
+    return int(lib().ora_flow_ca(_p(F, C.c_int32), F.shape[0], int(src), int(dst), int(lo), int(hi)))
+
+
+def flow_tract(F, src, dst, lo, hi):
+    """Tract.getFlowTo(dst, lo, hi) Tracts.java:477-482."""
+    F = np.ascontiguousarray(F, np.int32)
+    return int(lib().ora_flow_tract(_p(F, C.c_int32), F.shape[0], int(src), int(dst), int(lo), int(hi)))
+
+
 def crosstime_edges(F, order, L, mode, intervals=None):
     """CrossTimeGraph.constructGraph_CA(int[]) (mode 0) / constructGraph_tract() (mode 1)."""
     F = np.ascontiguousarray(F, np.int32)

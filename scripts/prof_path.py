@@ -22,7 +22,7 @@ def main():
     else:
         n_walks = int(sys.argv[2])
         conc = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-        ids, z, L, dim = synth.tract_ids(), synth.poi_latents(), 8, 20
+        ids, z, L, dim = synth.tract_ids(), synth.poi_latents(), (24 if level == "tract24" else 8), 20
         fl = host.Flows(ids, synth.planted_flow_tensor(z))
         host.CrossTimeGraph.numLayer = L
         gh = host.CrossTimeGraph.constructGraph_tract(fl, ctx=ctx)

@@ -113,3 +113,56 @@ def test_host_mirror_device_path_equals_host_enumeration(dge_lib, ctx):
     fl2 = host.Flows.from_trips(ids, np.repeat(s, reps), np.repeat(d, reps), np.repeat(h, reps), ctx=ctx)
     assert np.array_equal(fl2.F, F)
     host.CrossTimeGraph.numLayer = 8
+
+
+def test_static_exports_match_the_java_loops(dge_lib, oracle, ctx, tmp_path):
+    """the .matrix / .od exports (CommunityAreas.java:127-184, Tracts.java:236-301) written from the
+    device slot sums equal a literal restatement of the Java loops over the oracle's getFlowTo, byte for byte."""
+    from embedding_b200 import host, synth
+    n = 13
+    ids = np.arange(1, n + 1, dtype=np.int32)                    # community-area ids are 1..n
+    F = synth.flow_tensor(n, seed=21, density=0.4)
+    fl = host.Flows(ids[::-1].copy(), F)                          # ids stored in another order than 1..n
+    pos = {int(r): i for i, r in enumerate(fl.region_ids)}
+    ca = lambda i, j, lo, hi: oracle.flow_ca(F, pos[i], pos[j], lo, hi)
+    hour = lambda i, j, h: int(F[pos[i], h, pos[j]])
+    d = str(tmp_path)
+    fl.outputStaticFlowGraph(d, ctx)
+    rows, od = [], []
+    for i in range(1, n + 1):
+        w = [ca(i, j, 0, 23) for j in range(1, n + 1)]
+        rows.append(",".join(map(str, w)) + "\n")
+        od += ["%d %d %d\n" % (i, j, w[j - 1]) for j in range(1, n + 1) if w[j - 1] > 0]
+    assert open(d + "/taxi-CA-static.matrix").read() == "".join(rows)
+    assert open(d + "/taxi-CA-static.od").read() == "".join(od)
+    assert sum(ca(i, j, 0, 23) for i in range(1, n + 1) for j in range(1, n + 1)) == int(F[:, :23, :].sum())  # hour 23 left out
+    fl.outputAdjacencyMatrix_CA(d, ctx)
+    fl.outputEdgeGraph_LINE(d, ctx)
+    for h in (0, 7, 23):
+        ref = "".join(" ".join(str(hour(i, j, h)) for j in range(1, n + 1)) + "\n" for i in range(1, n + 1))
+        assert open(d + "/taxi-CA-h%d.matrix" % h).read() == ref
+        ref = "".join("%d %d %d\n" % (i, j, hour(i, j, h)) for i in range(1, n + 1) for j in range(1, n))
+        assert open(d + "/taxi-CA-h%d.od" % h).read() == ref
+    # tract level
+    tids = synth.tract_ids()[:40]
+    Ft = synth.flow_tensor(len(tids), seed=22, density=0.2)
+    ft = host.Flows(tids, Ft)
+    tp = {int(r): i for i, r in enumerate(tids)}
+    tr = lambda a, b, lo, hi: oracle.flow_tract(Ft, a, b, lo, hi)
+    ft.outputEdgeFile(d, 8, ctx)
+    ft.outputAdjacencyMatrix_tract(d, 8, ctx)
+    for h in (0, 5, 7):
+        ref = []
+        for a in ft.order:                                       # tracts.values(): HashMap iteration order
+            for b in ft.order:                                   # keySet of hour h: destinations with a trip in hour h
+                if Ft[a, h, b] > 0 and tr(a, b, h, h + 2) > 0:
+                    ref.append("%d %d %d\n" % (tids[a], tids[b], tr(a, b, h, h + 2)))
+        assert open(d + "/taxi-h%d.od" % h).read() == "".join(ref)
+        srt = sorted(int(r) for r in tids)
+        ref = "".join(",".join(str(tr(tp[a], tp[b], h, h + 2)) for b in srt) + "\n" for a in srt)
+        assert open(d + "/taxi-h%d.matrix" % h).read() == ref
+    ref = "".join("%d %d %d\n" % (tids[a], tids[b], tr(a, b, 0, 23)) for a in ft.order for b in ft.order if tr(a, b, 0, 23) > 0)
+    assert open(d + "/taxi-all.od").read() == ref
+    assert np.array_equal(ft.device(ctx).slot_weights(1, 0, 23), Ft.sum(axis=1))
+    with pytest.raises(dge_lib.DgeError):
+        ft.device(ctx).slot_weights(1, 0, 24)

@@ -89,6 +89,43 @@ def test_parallel_schedule_learns_the_same_structure(dge_lib, oracle, ctx, dim):
     assert g_gpu > 0.5 * g_ref, (g_gpu, g_ref)
 
 
+@pytest.mark.parametrize("dim,negative", [(8, 5), (20, 5), (20, 12), (64, 5), (100, 7), (128, 5), (128, 20)])
+def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negative, monkeypatch):
+    """The throughput kernel (work item = (sentence, centre), 128-bit L2 reductions, software pipeline) enumerates
+    the oracle's pairs and negatives and applies the same update arithmetic; only the interleaving differs.
+    Run on ONE warp (DGE_SGNS_DEBUG=8: items strictly in corpus order, at most 4 centres of one sentence in
+    lockstep) the interleaving is almost the oracle's, so the learned change of both tables must agree with the
+    sequential oracle to ~1 %: any slip in the dot products, the sigmoid table, the negative draws or the row
+    addressing is an O(1) error here.  With sentences in flight the deviation grows like sqrt(stale fraction)."""
+    rng = np.random.default_rng(100 + dim + negative)
+    n_ids = 3000
+    tok = rng.integers(0, n_ids, size=(500, 12)).astype(np.int32)
+    tok[rng.random(tok.shape) < 0.1] = -1
+    tok[:, 0] = np.maximum(tok[:, 0], 0)
+    kw = dict(dim=dim, window=6, negative=negative, min_count=1, seed=23)
+    ref = oracle.sgns_train(tok, n_ids, oracle.sgns_params(threads=1, **kw))
+    init = oracle.init_syn0(len(ref["id_of_word"]), dim, 23)
+    learned0 = np.linalg.norm(ref["syn0"] - init)
+    learned1 = np.linalg.norm(ref["syn1neg"])
+    assert learned0 > 0 and learned1 > 0
+    c = dge_lib.Corpus.from_tokens(ctx, tok, n_ids)
+
+    def rel_err(**p):
+        m = dge_lib.Model.train(ctx, [c], dge_lib.sgns_params(**p, **kw))
+        syn0, syn1, ids = m.vectors(want_syn1neg=True)
+        assert m.pairs == ref["pairs"] and np.array_equal(ids, ref["id_of_word"])
+        return np.linalg.norm(syn0 - ref["syn0"]) / learned0, np.linalg.norm(syn1 - ref["syn1neg"]) / learned1
+
+    monkeypatch.setenv("DGE_SGNS_DEBUG", "8")
+    e0, e1 = rel_err()
+    assert e0 < 0.05 and e1 < 0.05, (e0, e1)
+    monkeypatch.delenv("DGE_SGNS_DEBUG")
+    e0, e1 = rel_err(concurrency=2)                 # two sentences in flight
+    assert e0 < 0.35 and e1 < 0.35, (e0, e1)
+    e0, e1 = rel_err()                              # automatic full-GPU schedule
+    assert e0 < 0.7 and e1 < 0.7, (e0, e1)
+
+
 def test_vec_file_format(dge_lib, ctx, tmp_path):
     """WordVectorSerializer.writeWordVectors as its consumers read it (embeddingEvaluation_tract.py:139-166,
     skipheader=0): "<layer>-<region> v1 ... vD", one line per vocabulary word."""
