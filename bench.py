@@ -374,8 +374,12 @@ def run_gpu_arm(args, w, rank, world, dist):
     pairs_per_launch = float(np.mean(sg_pairs))
     walk_ach = steps_per_launch * WALK_BYTES_PER_STEP / (wk_ms * 1e-3) / 1e9
     sgns_ach = pairs_per_launch * sgns_bytes_per_pair(dim, neg) / (sk_ms * 1e-3) / 1e9
-    resident_note = ("graph and embedding tables are L2-resident at this size; HBM is not the binding limit (SURVEY 8(d))"
-                     if w["name"] != "synth100k" else "graph and tables stream from HBM")
+    resident_note = ("graph and embedding tables are L2-resident at this size; HBM is not the binding limit (SURVEY 8(d)); the "
+                     "binding limit of the item kernel is the L2's 128-bit reduction throughput: 34.5 G rows/s load+reduce "
+                     "for this access shape (scripts/red_microbench.cu, profiles/r1s7_red_microbench.txt) = 5.76 G pairs/s"
+                     if w["name"] != "synth100k" else
+                     "tables are 1.2 GB each, but the walk corpus is skewed: most row traffic hits L2 (ncu: 82 % hit rate), so "
+                     "algorithmic bytes/s can exceed the HBM peak; see traffic for the measured DRAM bytes")
     stages = dict(
         walk=dict(value=tot_steps / t_walk, unit="steps/s", ms_per_step=t_walk / args.steps * 1e3, kernel="k_walk_alias",
                   kernel_ms=wk_ms,
@@ -385,7 +389,7 @@ def run_gpu_arm(args, w, rank, world, dist):
                                 traffic=ncu_traffic(w["name"], "k_walk_alias"), bytes_per_unit=WALK_BYTES_PER_STEP, peak_source=peak_src,
                                 note=resident_note),
                   cpu_baseline=cpu["walk"] if cpu else None),
-        sgns=dict(value=tot_pairs / t_sgns, unit="pairs/s", ms_per_step=t_sgns / args.steps * 1e3, kernel="k_sgns_items",
+        sgns=dict(value=tot_pairs / t_sgns, unit="pairs/s", ms_per_step=t_sgns / args.steps * 1e3, kernel="k_sgns_items_v2",
                   kernel_ms=sk_ms, groups_in_flight=ctx.phase_ms("sgns_groups"), sync_rounds=ctx.phase_ms("sgns_rounds"),
                   sync_ms=ctx.phase_ms("sgns_sync"),
                   e2e=dict(value=e_tot_pairs / e_t_sgns, unit="pairs/s", h2d_bytes_per_step=int(d2h_walk), d2h_bytes_per_step=int(d2h_sgns),

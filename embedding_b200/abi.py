@@ -89,6 +89,8 @@ def lib():
     L.dge_flows_free.restype = None
     L.dge_crosstime_graph_build.argtypes = [vp, pi32, i32, C.c_int, pi32, P(vp)]
     L.dge_graph_labels.argtypes = [vp, pi32, pi32, pi32]
+    L.dge_eval_knn.argtypes = [vp, pf32, i32, i32, i32, pi32, pf64]
+    L.dge_eval_ndcg.argtypes = [vp, pf32, i32, i32, pi32, pf64, i32, i32, pf64, P(C.c_double)]
     L.dge_timer_start.argtypes = [vp]
     L.dge_timer_stop.argtypes = [vp, P(C.c_float)]
     L.dge_comm_unique_id.argtypes = [vp, C.c_size_t]
@@ -169,6 +171,31 @@ class Context:
 
     def kernel_launches(self):
         return int(lib().dge_kernel_launches(self._h))
+
+    def eval_knn(self, X, topk, want_dist=False):
+        """dge_eval_knn: topk nearest other rows by cosine distance (fp64), ties by row index."""
+        X = np.ascontiguousarray(X, np.float32)
+        m, dim = X.shape
+        nbr = np.empty((m, topk), np.int32)
+        dist = np.empty((m, topk), np.float64) if want_dist else None
+        _check(lib().dge_eval_knn(self._h, _ptr(X, C.c_float), m, dim, int(topk), _ptr(nbr, C.c_int32), _ptr(dist, C.c_double)),
+               self._h)
+        return (nbr, dist) if want_dist else nbr
+
+    def eval_ndcg(self, X, gt_index, gt_dist, topk):
+        """dge_eval_ndcg: (per-row nDCG@topk, mean) of one embedding layer against a ground-truth distance matrix."""
+        X = np.ascontiguousarray(X, np.float32)
+        gi = np.ascontiguousarray(gt_index, np.int32)
+        gt = np.ascontiguousarray(gt_dist, np.float64)
+        m, dim = X.shape
+        n = gt.shape[0]
+        if gt.shape != (n, n) or len(gi) != m:
+            raise ValueError("gt_dist must be [n, n] and gt_index must have one entry per row of X")
+        nd = np.empty(m, np.float64)
+        mean = C.c_double()
+        _check(lib().dge_eval_ndcg(self._h, _ptr(X, C.c_float), m, dim, _ptr(gi, C.c_int32), _ptr(gt, C.c_double), n, int(topk),
+                                   _ptr(nd, C.c_double), C.byref(mean)), self._h)
+        return nd, float(mean.value)
 
     def timer_start(self):
         _check(lib().dge_timer_start(self._h), self._h)

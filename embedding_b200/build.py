@@ -26,6 +26,7 @@ SOURCES = {
     "sgns.cu": [],
     "comm.cu": [],
     "flows.cu": [],
+    "eval.cu": ["--fmad=false"],
 }
 
 

@@ -413,165 +413,10 @@ k_sgns_items(const sgns_args a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Kernel B, software-pipelined (rows of up to 32 float4 slots, one slot per lane).  Same work decomposition and
-// arithmetic as k_sgns_items; the three dependent L2 round trips of a pair (token -> negative-table entry ->
-// rows) are taken off the critical path:
-//   * the item's sentence is staged in shared memory once;
-//   * iteration c issues the negative-table lookups of pair c+2, the row loads of pair c+1 (whose table entries
-//     were requested one iteration earlier) and only then computes pair c, whose rows were requested one
-//     iteration earlier.
-// With the bounded number of items in flight that the small-vocabulary configs allow, this is what keeps the
-// lanes busy: the kernel becomes issue / L2-reduction bound instead of L2-latency bound.
-template <int G>
-__global__ void __launch_bounds__(128)
-k_sgns_items_pipe(const sgns_args a) {
-    static_assert(G >= 8, "one negative per lane");
-    extern __shared__ int32_t smem[];
-    float *s_exp = reinterpret_cast<float *>(smem);
-    constexpr unsigned FULL = 0xffffffffu;
-    constexpr int GPW = 32 / G;
-    const int lane = threadIdx.x % G;
-    const int gw = (threadIdx.x & 31) / G;
-    int32_t *mytok = smem + a.exp_table_size + (threadIdx.x / G) * a.Lmax;
-    for (int i = threadIdx.x; i < a.exp_table_size; i += blockDim.x) s_exp[i] = a.exp_table[i];
-    __syncthreads();
-    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int E = a.exp_table_size;
-    const float idx_scale = (float)E / SGNS_MAX_EXP / 2.0f;
-    const int win = a.window;
-    const int64_t N = a.n_sent;
-    const int Lmax = a.Lmax;
-    const int64_t item_lo = a.s_lo * Lmax, n_items = a.s_hi * Lmax; // items [item_lo, n_items) of this launch
-    const double inv_total = 1.0 / (double)((int64_t)a.epochs * N);
-    const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
-    const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int K = a.V >= 2 ? a.negative : 0;
-    const int n4 = a.n4;
-    const bool live = lane < n4;
-    const int slot = live ? lane : 0;
-    const bool drawer = lane < SGNS_CH && lane < K;
-    const uint64_t my_a = a.lcg_a[lane < SGNS_MAX_NEG ? lane : 0], my_c = a.lcg_c[lane < SGNS_MAX_NEG ? lane : 0];
-    unsigned long long pairs = 0;
-
-    struct stage_t { int32_t last; bool act; uint64_t ns0, nsk; int32_t traw; };
-    struct stage_r { int32_t last; bool act; uint64_t ns0; int32_t tg[SGNS_CH]; float4 row[SGNS_CH]; float4 v0; };
-
-    for (int ep = a.ep_lo; ep < a.ep_hi; ep++) {
-        for (int64_t base = item_lo + warp_id * GPW; base < n_items; base += a.n_groups) { // warp-uniform trip count
-            const int64_t item = base + gw;
-            bool valid = item < n_items;
-            const int64_t s = valid ? item / Lmax : 0;
-            const int i = valid ? (int)(item - s * Lmax) : 0;
-            __syncwarp();
-            for (int j = lane; j < Lmax; j += G) mytok[j] = a.wtok[(int64_t)j * N + s];
-            __syncwarp();
-            const int32_t w1 = mytok[i];
-            valid = valid && w1 >= 0;
-            if (!__any_sync(FULL, valid)) continue;
-            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * N + s) * inv_total);
-            if (alpha < a.min_lr) alpha = a.min_lr;
-            const uint64_t S = sgns_sentence_rng(a.seed, ep, s);
-            const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
-            const int lo = i - win + b, hi = i + win - b; // inclusive context range (SkipGram.skipGram)
-            float4 *pw = reinterpret_cast<float4 *>(a.syn1neg + (int64_t)(valid ? w1 : 0) * a.stride);
-            float4 cur = ldcg4_if(pw + slot, valid && live), d1 = zero4; // current value and accumulated delta of syn1neg[w1]
-
-            auto stageT = [&](int c) { // which pair is position c, and request its negatives' table entries
-                stage_t t;
-                t.last = c < Lmax ? mytok[c] : -1;
-                t.act = valid && c >= lo && c <= hi && c != i && t.last >= 0 && t.last != w1;
-                t.ns0 = sgns_pair_rng(S, i, c);
-                t.nsk = my_a * t.ns0 + my_c; // lane k draws negative k: the LCG is affine
-                t.traw = 1; // a valid entry for lanes that draw nothing
-                if (drawer && t.act) t.traw = a.neg_table[mod48(t.nsk >> 16, tsize, inv_tsize)];
-                return t;
-            };
-            auto stageR = [&](const stage_t &t) { // resolve the negatives and request all rows of the pair
-                stage_r r;
-                r.last = t.last; r.act = t.act; r.ns0 = t.ns0;
-                int32_t tt = t.traw;
-                if (tt <= 0 || tt >= a.V) tt = (int32_t)mod64(t.nsk, vm1, inv_vm1) + 1;
-                const int32_t mine = (drawer && t.act && tt != w1) ? tt : -1;
-#pragma unroll
-                for (int k = 0; k < SGNS_CH; k++) r.tg[k] = __shfl_sync(FULL, mine, k, G);
-                r.v0 = ldcg4_if(reinterpret_cast<const float4 *>(a.syn0 + (int64_t)(t.act ? t.last : 0) * a.stride) + slot, t.act && live);
-#pragma unroll
-                for (int k = 0; k < SGNS_CH; k++)
-                    r.row[k] = ldcg4_if(reinterpret_cast<const float4 *>(a.syn1neg + (int64_t)(r.tg[k] < 0 ? 0 : r.tg[k]) * a.stride) + slot,
-                                        r.tg[k] >= 0 && live);
-                return r;
-            };
-
-            stage_t t1 = stageT(0);
-            stage_r r0 = stageR(t1);
-            t1 = stageT(1);
-            for (int c = 0; c < Lmax; c++) {
-                const stage_r rn = stageR(t1); // pair c+1
-                t1 = stageT(c + 2);            // pair c+2
-                if (__any_sync(FULL, r0.act)) { // ---- compute pair c
-                    pairs += r0.act;
-                    const float4 v0 = r0.v0;
-                    float4 neu = zero4;
-                    {
-                        float dot = group_sum<G>(dot4(v0, cur), FULL);
-                        float g = 0.f;
-                        if (!(sgns_g(dot, 1.f, alpha, s_exp, E, idx_scale, g) && r0.act)) g = 0.f;
-                        axpy4(neu, g, cur);
-                        axpy4(d1, g, v0);
-                        axpy4(cur, g, v0);
-                    }
-#pragma unroll
-                    for (int k = 0; k < SGNS_CH; k++) {
-                        float dot = group_sum<G>(dot4(v0, r0.row[k]), FULL);
-                        float g = 0.f;
-                        const bool upd = sgns_g(dot, 0.f, alpha, s_exp, E, idx_scale, g) && r0.tg[k] >= 0;
-                        if (!upd) g = 0.f;
-                        axpy4(neu, g, r0.row[k]);
-                        if (upd && live && !(a.dbg & 1))
-                            red_add4(reinterpret_cast<float4 *>(a.syn1neg + (int64_t)r0.tg[k] * a.stride) + slot, scale4(g, v0));
-                    }
-                    for (int k0 = SGNS_CH; k0 < K; k0 += SGNS_CH) { // negative > 5: further chunks, not pipelined
-                        int32_t mine = -1;
-                        if (lane < SGNS_CH && k0 + lane < K && r0.act) {
-                            const uint64_t nsk = a.lcg_a[k0 + lane] * r0.ns0 + a.lcg_c[k0 + lane];
-                            int32_t t = a.neg_table[mod48(nsk >> 16, tsize, inv_tsize)];
-                            if (t <= 0 || t >= a.V) t = (int32_t)mod64(nsk, vm1, inv_vm1) + 1;
-                            if (t != w1) mine = t;
-                        }
-                        int32_t tg[SGNS_CH];
-                        float4 vk[SGNS_CH];
-#pragma unroll
-                        for (int k = 0; k < SGNS_CH; k++) tg[k] = __shfl_sync(FULL, mine, k, G);
-#pragma unroll
-                        for (int k = 0; k < SGNS_CH; k++)
-                            vk[k] = ldcg4_if(reinterpret_cast<const float4 *>(a.syn1neg + (int64_t)(tg[k] < 0 ? 0 : tg[k]) * a.stride) + slot, tg[k] >= 0 && live);
-#pragma unroll
-                        for (int k = 0; k < SGNS_CH; k++) {
-                            float dot = group_sum<G>(dot4(v0, vk[k]), FULL);
-                            float g = 0.f;
-                            const bool upd = sgns_g(dot, 0.f, alpha, s_exp, E, idx_scale, g) && tg[k] >= 0;
-                            if (!upd) g = 0.f;
-                            axpy4(neu, g, vk[k]);
-                            if (upd && live && !(a.dbg & 1))
-                                red_add4(reinterpret_cast<float4 *>(a.syn1neg + (int64_t)tg[k] * a.stride) + slot, scale4(g, v0));
-                        }
-                    }
-                    if (r0.act && live && !(a.dbg & 1)) red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)r0.last * a.stride) + slot, neu);
-                }
-                r0 = rn;
-            }
-            if (valid && live && !(a.dbg & 1)) red_add4(pw + slot, d1);
-        }
-    }
-    if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Kernel C: the item kernel rebuilt around its measured limit.  ncu on the tract x 24 workload
-// (profiles/r1s3_sgns_tract24.json) showed k_sgns_items_pipe issue-bound (58 % issue slots busy, no memory stall):
-// ~600 warp instructions per 4 pairs, most of them integer / control overhead.  Same work decomposition, same
-// draws, same arithmetic per pair; what changed:
+// Kernel C: the item kernel for rows of up to 32 float4 slots (one slot per lane), rebuilt around its measured
+// limit.  ncu on the tract x 24 workload (profiles/r1s3_sgns_tract24.json) showed its predecessor issue-bound (58 %
+// of the issue slots busy, no memory stall): ~600 warp instructions per 4 pairs, most of them integer / control
+// overhead.  Same work decomposition as kernel B, same draws, same arithmetic per pair; what changed:
 //   * the K+1 dot products of a pair are reduced with ONE transposed butterfly (7 shuffles for up to 8 values over
 //     8 lanes, lane L ends with the total of value L) instead of K+1 separate butterflies (3 shuffles each);
 //   * lane L alone turns total L into its gradient scale g_L (one branch-free sigmoid-table lookup per lane instead
@@ -579,8 +424,10 @@ k_sgns_items_pipe(const sgns_args a) {
 //   * the per-pair hash of the negative stream is computed for G context positions at once (lane l: position
 //     c0 + l) and broadcast per pair, instead of G times redundantly per pair;
 //   * row addresses are 32-bit slot offsets from a per-lane base pointer (one IMAD.WIDE each);
-//   * the pipeline registers are ping-ponged by an unroll-by-two (no register rotation);
-//   * negatives > 5 are pipelined as further 5-wide chunks of the same pair (MULTI) instead of a serial tail;
+//   * only the negative-table lookups run one unit ahead; the rows of a unit are requested and consumed in the
+//     same unit, which fits 96 registers => 5 blocks per SM, and the extra resident warps hide the L2 latency
+//     better than a second row buffer did (profiles/r1s6_sgns_builds.txt);
+//   * negatives > 5 are further 5-wide chunks (units) of the same pair (MULTI) instead of a serial tail;
 //   * a reduction whose g is exactly 0 (saturated sigmoid) is not sent.
 // Rows sit on a sector-aligned pitch (args.stride, multiple of 8 floats), so a row of D floats touches
 // ceil(D/8) sectors instead of one more on every other row.
@@ -607,8 +454,11 @@ __device__ __forceinline__ void ldcg4_into(float4 &r, uint64_t p, bool pred) {
                  : "l"(p), "r"((int)pred));
 }
 
-template <int G, bool MULTI, int MINB>
-__global__ void __launch_bounds__(128, MINB)
+// After this rebuild the kernel runs at ~2/3 of what the memory system itself delivers for its access pattern
+// (random 80-byte-row 128-bit loads + reductions, scripts/red_microbench.cu, profiles/r1s7_red_microbench.txt):
+// the reductions, not the instruction stream, are the limit now.
+template <int G, bool MULTI>
+__global__ void __launch_bounds__(128, 5)
 k_sgns_items_v2(const sgns_args a) {
     static_assert(G == 8 || G == 16 || G == 32, "lane groups of 8, 16 or 32");
     extern __shared__ int32_t smem[];
@@ -753,17 +603,16 @@ k_sgns_items_v2(const sgns_args a) {
                 red_add4_if(row_addr(base0, (uint32_t)r.last, pitch), neu, (!MULTI || r.j == NCH - 1) && r.act && live && !(a.dbg & 1));
             };
 
-            stage_r rA, rB; // rows not (re)loaded keep stale finite values, cancelled by g = 0; start from zeros
-            rA.v0 = rB.v0 = zero4;
-#pragma unroll
-            for (int k = 0; k < SGNS_CH; k++) rA.row[k] = rB.row[k] = zero4;
-            stage_t t1 = stageT();
-            stageR(t1, rA);
-            t1 = stageT();
             const int U = Lmax * NCH;
-            for (int u = 0; u < U; u += 2) { // ping-pong: no register rotation
-                stageR(t1, rB); t1 = stageT(); compute(rA);
-                stageR(t1, rA); t1 = stageT(); compute(rB);
+            stage_r rA; // rows not (re)loaded keep stale finite values, cancelled by g = 0; start from zeros
+            rA.v0 = zero4;
+#pragma unroll
+            for (int k = 0; k < SGNS_CH; k++) rA.row[k] = zero4;
+            stage_t t1 = stageT();
+            for (int u = 0; u < U; u++) {
+                stageR(t1, rA);   // rows of unit u
+                t1 = stageT();    // table lookups of unit u+1 (independent work while the rows arrive)
+                compute(rA);
             }
             red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, valid && live && !(a.dbg & 1));
             pairs += (unsigned)npairs;
@@ -802,7 +651,7 @@ struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq,
 // Kernel A (exact order): rows of up to 8 float4 slots are held by ONE thread; wider rows give each lane of a
 // 16- or 32-lane group one 128-bit slot (2 or 4 for rows wider than 32 slots).
 // Kernel B (items): groups of 8 / 16 / 32 lanes, one slot per lane (2 or 4 beyond 32 slots).
-static bool pick_variant(int n4, int negative, bool legacy_items, bool occ3, sgns_variant *out) {
+static bool pick_variant(int n4, int negative, sgns_variant *out) {
     if (n4 > 128) return false;
     sgns_kernel_t seq = nullptr, items = nullptr;
     int Gs = 1, Vs = 1;
@@ -822,9 +671,9 @@ static bool pick_variant(int n4, int negative, bool legacy_items, bool occ3, sgn
     }
     int Gi, Vi = 1;
     const bool multi = negative > SGNS_CH; // more than one 5-wide chunk of negatives per pair
-    if (n4 <= 8) { Gi = 8; items = legacy_items ? k_sgns_items_pipe<8> : multi ? (occ3 ? k_sgns_items_v2<8, true, 3> : k_sgns_items_v2<8, true, 4>) : (occ3 ? k_sgns_items_v2<8, false, 3> : k_sgns_items_v2<8, false, 4>); }
-    else if (n4 <= 16) { Gi = 16; items = legacy_items ? k_sgns_items_pipe<16> : multi ? (occ3 ? k_sgns_items_v2<16, true, 3> : k_sgns_items_v2<16, true, 4>) : (occ3 ? k_sgns_items_v2<16, false, 3> : k_sgns_items_v2<16, false, 4>); }
-    else if (n4 <= 32) { Gi = 32; items = legacy_items ? k_sgns_items_pipe<32> : multi ? (occ3 ? k_sgns_items_v2<32, true, 3> : k_sgns_items_v2<32, true, 4>) : (occ3 ? k_sgns_items_v2<32, false, 3> : k_sgns_items_v2<32, false, 4>); }
+    if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true> : k_sgns_items_v2<8, false>; }
+    else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v2<16, true> : k_sgns_items_v2<16, false>; }
+    else if (n4 <= 32) { Gi = 32; items = multi ? k_sgns_items_v2<32, true> : k_sgns_items_v2<32, false>; }
     else if (n4 <= 64) { Gi = 32; Vi = 2; items = k_sgns_items<32, 2>; }
     else { Gi = 32; Vi = 4; items = k_sgns_items<32, 4>; }
     out->G_seq = Gs; out->VPL_seq = Vs; out->seq = seq;
@@ -872,9 +721,9 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
     }
     const int32_t n4 = (p->dim + 3) / 4;        // float4 slots that carry data (zero-padded to whole slots)
     const int32_t stride = ((p->dim + 7) / 8) * 8; // row pitch in floats: rows start on 32-byte sector boundaries
-    const int dbg = getenv("DGE_SGNS_DEBUG") ? atoi(getenv("DGE_SGNS_DEBUG")) : 0; // 1: no reductions, 2: previous item kernel, 4: 3 blocks/SM build, 8: item kernel on ONE warp (tests)
+    const int dbg = getenv("DGE_SGNS_DEBUG") ? atoi(getenv("DGE_SGNS_DEBUG")) : 0; // 1: no reductions (timing experiments), 8: item kernel on ONE warp (tests)
     sgns_variant var;
-    if (!pick_variant(n4, p->negative, (dbg & 2) != 0, (dbg & 4) != 0, &var)) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: dim must be <= 512");
+    if (!pick_variant(n4, p->negative, &var)) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: dim must be <= 512");
     if (p->neg_table_size >= (1 << 30)) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: neg_table_size must be < 2^30");
     DGE_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;

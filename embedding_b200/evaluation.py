@@ -88,6 +88,20 @@ def pairwise_ndcg(gt, layers, ks=(5, 10, 20, 30, 40, 50, 60, 70)):
     return out
 
 
+def pairwise_ndcg_device(ctx, gt, layers, ks=(5, 10, 20, 30, 40, 50, 60, 70)):
+    """pairwise_ndcg() with the kNN + DCG of every layer computed by libdge (dge_eval_ndcg)."""
+    out = {}
+    for k in ks:
+        vals = []
+        for _, (f, r) in sorted(layers.items()):
+            if len(r) <= k:
+                continue
+            gi = np.array([gt.index[int(x)] for x in r], np.int32)
+            vals.append(ctx.eval_ndcg(f, gi, gt.D, k)[1])
+        out[int(k)] = float(np.mean(vals)) if vals else float("nan")
+    return out
+
+
 def knn_overlap(layers_a, layers_b, k=10):
     """Mean Jaccard-free overlap |kNN_a(r) & kNN_b(r)| / k over regions and layers: how much two embeddings agree
     on neighbourhoods (an extra, label-free parity measure; not in the reference)."""

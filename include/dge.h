@@ -229,6 +229,19 @@ int dge_model_write_vec(const dge_model *m, const int32_t *label_layer, const in
                         const char *path);
 void dge_model_free(dge_model *m);
 
+/* ------------------------------------------------------------------ downstream metric
+ * The reference's pairwise-similarity evaluation of an embedding layer on device, fp64 as numpy / scipy:
+ * python/embeddingEvaluation_tract.py:169-196 (pairwiseEstimator: cosine distance of every pair of rows, NaN -> 2,
+ * the topk nearest OTHER rows; ties by ascending row index like numpy's stable argsort) and :249-260 (dcg_atK /
+ * ndcg_atK with relevance 1 - ground-truth distance, discount 1 / log2(rank + 2), normalised by the DCG of the
+ * ground truth's own ordering, generatePairWiseGT :63-103).
+ * dge_eval_knn: X[m*dim] row-major -> nbr[m*topk] (row indices, -1 padded when m <= topk), dist[m*topk] or NULL.
+ * dge_eval_ndcg: gt_index[m] = row of every X row in the ground-truth distance matrix gt_dist[n*n]; ndcg[m] (or NULL)
+ * per row and their mean.  With m <= topk the reference reports nothing: *mean = NaN. */
+int dge_eval_knn(dge_ctx *ctx, const float *X, int32_t m, int32_t dim, int32_t topk, int32_t *nbr, double *dist);
+int dge_eval_ndcg(dge_ctx *ctx, const float *X, int32_t m, int32_t dim, const int32_t *gt_index, const double *gt_dist,
+                  int32_t n, int32_t topk, double *ndcg, double *mean);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,89 @@
+// red_microbench.cu -- what the L2 can take: random-row 128-bit reductions (red.global.add.v4.f32) and 128-bit
+// L2 loads (ld.global.cg.v4.f32) in the access shapes of the skip-gram item kernel.  It gives the denominator for
+// "how close is k_sgns_items_v2 to the reduction / load throughput of the memory system" (DESIGN.md 3.3).
+//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o scripts/bin/red_microbench scripts/red_microbench.cu
+//   scripts/bin/red_microbench
+// Shapes: G lanes per row, `live` of them active, row pitch in bytes, V rows.  Every warp-level instruction
+// touches 32/G random rows.  mode 0 = red only, 1 = load only, 2 = load + red of the same row.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ void red4(float4 *p, float v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %1, %1, %1};" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld4(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+template <int G, int MODE>
+__global__ void __launch_bounds__(128) k(float *table, uint32_t V, uint32_t pitch, int live, int iters, float *sink) {
+    const int lane = threadIdx.x % G;
+    const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    uint32_t s = gid * 2654435761u + 12345u;
+    float acc = 0.f;
+    char *base = reinterpret_cast<char *>(table) + (lane < live ? lane : 0) * 16;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 6; u++) { // 6 rows per "pair", like K+1 targets
+            s = s * 1664525u + 1013904223u;
+            uint32_t row = (uint32_t)(((uint64_t)(s >> 4) * V) >> 28);
+            float4 *p = reinterpret_cast<float4 *>(base + (uint64_t)row * pitch);
+            if (lane < live) {
+                if (MODE >= 1) { float4 v = ld4(p); acc += v.x + v.y + v.z + v.w; }
+                if (MODE != 1) red4(p, 1e-9f);
+            }
+        }
+    }
+    if (acc == 123.456f) *sink = acc;
+}
+
+template <int G, int MODE>
+static void run(const char *name, float *table, uint32_t V, uint32_t pitch, int live, int sms) {
+    float *sink;
+    cudaMalloc(&sink, 4);
+    const int blocks = sms * 8, iters = 2000;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k<G, MODE><<<blocks, 128>>>(table, V, pitch, live, 50, sink);
+    cudaEventRecord(e0);
+    k<G, MODE><<<blocks, 128>>>(table, V, pitch, live, iters, sink);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double rows = (double)blocks * 128 / G * iters * 6;
+    double lane_ops = rows * live * (MODE == 2 ? 2 : 1);
+    printf("%-34s G=%2d live=%2d pitch=%4u V=%8u mode=%d : %8.1f M rows/s  %8.1f G lane-ops/s  %7.1f GB/s  (%.2f ms)\n", name, G, live, pitch,
+           V, MODE, rows / ms / 1e3, lane_ops / ms / 1e6, lane_ops * 16 / ms / 1e6, ms);
+    cudaFree(sink);
+}
+
+int main() {
+    cudaDeviceProp p;
+    cudaGetDeviceProperties(&p, 0);
+    const int sms = p.multiProcessorCount;
+    printf("%s, %d SMs\n", p.name, sms);
+    float *small, *big;
+    const uint32_t Vs = 19224, Vb = 2400000;
+    cudaMalloc(&small, (size_t)Vs * 128);
+    cudaMalloc(&big, (size_t)Vb * 512);
+    cudaMemset(small, 0, (size_t)Vs * 128);
+    cudaMemset(big, 0, (size_t)Vb * 512);
+    // tract x 24 shape: 80-byte rows on a 96-byte pitch, 5 of 8 lanes live, 19 224 rows (L2-resident)
+    run<8, 0>("tract24 rows: red", small, Vs, 96, 5, sms);
+    run<8, 1>("tract24 rows: load", small, Vs, 96, 5, sms);
+    run<8, 2>("tract24 rows: load+red", small, Vs, 96, 5, sms);
+    run<8, 0>("128 B rows, 8/8 live: red", small, Vs, 128, 8, sms);
+    run<8, 0>("32 B rows (CA D=8), 2/8 live: red", small, Vs, 32, 2, sms);
+    run<4, 0>("64 B rows, G=4 4/4 live: red", small, Vs, 64, 4, sms);
+    // synthetic shape: 512-byte rows, 32 lanes, 2.4 M rows (1.2 GB: HBM unless the draw is skewed)
+    run<32, 0>("512 B rows, uniform 2.4M: red", big, Vb, 512, 32, sms);
+    run<32, 1>("512 B rows, uniform 2.4M: load", big, Vb, 512, 32, sms);
+    run<32, 2>("512 B rows, uniform 2.4M: load+red", big, Vb, 512, 32, sms);
+    run<32, 0>("512 B rows, 100K hot rows: red", big, 100000, 512, 32, sms);
+    run<32, 2>("512 B rows, 100K hot rows: ld+red", big, 100000, 512, 32, sms);
+    return 0;
+}
