@@ -409,11 +409,11 @@ def run_gpu_arm(args, w, rank, world, dist):
                 e2e=stages["walk"]["e2e"],
                 # roofline of the DOMINANT kernel of the step (the skip-gram item kernel, `share` of the step's kernel
                 # time); the walk kernel's own roofline is stages.walk.roofline
-                roofline=dict(stages["sgns"]["roofline"], kernel="k_sgns_items", share_of_step_kernel_time=share,
+                roofline=dict(stages["sgns"]["roofline"], kernel="k_sgns_items_v2", share_of_step_kernel_time=share,
                               units="SGNS pairs; the top-level value counts walk steps, see stages"),
                 cpu_baseline=stages["walk"]["cpu_baseline"],
                 clocks=clk, gpu_launches=int(launches), stages=stages,
-                dominant_kernel=dict(name="k_sgns_items", share_of_step_kernel_time=share),
+                dominant_kernel=dict(name="k_sgns_items_v2", share_of_step_kernel_time=share),
                 published=dict(note="reference publishes walk wall times only (python/running_time.py:16-20; other hardware, includes "
                                     "String.join + file write): tract alias 0.28 M walks/s, CA alias 0.514 M walks/s = 12.3 M steps/s"))
     print(json.dumps(line), flush=True)
