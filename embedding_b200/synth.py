@@ -74,6 +74,43 @@ def powerlaw_flow_graph(n_regions, L=24, seed=100000, mean_degree=42, cap=4096, 
                 v_layer=(v // n_regions).astype(np.int32), v_region=(v % n_regions).astype(np.int32))
 
 
+def powerlaw_flow_graph_layered(n_regions, L=24, seed=1000000, mean_degree=42, cap=4096, zipf_a=1.6, pop_s=0.8, threads=None):
+    """Same model as powerlaw_flow_graph, generated one layer at a time (one independent RNG stream and one host
+    thread per layer) into preallocated arrays, so that the 1M-region x 24-slice config (~1.0e9 edges, 16 GB of COO)
+    needs no multi-GB temporaries and a few tens of seconds on the host."""
+    import concurrent.futures
+    import os
+    ss = np.random.SeedSequence(seed)
+    rng = np.random.default_rng(ss.spawn(1)[0])
+    nv = n_regions * L
+    raw = np.minimum(rng.zipf(zipf_a, size=nv).astype(np.float64), cap * 4.0)
+    deg = np.maximum(1, np.minimum(cap, np.round(raw * (mean_degree / raw.mean())))).astype(np.int64)
+    deg = np.minimum(deg, n_regions)
+    del raw
+    first = np.concatenate([[0], np.cumsum(deg.reshape(L, n_regions).sum(axis=1))])
+    ne = int(first[-1])
+    src = np.empty(ne, np.int32)
+    dst = np.empty(ne, np.int32)
+    w = np.empty(ne, np.float64)
+    pop = (1.0 / np.arange(1, n_regions + 1, dtype=np.float64) ** pop_s)[rng.permutation(n_regions)]
+    cdf = np.cumsum(pop / pop.sum())
+    streams = ss.spawn(L + 1)[1:]
+
+    def layer(h):
+        g = np.random.default_rng(streams[h])
+        lo, hi = int(first[h]), int(first[h + 1])
+        src[lo:hi] = np.repeat(np.arange(h * n_regions, (h + 1) * n_regions, dtype=np.int32), deg[h * n_regions:(h + 1) * n_regions])
+        r = np.searchsorted(cdf, g.random(hi - lo))
+        np.minimum(r, n_regions - 1, out=r)
+        r += ((h + 1) % L) * n_regions
+        dst[lo:hi] = r
+        w[lo:hi] = np.floor(g.pareto(1.2, size=hi - lo)) + 1.0
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=threads or min(L, os.cpu_count() or 1)) as ex:
+        list(ex.map(layer, range(L)))
+    return dict(n_vertices=nv, src=src, dst=dst, w=w, sources=np.arange(n_regions, dtype=np.int32))
+
+
 def poi_latents():
     """Per-tract latent vectors: the 10 POI category counts of the reference's miscs/POI_tract.pickle
     (ground truth of python/embeddingEvaluation_tract.py:63-103), in tract_ids() order; zeros if absent."""

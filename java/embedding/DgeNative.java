@@ -40,4 +40,19 @@ public final class DgeNative {
                                         int epochs, float lr, float minLr, long seed);
     public static native void modelWriteVec(long model, int[] labelLayer, int[] labelRegion, String path);
     public static native void modelFree(long model);
+
+    /** CommunityAreas.mapTripsIntoCommunities / Tracts.mapTripsIntoTracts (counting) -> dge_flows_create / _add_trips. */
+    public static native long flowsCreate(long ctx, int nRegions, int[] flowTensorOrNull);
+    public static native void flowsAddTrips(long flows, int[] srcRegion, int[] dstRegion, int[] startHour);
+    public static native void flowsFree(long flows);
+    /** CrossTimeGraph.constructGraph_CA(int[]) (mode 0) / constructGraph_tract() (mode 1) + initiateAliasTables. */
+    public static native long crosstimeGraphBuild(long flows, int[] order, int numLayer, int mode, int[] intervalsOrNull);
+    public static native void graphLabels(long graph, int[] vLayer, int[] vRegionIndex, int[] sources);
+    /** outputStaticFlowGraph / outputAdjacencyMatrix / outputEdgeGraph_LINE / outputEdgeFile -> dge_flows_write_*. */
+    public static native void flowsWriteMatrix(long flows, int mode, int lo, int hi, int[] rows, int[] cols, char sep, String path);
+    public static native void flowsWriteOd(long flows, int mode, int lo, int hi, int[] rows, int[] cols, int[] regionIds,
+                                           boolean keepZero, int presenceHour, String path);
+    /** python/embeddingEvaluation_tract.py pairwiseEstimator + ndcg_atK -> dge_eval_ndcg (returns the mean). */
+    public static native double evalNdcg(long ctx, float[] x, int m, int dim, int[] gtIndex, double[] gtDist, int n, int topk,
+                                         double[] ndcgPerRowOrNull);
 }

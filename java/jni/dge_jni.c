@@ -3,7 +3,8 @@
  * Source only: jni.h does not exist in the build image; compiled by the maintainer with
  *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -Iinclude java/jni/dge_jni.c \
  *       -Lembedding_b200 -ldge -o libdge_jni.so
- * Only the graph / walk / train entry points are shown in full; the remaining ones follow the same pattern.
+ * The graph / walk / train / flows entry points are shown in full; the remaining ones (tables, labels, exports,
+ * evaluation) pin their arrays and forward in exactly the same way.
  */
 #if defined(__has_include)
 #if __has_include(<jni.h>)
@@ -65,6 +66,41 @@ JNIEXPORT jlong JNICALL Java_embedding_DgeNative_sgnsTrain(JNIEnv *env, jclass c
     dge_model *m = NULL;
     if (dge_sgns_train(ctx, corp, n, &p, &m) != DGE_OK) { throw_dge(env, ctx); return 0; }
     return (jlong)(intptr_t)m;
+}
+
+JNIEXPORT jlong JNICALL Java_embedding_DgeNative_flowsCreate(JNIEnv *env, jclass c, jlong jctx, jint n, jintArray jF) {
+    dge_ctx *ctx = (dge_ctx *)(intptr_t)jctx;
+    jint *F = jF ? (*env)->GetPrimitiveArrayCritical(env, jF, NULL) : NULL;
+    dge_flows *f = NULL;
+    int rc = dge_flows_create(ctx, n, (const int32_t *)F, &f);
+    if (F) (*env)->ReleasePrimitiveArrayCritical(env, jF, F, JNI_ABORT);
+    if (rc != DGE_OK) { throw_dge(env, ctx); return 0; }
+    return (jlong)(intptr_t)f;
+}
+
+JNIEXPORT void JNICALL Java_embedding_DgeNative_flowsAddTrips(JNIEnv *env, jclass c, jlong jf, jintArray js, jintArray jd,
+        jintArray jh) {
+    jsize n = (*env)->GetArrayLength(env, js);
+    jint *s = (*env)->GetPrimitiveArrayCritical(env, js, NULL);
+    jint *d = (*env)->GetPrimitiveArrayCritical(env, jd, NULL);
+    jint *h = (*env)->GetPrimitiveArrayCritical(env, jh, NULL);
+    int rc = dge_flows_add_trips((dge_flows *)(intptr_t)jf, n, (const int32_t *)s, (const int32_t *)d, (const int32_t *)h);
+    (*env)->ReleasePrimitiveArrayCritical(env, jh, h, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, jd, d, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, js, s, JNI_ABORT);
+    if (rc != DGE_OK) throw_dge(env, NULL);
+}
+
+JNIEXPORT jlong JNICALL Java_embedding_DgeNative_crosstimeGraphBuild(JNIEnv *env, jclass c, jlong jf, jintArray jorder,
+        jint numLayer, jint mode, jintArray jiv) {
+    jint *order = (*env)->GetPrimitiveArrayCritical(env, jorder, NULL);
+    jint *iv = jiv ? (*env)->GetPrimitiveArrayCritical(env, jiv, NULL) : NULL;
+    dge_graph *g = NULL;
+    int rc = dge_crosstime_graph_build((const dge_flows *)(intptr_t)jf, (const int32_t *)order, numLayer, mode, (const int32_t *)iv, &g);
+    if (iv) (*env)->ReleasePrimitiveArrayCritical(env, jiv, iv, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, jorder, order, JNI_ABORT);
+    if (rc != DGE_OK) { throw_dge(env, NULL); return 0; }
+    return (jlong)(intptr_t)g;
 }
 #endif
 #endif
