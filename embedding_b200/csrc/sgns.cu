@@ -621,6 +621,229 @@ k_sgns_items_v2(const sgns_args a) {
     if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Kernel D: the item kernel for NARROW rows (up to 8 float4 slots: D <= 32, i.e. the reference's own D = 8 and
+// D = 20).  Same draws and arithmetic as kernel C; a group is 4 lanes holding VPL = 1 or 2 slots each (slot
+// lane + 4v), so 8 items run in lockstep per warp instead of 4 and the per-unit overhead (pair hash, negative
+// draws, shuffles, sigmoid lookups, addressing) is spread over twice as many pairs.  The reductions are the
+// limit of kernel C at these sizes: fewer instructions per pair leave the LSU / L2 reduction
+// path less idle.  Lane ownership after the transposed reduction (8 values over 4 lanes, 6 shuffles): lane l owns
+// values 2l and 2l+1 -- negatives 0..4 of the chunk and, as value 5, the positive target; lane l therefore also
+// draws negatives 2l and 2l+1.
+__device__ __forceinline__ float sgns_g_lane(float tot, float label, float alpha, float g_hi, float g_lo, const float *s_exp,
+                                             int E, float idx_scale) {
+    const float f = (tot + SGNS_MAX_EXP) * idx_scale;
+    const int idx = (int)f;
+    const float sg = s_exp[min(max(idx, 0), E - 1)];
+    float g = (label - sg) * alpha;
+    if (idx < 0 || idx >= E) g = 0.f; // table index out of range: the aggregate skips the target
+    if (tot > SGNS_MAX_EXP) g = g_hi;
+    else if (tot < -SGNS_MAX_EXP) g = g_lo;
+    return g;
+}
+
+template <int VPL, bool MULTI>
+__global__ void __launch_bounds__(128, 4)
+k_sgns_items_g4(const sgns_args a) {
+    static_assert(VPL == 1 || VPL == 2, "one or two float4 slots per lane");
+    constexpr int G = 4;
+    extern __shared__ int32_t smem[];
+    float *s_exp = reinterpret_cast<float *>(smem);
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int GPW = 32 / G;
+    const int lane = threadIdx.x % G;
+    const int gw = (threadIdx.x & 31) / G;
+    int32_t *mytok = smem + a.exp_table_size + (threadIdx.x / G) * a.Lmax;
+    for (int i = threadIdx.x; i < a.exp_table_size; i += blockDim.x) s_exp[i] = a.exp_table[i];
+    __syncthreads();
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int E = a.exp_table_size;
+    const float idx_scale = (float)E / SGNS_MAX_EXP / 2.0f;
+    const int win = a.window;
+    const int64_t N = a.n_sent;
+    const int Lmax = a.Lmax;
+    const int64_t item_lo = a.s_lo * Lmax, n_items = a.s_hi * Lmax;
+    const double inv_total = 1.0 / (double)((int64_t)a.epochs * N);
+    const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
+    const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int K = a.V >= 2 ? a.negative : 0;
+    const int NCH = MULTI ? max(1, (K + SGNS_CH - 1) / SGNS_CH) : 1;
+    bool live[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; v++) live[v] = lane + v * G < a.n4;
+    const uint32_t pitch = (uint32_t)a.stride * 4u;
+    // slot v of a row sits at base + v * 64 bytes (a dead slot is never dereferenced)
+    const char *base0 = reinterpret_cast<const char *>(a.syn0) + (live[0] ? lane : 0) * 16;
+    const char *base1 = reinterpret_cast<const char *>(a.syn1neg) + (live[0] ? lane : 0) * 16;
+    const bool up2 = (lane & 2) != 0, up1 = (lane & 1) != 0;
+    // owned values: A = 2*lane (always a negative), B = 2*lane + 1 (lane 2: the positive target, lane 3: nothing)
+    const int kA = 2 * lane, kB = 2 * lane + 1;
+    const float labelB = kB == SGNS_CH ? 1.f : 0.f;
+    unsigned long long pairs = 0;
+
+    struct stage_t { int32_t last; bool act; uint64_t nskA, nskB; int32_t trawA, trawB; int j; };
+    struct stage_r { int32_t last; bool act; int j; int32_t mineA, mineB; int32_t tg[SGNS_CH]; float4 row[SGNS_CH][VPL]; float4 v0[VPL]; };
+
+    for (int ep = a.ep_lo; ep < a.ep_hi; ep++) {
+        for (int64_t base = item_lo + warp_id * GPW; base < n_items; base += a.n_groups) { // warp-uniform trip count
+            const int64_t item = base + gw;
+            bool valid = item < n_items;
+            const int64_t s = valid ? item / Lmax : 0;
+            const int i = valid ? (int)(item - s * Lmax) : 0;
+            __syncwarp();
+            for (int j = lane; j < Lmax; j += G) mytok[j] = a.wtok[(int64_t)j * N + s];
+            __syncwarp();
+            const int32_t w1 = mytok[i];
+            valid = valid && w1 >= 0;
+            if (!__any_sync(FULL, valid)) continue;
+            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * N + s) * inv_total);
+            if (alpha < a.min_lr) alpha = a.min_lr;
+            const float gB_hi = (labelB - 1.f) * alpha, gB_lo = labelB * alpha; // saturated sigmoid (value B)
+            const float gA_hi = -alpha;                                         // value A is always a negative: label 0
+            const uint64_t S = sgns_sentence_rng(a.seed, ep, s);
+            const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
+            const int lo = valid ? i - win + b : 1, hi = valid ? i + win - b : 0;
+            float4 cur[VPL], d1[VPL], neu[VPL], v0p[VPL];
+#pragma unroll
+            for (int v = 0; v < VPL; v++) {
+                cur[v] = d1[v] = neu[v] = v0p[v] = zero4;
+                ldcg4_into(cur[v], row_addr(base1, (uint32_t)w1, pitch) + v * 64, valid && live[v]);
+            }
+            int npairs = 0;
+            int cT = 0, jT = 0;
+            uint64_t hc = 0;
+
+            auto stageT = [&]() {
+                stage_t t;
+                t.j = jT;
+                t.last = cT < Lmax ? mytok[cT] : -1;
+                t.act = cT >= lo && cT <= hi && cT != i && t.last >= 0 && t.last != w1;
+                if ((cT & (G - 1)) == 0 && jT == 0) hc = sgns_pair_rng(S, i, cT + lane); // warp-uniform condition
+                const uint64_t ns0 = shfl64(hc, cT & (G - 1), G);
+                const int kkA = jT * SGNS_CH + kA, kkB = jT * SGNS_CH + kB;
+                const bool drawA = kA < SGNS_CH && kkA < K, drawB = kB < SGNS_CH && kkB < K;
+                t.nskA = a.lcg_a[drawA ? kkA : 0] * ns0 + a.lcg_c[drawA ? kkA : 0];
+                t.nskB = a.lcg_a[drawB ? kkB : 0] * ns0 + a.lcg_c[drawB ? kkB : 0];
+                t.trawA = t.trawB = -2; // "draws nothing"
+                if (drawA && t.act) t.trawA = a.neg_table[mod48(t.nskA >> 16, tsize, inv_tsize)];
+                if (drawB && t.act) t.trawB = a.neg_table[mod48(t.nskB >> 16, tsize, inv_tsize)];
+                if (MULTI) { if (++jT == NCH) { jT = 0; cT++; } }
+                else cT++;
+                return t;
+            };
+            auto stageR = [&](const stage_t &t, stage_r &r) {
+                r.last = t.last; r.act = t.act; r.j = t.j;
+                int32_t ta = t.trawA, tb = t.trawB;
+                const bool reA = ta != -2 && (ta <= 0 || ta >= a.V), reB = tb != -2 && (tb <= 0 || tb >= a.V);
+                if (__any_sync(FULL, reA || reB)) { // DL4J: target = r % (V-1) + 1
+                    if (reA) ta = (int32_t)mod64(t.nskA, vm1, inv_vm1) + 1;
+                    if (reB) tb = (int32_t)mod64(t.nskB, vm1, inv_vm1) + 1;
+                }
+                r.mineA = (ta != -2 && ta != w1) ? ta : -1;
+                r.mineB = (tb != -2 && tb != w1) ? tb : -1;
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) r.tg[k] = __shfl_sync(FULL, (k & 1) ? r.mineB : r.mineA, k >> 1, G);
+                if (!MULTI || t.j == 0) {
+                    const uint64_t p = row_addr(base0, (uint32_t)t.last, pitch);
+#pragma unroll
+                    for (int v = 0; v < VPL; v++) ldcg4_into(r.v0[v], p + v * 64, t.act && live[v]);
+                }
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) {
+                    const uint64_t p = row_addr(base1, (uint32_t)r.tg[k], pitch);
+#pragma unroll
+                    for (int v = 0; v < VPL; v++) ldcg4_into(r.row[k][v], p + v * 64, r.tg[k] >= 0 && live[v]);
+                }
+            };
+            auto compute = [&](const stage_r &r) {
+                if (!__any_sync(FULL, r.act)) return;
+                const bool first = !MULTI || r.j == 0;
+                if (first) {
+                    npairs += r.act;
+#pragma unroll
+                    for (int v = 0; v < VPL; v++) neu[v] = zero4;
+                }
+                if (MULTI && first) {
+#pragma unroll
+                    for (int v = 0; v < VPL; v++) v0p[v] = r.v0[v];
+                }
+                float4 v0[VPL];
+#pragma unroll
+                for (int v = 0; v < VPL; v++) v0[v] = MULTI ? v0p[v] : r.v0[v];
+                float d[8];
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) {
+                    d[k] = dot4(v0[0], r.row[k][0]);
+                    if (VPL == 2) d[k] += dot4(v0[1], r.row[k][1]);
+                }
+                d[5] = 0.f;
+                if (first) {
+                    d[5] = dot4(v0[0], cur[0]);
+                    if (VPL == 2) d[5] += dot4(v0[1], cur[1]);
+                }
+                d[6] = d[7] = 0.f;
+                // transposed reduction, 8 values over 4 lanes: offset 2 (bit 1 clear keeps values 0..3), then offset 1
+                float e[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) e[j] = (up2 ? d[j + 4] : d[j]) + __shfl_xor_sync(FULL, up2 ? d[j] : d[j + 4], 2);
+                const float totA = (up1 ? e[2] : e[0]) + __shfl_xor_sync(FULL, up1 ? e[0] : e[2], 1); // value 2*lane
+                const float totB = (up1 ? e[3] : e[1]) + __shfl_xor_sync(FULL, up1 ? e[1] : e[3], 1); // value 2*lane + 1
+                float gA = sgns_g_lane(totA, 0.f, alpha, gA_hi, 0.f, s_exp, E, idx_scale);
+                float gB = sgns_g_lane(totB, labelB, alpha, gB_hi, gB_lo, s_exp, E, idx_scale);
+                if (r.mineA < 0) gA = 0.f;
+                const bool okB = kB < SGNS_CH ? r.mineB >= 0 : (kB == SGNS_CH && r.act && first);
+                if (!okB) gB = 0.f;
+                float gk[SGNS_CH + 1];
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) gk[k] = __shfl_sync(FULL, (k & 1) ? gB : gA, k >> 1, G);
+                gk[SGNS_CH] = first ? __shfl_sync(FULL, gB, SGNS_CH >> 1, G) : 0.f;
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) {
+                    const uint64_t p = row_addr(base1, (uint32_t)r.tg[k], pitch);
+#pragma unroll
+                    for (int v = 0; v < VPL; v++) {
+                        axpy4(neu[v], gk[k], r.row[k][v]);
+                        red_add4_if(p + v * 64, scale4(gk[k], v0[v]), gk[k] != 0.f && live[v] && !(a.dbg & 1));
+                    }
+                }
+                if (first) {
+#pragma unroll
+                    for (int v = 0; v < VPL; v++) {
+                        axpy4(neu[v], gk[SGNS_CH], cur[v]);
+                        axpy4(d1[v], gk[SGNS_CH], v0[v]);
+                        axpy4(cur[v], gk[SGNS_CH], v0[v]);
+                    }
+                }
+                const uint64_t p0 = row_addr(base0, (uint32_t)r.last, pitch);
+#pragma unroll
+                for (int v = 0; v < VPL; v++)
+                    red_add4_if(p0 + v * 64, neu[v], (!MULTI || r.j == NCH - 1) && r.act && live[v] && !(a.dbg & 1));
+            };
+
+            const int U = Lmax * NCH;
+            stage_r rA; // rows not (re)loaded keep stale finite values, cancelled by g = 0; start from zeros
+#pragma unroll
+            for (int v = 0; v < VPL; v++) {
+                rA.v0[v] = zero4;
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) rA.row[k][v] = zero4;
+            }
+            stage_t t1 = stageT();
+            for (int u = 0; u < U; u++) {
+                stageR(t1, rA);
+                t1 = stageT();
+                compute(rA);
+            }
+            const uint64_t pw = row_addr(base1, (uint32_t)w1, pitch);
+#pragma unroll
+            for (int v = 0; v < VPL; v++) red_add4_if(pw + v * 64, d1[v], valid && live[v] && !(a.dbg & 1));
+            pairs += (unsigned)npairs;
+        }
+    }
+    if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
+}
+
 // multi-GPU delta exchange (see dge_sgns_train): cur -= base  ...all-reduce(cur)...  base += cur; cur = base
 __global__ void k_delta_begin(float *__restrict__ c0, const float *__restrict__ b0, float *__restrict__ c1,
                               const float *__restrict__ b1, size_t n) {
@@ -651,7 +874,7 @@ struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq,
 // Kernel A (exact order): rows of up to 8 float4 slots are held by ONE thread; wider rows give each lane of a
 // 16- or 32-lane group one 128-bit slot (2 or 4 for rows wider than 32 slots).
 // Kernel B (items): groups of 8 / 16 / 32 lanes, one slot per lane (2 or 4 beyond 32 slots).
-static bool pick_variant(int n4, int negative, sgns_variant *out) {
+static bool pick_variant(int n4, int negative, bool wide_groups, sgns_variant *out) {
     if (n4 > 128) return false;
     sgns_kernel_t seq = nullptr, items = nullptr;
     int Gs = 1, Vs = 1;
@@ -671,7 +894,9 @@ static bool pick_variant(int n4, int negative, sgns_variant *out) {
     }
     int Gi, Vi = 1;
     const bool multi = negative > SGNS_CH; // more than one 5-wide chunk of negatives per pair
-    if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true> : k_sgns_items_v2<8, false>; }
+    if (n4 <= 4 && !wide_groups) { Gi = 4; items = multi ? k_sgns_items_g4<1, true> : k_sgns_items_g4<1, false>; }
+    else if (n4 <= 8 && !wide_groups) { Gi = 4; items = multi ? k_sgns_items_g4<2, true> : k_sgns_items_g4<2, false>; }
+    else if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true> : k_sgns_items_v2<8, false>; }
     else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v2<16, true> : k_sgns_items_v2<16, false>; }
     else if (n4 <= 32) { Gi = 32; items = multi ? k_sgns_items_v2<32, true> : k_sgns_items_v2<32, false>; }
     else if (n4 <= 64) { Gi = 32; Vi = 2; items = k_sgns_items<32, 2>; }
@@ -721,9 +946,9 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
     }
     const int32_t n4 = (p->dim + 3) / 4;        // float4 slots that carry data (zero-padded to whole slots)
     const int32_t stride = ((p->dim + 7) / 8) * 8; // row pitch in floats: rows start on 32-byte sector boundaries
-    const int dbg = getenv("DGE_SGNS_DEBUG") ? atoi(getenv("DGE_SGNS_DEBUG")) : 0; // 1: no reductions (timing experiments), 8: item kernel on ONE warp (tests)
+    const int dbg = getenv("DGE_SGNS_DEBUG") ? atoi(getenv("DGE_SGNS_DEBUG")) : 0; // 1: no reductions (timing experiments), 2: 8-lane groups for narrow rows (A/B), 8: item kernel on ONE warp (tests)
     sgns_variant var;
-    if (!pick_variant(n4, p->negative, &var)) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: dim must be <= 512");
+    if (!pick_variant(n4, p->negative, (dbg & 2) != 0, &var)) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: dim must be <= 512");
     if (p->neg_table_size >= (1 << 30)) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: neg_table_size must be < 2^30");
     DGE_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;

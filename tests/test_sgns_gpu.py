@@ -89,7 +89,7 @@ def test_parallel_schedule_learns_the_same_structure(dge_lib, oracle, ctx, dim):
     assert g_gpu > 0.5 * g_ref, (g_gpu, g_ref)
 
 
-@pytest.mark.parametrize("dim,negative", [(8, 5), (20, 5), (20, 12), (64, 5), (100, 7), (128, 5), (128, 20)])
+@pytest.mark.parametrize("dim,negative", [(8, 5), (8, 10), (20, 5), (20, 12), (32, 5), (64, 5), (100, 7), (128, 5), (128, 20)])
 def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negative, monkeypatch):
     """The throughput kernel (work item = (sentence, centre), 128-bit L2 reductions, software pipeline) enumerates
     the oracle's pairs and negatives and applies the same update arithmetic; only the interleaving differs.
