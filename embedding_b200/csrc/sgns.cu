@@ -280,6 +280,7 @@ k_sgns_items(const sgns_args a) {
     float *s_exp = reinterpret_cast<float *>(smem);
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int GPW = 32 / G; // groups per warp; they run in lockstep
+    const int gpw_eff = (a.dbg & 8) ? 1 : GPW; // test mode: one item at a time (n_groups = 1)
     const int lane = threadIdx.x % G;
     const int gw = (threadIdx.x & 31) / G;
     for (int i = threadIdx.x; i < a.exp_table_size; i += blockDim.x) s_exp[i] = a.exp_table[i];
@@ -306,9 +307,9 @@ k_sgns_items(const sgns_args a) {
     for (int v = 0; v < VPL; v++) { live[v] = lane + v * G < n4; slot[v] = live[v] ? lane + v * G : 0; }
     unsigned long long pairs = 0;
     for (int ep = a.ep_lo; ep < a.ep_hi; ep++) {
-        for (int64_t base = item_lo + warp_id * GPW; base < n_items; base += a.n_groups) { // warp-uniform trip count
+        for (int64_t base = item_lo + warp_id * gpw_eff; base < n_items; base += a.n_groups) { // warp-uniform trip count
             const int64_t item = base + gw;
-            bool valid = item < n_items;
+            bool valid = item < n_items && gw < gpw_eff;
             const int64_t s = valid ? item / a.Lmax : 0;
             const int i = valid ? (int)(item - s * a.Lmax) : 0;
             const int32_t w1 = a.wtok[(int64_t)i * N + s]; // (s, i) = (0, 0) when the item is out of range: in bounds
@@ -465,6 +466,8 @@ k_sgns_items_v2(const sgns_args a) {
     float *s_exp = reinterpret_cast<float *>(smem);
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int GPW = 32 / G;
+    constexpr bool MERGE_SYN0 = GPW > 1; // sum the syn0[last] updates of the warp's groups before reducing them (+6 % at G = 8)
+    const int gpw_eff = (a.dbg & 8) ? 1 : GPW; // test mode: one item at a time (n_groups = 1)
     const int lane = threadIdx.x % G;
     const int gw = (threadIdx.x & 31) / G;
     int32_t *mytok = smem + a.exp_table_size + (threadIdx.x / G) * a.Lmax;
@@ -497,14 +500,21 @@ k_sgns_items_v2(const sgns_args a) {
     struct stage_r { int32_t last; bool act; int j; int32_t mine; int32_t tg[SGNS_CH]; float4 row[SGNS_CH]; float4 v0; };
 
     for (int ep = a.ep_lo; ep < a.ep_hi; ep++) {
-        for (int64_t base = item_lo + warp_id * GPW; base < n_items; base += a.n_groups) { // warp-uniform trip count
+        for (int64_t base = item_lo + warp_id * gpw_eff; base < n_items; base += a.n_groups) { // warp-uniform trip count
             const int64_t item = base + gw;
-            bool valid = item < n_items;
+            bool valid = item < n_items && gw < gpw_eff;
             const int64_t s = valid ? item / Lmax : 0;
             const int i = valid ? (int)(item - s * Lmax) : 0;
+            // all groups of the warp on one sentence (the rule; not at the tail or in the one-item test mode): they
+            // share every context row syn0[last], whose K+1-target updates are then summed in the warp and reduced once
+            const long long s_first = __shfl_sync(FULL, (long long)s, 0); // every lane takes part (no short-circuit)
+            const bool same_s = MERGE_SYN0 && __all_sync(FULL, valid && (long long)s == s_first);
             __syncwarp();
-            for (int j = lane; j < Lmax; j += G) mytok[j] = a.wtok[(int64_t)j * N + s];
+            int n_tok = 0; // tokens of the (compacted) sentence
+            for (int j = lane; j < Lmax; j += G) { const int32_t tk = a.wtok[(int64_t)j * N + s]; mytok[j] = tk; n_tok += tk >= 0; }
             __syncwarp();
+#pragma unroll
+            for (int o = G >> 1; o > 0; o >>= 1) n_tok += __shfl_xor_sync(FULL, n_tok, o);
             const int32_t w1 = mytok[i];
             valid = valid && w1 >= 0;
             if (!__any_sync(FULL, valid)) continue;
@@ -515,18 +525,23 @@ k_sgns_items_v2(const sgns_args a) {
             const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
             // inclusive context range (SkipGram.skipGram); an invalid item gets the empty range
             const int lo = valid ? i - win + b : 1, hi = valid ? i + win - b : 0;
+            // context positions any group of the warp can pair with: units outside [c_min, c_max] are skipped
+            const int c_min = __reduce_min_sync(FULL, valid ? max(lo, 0) : Lmax);
+            const int c_max = __reduce_max_sync(FULL, valid ? min(hi, n_tok - 1) : -1);
+            if (c_max < c_min) continue;
             float4 cur = zero4, d1 = zero4, neu = zero4, v0p = zero4;
             ldcg4_into(cur, row_addr(base1, (uint32_t)w1, pitch), valid && live); // private copy of syn1neg[w1]
             int npairs = 0;
-            int cT = 0, jT = 0;    // (context position, chunk) of the next unit the T stage hands out
-            uint64_t hc = 0;       // pair hash of context position (cT rounded down to G) + lane
+            int cT = c_min, jT = 0; // (context position, chunk) of the next unit the T stage hands out
+            uint64_t hc = 0;        // pair hash of context position hcb * G + lane
+            int hcb = -1;
 
             auto stageT = [&]() { // which (pair, chunk) comes next; request its negatives' table entries
                 stage_t t;
                 t.j = jT;
                 t.last = cT < Lmax ? mytok[cT] : -1;
                 t.act = cT >= lo && cT <= hi && cT != i && t.last >= 0 && t.last != w1;
-                if ((cT & (G - 1)) == 0 && jT == 0) hc = sgns_pair_rng(S, i, cT + lane); // warp-uniform condition
+                if (cT / G != hcb) { hcb = cT / G; hc = sgns_pair_rng(S, i, hcb * G + lane); } // warp-uniform condition
                 const uint64_t ns0 = shfl64(hc, cT & (G - 1), G);
                 const int kk = jT * SGNS_CH + lane;      // this lane's negative of the pair (lanes 0..4 draw)
                 const bool drawer = lane < SGNS_CH && kk < K;
@@ -600,10 +615,22 @@ k_sgns_items_v2(const sgns_args a) {
                     axpy4(d1, gk[SGNS_CH], v0);
                     axpy4(cur, gk[SGNS_CH], v0);
                 }
-                red_add4_if(row_addr(base0, (uint32_t)r.last, pitch), neu, (!MULTI || r.j == NCH - 1) && r.act && live && !(a.dbg & 1));
+                if (!MULTI || r.j == NCH - 1) { // the pair is complete: syn0[last] += neu
+                    if (same_s) { // one row for the whole warp (inactive groups carry neu = 0)
+                        float4 ns = neu;
+#pragma unroll
+                        for (int o = G; o < 32; o <<= 1) {
+                            ns.x += __shfl_xor_sync(FULL, ns.x, o); ns.y += __shfl_xor_sync(FULL, ns.y, o);
+                            ns.z += __shfl_xor_sync(FULL, ns.z, o); ns.w += __shfl_xor_sync(FULL, ns.w, o);
+                        }
+                        red_add4_if(row_addr(base0, (uint32_t)r.last, pitch), ns, gw == 0 && live && !(a.dbg & 1));
+                    } else {
+                        red_add4_if(row_addr(base0, (uint32_t)r.last, pitch), neu, r.act && live && !(a.dbg & 1));
+                    }
+                }
             };
 
-            const int U = Lmax * NCH;
+            const int U = (c_max - c_min + 1) * NCH;
             stage_r rA; // rows not (re)loaded keep stale finite values, cancelled by g = 0; start from zeros
             rA.v0 = zero4;
 #pragma unroll
@@ -651,6 +678,8 @@ k_sgns_items_g4(const sgns_args a) {
     float *s_exp = reinterpret_cast<float *>(smem);
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int GPW = 32 / G;
+    constexpr bool MERGE_SYN0 = false; // summing 8 groups costs 12 shuffles per pair: measured -7 % at D = 16, so off here
+    const int gpw_eff = (a.dbg & 8) ? 1 : GPW; // test mode: one item at a time (n_groups = 1)
     const int lane = threadIdx.x % G;
     const int gw = (threadIdx.x & 31) / G;
     int32_t *mytok = smem + a.exp_table_size + (threadIdx.x / G) * a.Lmax;
@@ -686,14 +715,21 @@ k_sgns_items_g4(const sgns_args a) {
     struct stage_r { int32_t last; bool act; int j; int32_t mineA, mineB; int32_t tg[SGNS_CH]; float4 row[SGNS_CH][VPL]; float4 v0[VPL]; };
 
     for (int ep = a.ep_lo; ep < a.ep_hi; ep++) {
-        for (int64_t base = item_lo + warp_id * GPW; base < n_items; base += a.n_groups) { // warp-uniform trip count
+        for (int64_t base = item_lo + warp_id * gpw_eff; base < n_items; base += a.n_groups) { // warp-uniform trip count
             const int64_t item = base + gw;
-            bool valid = item < n_items;
+            bool valid = item < n_items && gw < gpw_eff;
             const int64_t s = valid ? item / Lmax : 0;
             const int i = valid ? (int)(item - s * Lmax) : 0;
+            // all groups of the warp on one sentence (the rule; not at the tail or in the one-item test mode): they
+            // share every context row syn0[last], whose K+1-target updates are then summed in the warp and reduced once
+            const long long s_first = __shfl_sync(FULL, (long long)s, 0); // every lane takes part (no short-circuit)
+            const bool same_s = MERGE_SYN0 && __all_sync(FULL, valid && (long long)s == s_first);
             __syncwarp();
-            for (int j = lane; j < Lmax; j += G) mytok[j] = a.wtok[(int64_t)j * N + s];
+            int n_tok = 0; // tokens of the (compacted) sentence
+            for (int j = lane; j < Lmax; j += G) { const int32_t tk = a.wtok[(int64_t)j * N + s]; mytok[j] = tk; n_tok += tk >= 0; }
             __syncwarp();
+#pragma unroll
+            for (int o = G >> 1; o > 0; o >>= 1) n_tok += __shfl_xor_sync(FULL, n_tok, o);
             const int32_t w1 = mytok[i];
             valid = valid && w1 >= 0;
             if (!__any_sync(FULL, valid)) continue;
@@ -704,6 +740,10 @@ k_sgns_items_g4(const sgns_args a) {
             const uint64_t S = sgns_sentence_rng(a.seed, ep, s);
             const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
             const int lo = valid ? i - win + b : 1, hi = valid ? i + win - b : 0;
+            // context positions any group of the warp can pair with: units outside [c_min, c_max] are skipped
+            const int c_min = __reduce_min_sync(FULL, valid ? max(lo, 0) : Lmax);
+            const int c_max = __reduce_max_sync(FULL, valid ? min(hi, n_tok - 1) : -1);
+            if (c_max < c_min) continue;
             float4 cur[VPL], d1[VPL], neu[VPL], v0p[VPL];
 #pragma unroll
             for (int v = 0; v < VPL; v++) {
@@ -711,15 +751,16 @@ k_sgns_items_g4(const sgns_args a) {
                 ldcg4_into(cur[v], row_addr(base1, (uint32_t)w1, pitch) + v * 64, valid && live[v]);
             }
             int npairs = 0;
-            int cT = 0, jT = 0;
+            int cT = c_min, jT = 0;
             uint64_t hc = 0;
+            int hcb = -1;
 
             auto stageT = [&]() {
                 stage_t t;
                 t.j = jT;
                 t.last = cT < Lmax ? mytok[cT] : -1;
                 t.act = cT >= lo && cT <= hi && cT != i && t.last >= 0 && t.last != w1;
-                if ((cT & (G - 1)) == 0 && jT == 0) hc = sgns_pair_rng(S, i, cT + lane); // warp-uniform condition
+                if (cT / G != hcb) { hcb = cT / G; hc = sgns_pair_rng(S, i, hcb * G + lane); } // warp-uniform condition
                 const uint64_t ns0 = shfl64(hc, cT & (G - 1), G);
                 const int kkA = jT * SGNS_CH + kA, kkB = jT * SGNS_CH + kB;
                 const bool drawA = kA < SGNS_CH && kkA < K, drawB = kB < SGNS_CH && kkB < K;
@@ -815,13 +856,26 @@ k_sgns_items_g4(const sgns_args a) {
                         axpy4(cur[v], gk[SGNS_CH], v0[v]);
                     }
                 }
-                const uint64_t p0 = row_addr(base0, (uint32_t)r.last, pitch);
+                if (!MULTI || r.j == NCH - 1) { // the pair is complete: syn0[last] += neu
+                    const uint64_t p0 = row_addr(base0, (uint32_t)r.last, pitch);
 #pragma unroll
-                for (int v = 0; v < VPL; v++)
-                    red_add4_if(p0 + v * 64, neu[v], (!MULTI || r.j == NCH - 1) && r.act && live[v] && !(a.dbg & 1));
+                    for (int v = 0; v < VPL; v++) {
+                        if (same_s) { // one row for the whole warp (inactive groups carry neu = 0)
+                            float4 ns = neu[v];
+#pragma unroll
+                            for (int o = G; o < 32; o <<= 1) {
+                                ns.x += __shfl_xor_sync(FULL, ns.x, o); ns.y += __shfl_xor_sync(FULL, ns.y, o);
+                                ns.z += __shfl_xor_sync(FULL, ns.z, o); ns.w += __shfl_xor_sync(FULL, ns.w, o);
+                            }
+                            red_add4_if(p0 + v * 64, ns, gw == 0 && live[v] && !(a.dbg & 1));
+                        } else {
+                            red_add4_if(p0 + v * 64, neu[v], r.act && live[v] && !(a.dbg & 1));
+                        }
+                    }
+                }
             };
 
-            const int U = Lmax * NCH;
+            const int U = (c_max - c_min + 1) * NCH;
             stage_r rA; // rows not (re)loaded keep stale finite values, cancelled by g = 0; start from zeros
 #pragma unroll
             for (int v = 0; v < VPL; v++) {
@@ -874,7 +928,7 @@ struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq,
 // Kernel A (exact order): rows of up to 8 float4 slots are held by ONE thread; wider rows give each lane of a
 // 16- or 32-lane group one 128-bit slot (2 or 4 for rows wider than 32 slots).
 // Kernel B (items): groups of 8 / 16 / 32 lanes, one slot per lane (2 or 4 beyond 32 slots).
-static bool pick_variant(int n4, int negative, bool wide_groups, sgns_variant *out) {
+static bool pick_variant(int n4, int negative, bool narrow_groups, sgns_variant *out) {
     if (n4 > 128) return false;
     sgns_kernel_t seq = nullptr, items = nullptr;
     int Gs = 1, Vs = 1;
@@ -894,8 +948,10 @@ static bool pick_variant(int n4, int negative, bool wide_groups, sgns_variant *o
     }
     int Gi, Vi = 1;
     const bool multi = negative > SGNS_CH; // more than one 5-wide chunk of negatives per pair
-    if (n4 <= 4 && !wide_groups) { Gi = 4; items = multi ? k_sgns_items_g4<1, true> : k_sgns_items_g4<1, false>; }
-    else if (n4 <= 8 && !wide_groups) { Gi = 4; items = multi ? k_sgns_items_g4<2, true> : k_sgns_items_g4<2, false>; }
+    // 4-lane groups only for D <= 16 (+54 % at D = 16; at D = 20 / 32 the two-slot build measured -4 % / +5 %, the
+    // reductions being the limit either way: profiles/r1s12_sgns_narrow_ab.txt) and only when the staleness bound
+    // still lets them fill the GPU (with few items in flight, wider groups mean more warps to hide latency with)
+    if (n4 <= 4 && narrow_groups) { Gi = 4; items = multi ? k_sgns_items_g4<1, true> : k_sgns_items_g4<1, false>; }
     else if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true> : k_sgns_items_v2<8, false>; }
     else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v2<16, true> : k_sgns_items_v2<16, false>; }
     else if (n4 <= 32) { Gi = 32; items = multi ? k_sgns_items_v2<32, true> : k_sgns_items_v2<32, false>; }
@@ -946,9 +1002,9 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
     }
     const int32_t n4 = (p->dim + 3) / 4;        // float4 slots that carry data (zero-padded to whole slots)
     const int32_t stride = ((p->dim + 7) / 8) * 8; // row pitch in floats: rows start on 32-byte sector boundaries
-    const int dbg = getenv("DGE_SGNS_DEBUG") ? atoi(getenv("DGE_SGNS_DEBUG")) : 0; // 1: no reductions (timing experiments), 2: 8-lane groups for narrow rows (A/B), 8: item kernel on ONE warp (tests)
+    const int dbg = getenv("DGE_SGNS_DEBUG") ? atoi(getenv("DGE_SGNS_DEBUG")) : 0; // 1: no reductions (timing experiments), 2 / 32: never / always use 4-lane groups for D <= 16 (A/B, tests), 8: item kernel on ONE warp, one item at a time (tests)
     sgns_variant var;
-    if (!pick_variant(n4, p->negative, (dbg & 2) != 0, &var)) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: dim must be <= 512");
+    if (n4 > 128) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: dim must be <= 512");
     if (p->neg_table_size >= (1 << 30)) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: neg_table_size must be < 2^30");
     DGE_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -1080,6 +1136,11 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         //                             concurrency * Lmax items, or (auto) min(full GPU, 8 * V / (negative + 1)) so
         //                             that a row sees at most ~8 concurrent stale updates
         const bool sequential = p->concurrency == 1 || p->schedule == DGE_SCHEDULE_SENTENCE;
+        {   // kernel variant; 4-lane groups need (sentences in flight allowed) >= what fills the GPU with them
+            const int64_t allowed = p->concurrency > 0 ? (int64_t)p->concurrency * Lmax : (int64_t)SGNS_STALE_BOUND * V / (p->negative + 1);
+            const bool narrow = (dbg & 32) || (!(dbg & 2) && allowed >= (int64_t)ctx->sm_count * 4 * 32);
+            if (!pick_variant(n4, p->negative, narrow, &var)) { dge_free(ctx, d_wtok); return fail("dge_sgns_train: no kernel variant"); }
+        }
         sgns_kernel_t fn = sequential ? var.seq : var.items;
         const int G = sequential ? var.G_seq : var.G_items;
         uint64_t la = 1, lc = 0;
@@ -1104,12 +1165,13 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         if (p->concurrency > 0) want = sequential ? (int64_t)p->concurrency : (int64_t)p->concurrency * Lmax;
         else if (sequential) want = full_groups;
         else want = std::min<int64_t>(full_groups, std::max<int64_t>(gpb, (int64_t)SGNS_STALE_BOUND * V / (p->negative + 1)));
-        if (!sequential && (dbg & 8)) want = 1; // one warp: items strictly in corpus order (arithmetic check against the oracle)
+        if (!sequential && (dbg & 8)) want = 1; // one warp, one item at a time, strictly in corpus order (arithmetic check against the oracle)
         want = std::max<int64_t>(1, std::min(want, units));
         while (threads > 32 && threads > G && want < (int64_t)ctx->sm_count * gpb) { threads >>= 1; gpb = threads / G; }
         if (sequential && want < gpb) { gpb = (int)want; threads = gpb * G; } // kernel B keeps whole warps
         int blocks = (int)((want + gpb - 1) / gpb);
         a.n_groups = (int64_t)blocks * gpb;
+        if (!sequential && (dbg & 8)) a.n_groups = 1; // the single warp advances one item at a time
         ctx->phase_ms["sgns_groups"] = (float)a.n_groups;
         // ---- launches.  Single GPU: one launch over all epochs and sentences.  Data-parallel (ctx has a communicator,
         // or sync_rounds > 0): each epoch is cut into `rounds` slices of sentences; after every slice the ranks

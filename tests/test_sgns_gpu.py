@@ -93,8 +93,8 @@ def test_parallel_schedule_learns_the_same_structure(dge_lib, oracle, ctx, dim):
 def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negative, monkeypatch):
     """The throughput kernel (work item = (sentence, centre), 128-bit L2 reductions, software pipeline) enumerates
     the oracle's pairs and negatives and applies the same update arithmetic; only the interleaving differs.
-    Run on ONE warp (DGE_SGNS_DEBUG=8: items strictly in corpus order, at most 4 centres of one sentence in
-    lockstep) the interleaving is almost the oracle's, so the learned change of both tables must agree with the
+    Run on ONE warp, one item at a time (DGE_SGNS_DEBUG=8: items strictly in corpus order) the interleaving is
+    the oracle's up to the prefetch of a pair's rows, so the learned change of both tables must agree with the
     sequential oracle to ~1 %: any slip in the dot products, the sigmoid table, the negative draws or the row
     addressing is an O(1) error here.  With sentences in flight the deviation grows like sqrt(stale fraction)."""
     rng = np.random.default_rng(100 + dim + negative)
@@ -116,9 +116,10 @@ def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negati
         assert m.pairs == ref["pairs"] and np.array_equal(ids, ref["id_of_word"])
         return np.linalg.norm(syn0 - ref["syn0"]) / learned0, np.linalg.norm(syn1 - ref["syn1neg"]) / learned1
 
-    monkeypatch.setenv("DGE_SGNS_DEBUG", "8")
-    e0, e1 = rel_err()
-    assert e0 < 0.05 and e1 < 0.05, (e0, e1)
+    for flags in (["8"] if dim > 16 else ["8", "40"]):    # 40 = 8 | 32: the 4-lane-group kernel for D <= 16
+        monkeypatch.setenv("DGE_SGNS_DEBUG", flags)
+        e0, e1 = rel_err()
+        assert e0 < 0.02 and e1 < 0.02, (flags, e0, e1)
     monkeypatch.delenv("DGE_SGNS_DEBUG")
     e0, e1 = rel_err(concurrency=2)                 # two sentences in flight
     assert e0 < 0.35 and e1 < 0.35, (e0, e1)
