@@ -357,7 +357,10 @@ def run_gpu_arm(args, w, rank, world, dist):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         nproc = os.cpu_count() or 1
-        r = cpu_reference(w, 1, 0, walk_sample=2_000_000, sent_sample=200_000 if L >= 24 else 1_500_000, threads=min(8, nproc))
+        # bounded sample, ~20 s of CPU work: ~5 s of single-thread walks, ~15 s of 8-thread skip-gram
+        r = cpu_reference(w, 1, 0, walk_sample=10_000_000 if w["name"] != "synth100k" else 4_000_000,
+                          sent_sample=(200_000 if w["dim"] >= 64 else 800_000) if L >= 24 else 5_000_000,
+                          threads=min(8, nproc))
         cpu = dict(
             walk=dict(value=r["walk_steps_per_s"], unit="steps/s", cores=1, kind="port",
                       sample="%d single-thread alias walks x L=%d with a java.util.Random LCG (oracle/dge_oracle.c, %.1f s)"
@@ -368,6 +371,9 @@ def run_gpu_arm(args, w, rank, world, dist):
 
     if rank != 0:
         return
+    # which skip-gram kernel the library picked for this shape (phase "sgns_kernel", sgns.cu pick_variant)
+    sg_kernel = {0: "k_sgns_seq", 1: "k_sgns_items", 2: "k_sgns_items_v2", 3: "k_sgns_items_g4",
+                 4: "k_sgns_items_tp"}.get(int(ctx.phase_ms("sgns_kernel")), "k_sgns_items_v2")
     wk_ms = float(np.mean(walk_kernel_ms))
     sk_ms = float(np.mean(sg_kernel_ms))
     steps_per_launch = per_step_steps
@@ -389,7 +395,7 @@ def run_gpu_arm(args, w, rank, world, dist):
                                 traffic=ncu_traffic(w["name"], "k_walk_alias"), bytes_per_unit=WALK_BYTES_PER_STEP, peak_source=peak_src,
                                 note=resident_note),
                   cpu_baseline=cpu["walk"] if cpu else None),
-        sgns=dict(value=tot_pairs / t_sgns, unit="pairs/s", ms_per_step=t_sgns / args.steps * 1e3, kernel="k_sgns_items_v2",
+        sgns=dict(value=tot_pairs / t_sgns, unit="pairs/s", ms_per_step=t_sgns / args.steps * 1e3, kernel=sg_kernel,
                   kernel_ms=sk_ms, groups_in_flight=ctx.phase_ms("sgns_groups"), sync_rounds=ctx.phase_ms("sgns_rounds"),
                   sync_ms=ctx.phase_ms("sgns_sync"),
                   e2e=dict(value=e_tot_pairs / e_t_sgns, unit="pairs/s", h2d_bytes_per_step=int(d2h_walk), d2h_bytes_per_step=int(d2h_sgns),
@@ -409,11 +415,11 @@ def run_gpu_arm(args, w, rank, world, dist):
                 e2e=stages["walk"]["e2e"],
                 # roofline of the DOMINANT kernel of the step (the skip-gram item kernel, `share` of the step's kernel
                 # time); the walk kernel's own roofline is stages.walk.roofline
-                roofline=dict(stages["sgns"]["roofline"], kernel="k_sgns_items_v2", share_of_step_kernel_time=share,
+                roofline=dict(stages["sgns"]["roofline"], kernel=sg_kernel, share_of_step_kernel_time=share,
                               units="SGNS pairs; the top-level value counts walk steps, see stages"),
                 cpu_baseline=stages["walk"]["cpu_baseline"],
                 clocks=clk, gpu_launches=int(launches), stages=stages,
-                dominant_kernel=dict(name="k_sgns_items_v2", share_of_step_kernel_time=share),
+                dominant_kernel=dict(name=sg_kernel, share_of_step_kernel_time=share),
                 published=dict(note="reference publishes walk wall times only (python/running_time.py:16-20; other hardware, includes "
                                     "String.join + file write): tract alias 0.28 M walks/s, CA alias 0.514 M walks/s = 12.3 M steps/s"))
     print(json.dumps(line), flush=True)

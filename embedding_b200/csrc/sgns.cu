@@ -898,6 +898,158 @@ k_sgns_items_g4(const sgns_args a) {
     if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Kernel E: the item kernel for SMALL VOCABULARIES with narrow rows (the reference's own community-area run:
+// V = 1 848, D = 8).  There the staleness bound (SGNS_STALE_BOUND * V / (K + 1) pairs in flight) leaves ~4 warps per
+// SM, every warp scheduler holds one warp, and the epoch time is  pairs / in-flight pairs x (latency of one pair) --
+// kernels C / D spend ~480 dependent-issue slots per pair step (2 800 cycles measured, profiles/r1s15_bench_ca.json).
+// This kernel shortens that chain instead of widening the machine: the K + 1 targets of a pair are handled by
+// DIFFERENT lanes (target slot ts = 0: the positive target, 1..K: the negatives; NL lanes per target row, one
+// 128-bit slot each), so a pair step is ONE row load, ONE dot product, ONE sigmoid lookup and ONE reduction deep,
+// and the rows of the next pair step are requested before the current one is computed (software pipeline: table
+// lookups two steps ahead, rows one step ahead).  Same draws and arithmetic per target as kernels B-D.
+template <int NL>
+__global__ void __launch_bounds__(128)
+k_sgns_items_tp(const sgns_args a) {
+    static_assert(NL == 1 || NL == 2 || NL == 4, "1, 2 or 4 lanes (128-bit slots) per target row");
+    constexpr int GP = 8 * NL;   // lanes per item: 8 target slots (1 positive + up to 7 negatives) x NL
+    constexpr int GPW = 32 / GP; // items per warp, in lockstep
+    extern __shared__ int32_t smem[];
+    float *s_exp = reinterpret_cast<float *>(smem);
+    constexpr unsigned FULL = 0xffffffffu;
+    const int gpw_eff = (a.dbg & 8) ? 1 : GPW; // test mode: one item at a time (n_groups = 1)
+    const int lane = threadIdx.x % GP;
+    const int gw = (threadIdx.x & 31) / GP;
+    const int ts = lane / NL, q = lane % NL;
+    int32_t *mytok = smem + a.exp_table_size + (threadIdx.x / GP) * a.Lmax;
+    for (int i = threadIdx.x; i < a.exp_table_size; i += blockDim.x) s_exp[i] = a.exp_table[i];
+    __syncthreads();
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int E = a.exp_table_size;
+    const float idx_scale = (float)E / SGNS_MAX_EXP / 2.0f;
+    const int win = a.window;
+    const int64_t N = a.n_sent;
+    const int Lmax = a.Lmax;
+    const int64_t item_lo = a.s_lo * Lmax, n_items = a.s_hi * Lmax;
+    const double inv_total = 1.0 / (double)((int64_t)a.epochs * N);
+    const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
+    const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int K = a.V >= 2 ? a.negative : 0; // <= 7 (host)
+    const bool is_pos = ts == 0, is_neg = ts >= 1 && ts <= K;
+    const bool live = q < a.n4;
+    const float label = is_pos ? 1.f : 0.f;
+    const uint32_t pitch = (uint32_t)a.stride * 4u;
+    const char *base0 = reinterpret_cast<const char *>(a.syn0) + (live ? q : 0) * 16;
+    const char *base1 = reinterpret_cast<const char *>(a.syn1neg) + (live ? q : 0) * 16;
+    const uint64_t my_a = a.lcg_a[is_neg ? ts - 1 : 0], my_c = a.lcg_c[is_neg ? ts - 1 : 0]; // negative ts-1 of the pair
+    const bool reds_on = !(a.dbg & 1);
+    unsigned long long pairs = 0;
+
+    struct stage_t { int32_t last; bool act; uint64_t nsk; int32_t traw; };
+    struct stage_r { int32_t last; bool act; int32_t mine; float4 row, v0; };
+
+    for (int ep = a.ep_lo; ep < a.ep_hi; ep++) {
+        for (int64_t base = item_lo + warp_id * gpw_eff; base < n_items; base += a.n_groups) { // warp-uniform trip count
+            const int64_t item = base + gw;
+            bool valid = item < n_items && gw < gpw_eff;
+            const int64_t s = valid ? item / Lmax : 0;
+            const int i = valid ? (int)(item - s * Lmax) : 0;
+            __syncwarp();
+            int n_tok = 0;
+            for (int j = lane; j < Lmax; j += GP) { const int32_t tk = a.wtok[(int64_t)j * N + s]; mytok[j] = tk; n_tok += tk >= 0; }
+            __syncwarp();
+#pragma unroll
+            for (int o = GP >> 1; o > 0; o >>= 1) n_tok += __shfl_xor_sync(FULL, n_tok, o);
+            const int32_t w1 = mytok[i];
+            valid = valid && w1 >= 0;
+            if (!__any_sync(FULL, valid)) continue;
+            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * N + s) * inv_total);
+            if (alpha < a.min_lr) alpha = a.min_lr;
+            const float g_hi = (label - 1.f) * alpha, g_lo = label * alpha; // saturated sigmoid: dot > 6, dot < -6
+            const uint64_t S = sgns_sentence_rng(a.seed, ep, s);
+            const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
+            const int lo = valid ? i - win + b : 1, hi = valid ? i + win - b : 0; // inclusive context range; empty if invalid
+            const int c_min = __reduce_min_sync(FULL, valid ? max(lo, 0) : Lmax);
+            const int c_max = __reduce_max_sync(FULL, valid ? min(hi, n_tok - 1) : -1);
+            if (c_max < c_min) continue;
+            float4 cur = zero4, d1 = zero4; // positive-slot lanes: private copy of syn1neg[w1] and its accumulated delta
+            ldcg4_into(cur, row_addr(base1, (uint32_t)w1, pitch), valid && live && is_pos);
+            int npairs = 0;
+            int cT = c_min;
+            uint64_t hc = 0; // pair hash of context position hcb * GP + lane
+            int hcb = -1;
+
+            auto stageT = [&]() { // next pair step: which context, and this lane's negative-table entry
+                stage_t t;
+                t.last = cT < Lmax ? mytok[cT] : -1;
+                t.act = cT >= lo && cT <= hi && cT != i && t.last >= 0 && t.last != w1;
+                if (cT / GP != hcb) { hcb = cT / GP; hc = sgns_pair_rng(S, i, hcb * GP + lane); } // warp-uniform condition
+                const uint64_t ns0 = shfl64(hc, cT & (GP - 1), GP);
+                t.nsk = my_a * ns0 + my_c; // the LCG is affine: state after ts steps
+                t.traw = -2;               // "draws nothing"
+                if (is_neg && t.act) t.traw = a.neg_table[mod48(t.nsk >> 16, tsize, inv_tsize)];
+                cT++;
+                return t;
+            };
+            auto stageR = [&](const stage_t &t, stage_r &r) { // resolve the negative, request this lane's rows
+                r.last = t.last; r.act = t.act;
+                int32_t tt = t.traw;
+                const bool redraw = tt != -2 && (tt <= 0 || tt >= a.V); // DL4J: target = r % (V-1) + 1
+                if (__any_sync(FULL, redraw)) {
+                    if (redraw) tt = (int32_t)mod64(t.nsk, vm1, inv_vm1) + 1;
+                }
+                r.mine = (tt != -2 && tt != w1) ? tt : -1;
+                ldcg4_into(r.v0, row_addr(base0, (uint32_t)t.last, pitch), t.act && live);     // same row in all 8 slots: one sector
+                ldcg4_into(r.row, row_addr(base1, (uint32_t)r.mine, pitch), r.mine >= 0 && live);
+            };
+            auto compute = [&](const stage_r &r) {
+                if (!__any_sync(FULL, r.act)) return;
+                npairs += r.act;
+                const float4 rowv = is_pos ? cur : r.row;
+                float dot = live ? dot4(r.v0, rowv) : 0.f;
+#pragma unroll
+                for (int o = NL >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
+                float g = sgns_g_lane(dot, label, alpha, g_hi, g_lo, s_exp, E, idx_scale);
+                if (!(is_pos ? r.act : r.mine >= 0)) g = 0.f; // idle slots, skipped negatives, inactive items
+                const float4 upd = scale4(g, r.v0);            // target row += g * syn0[last]
+                red_add4_if(row_addr(base1, (uint32_t)r.mine, pitch), upd, g != 0.f && live && !is_pos && reds_on);
+                float4 ns = scale4(g, rowv);                   // this target's share of neu1e
+                if (is_pos) { axpy4(d1, 1.f, upd); axpy4(cur, 1.f, upd); }
+#pragma unroll
+                for (int o = NL; o < GP; o <<= 1) {
+                    ns.x += __shfl_xor_sync(FULL, ns.x, o); ns.y += __shfl_xor_sync(FULL, ns.y, o);
+                    ns.z += __shfl_xor_sync(FULL, ns.z, o); ns.w += __shfl_xor_sync(FULL, ns.w, o);
+                }
+                red_add4_if(row_addr(base0, (uint32_t)r.last, pitch), ns, is_pos && r.act && live && reds_on); // syn0[last] += neu1e
+            };
+
+            const int U = c_max - c_min + 1;
+            stage_r rA, rB; // rows not (re)loaded keep stale finite values, cancelled by g = 0; start from zeros
+            rA.v0 = rA.row = rB.v0 = rB.row = zero4;
+            // table entries one pair step ahead, rows one pair step ahead of their use.  (Requesting the table entries
+            // two steps ahead measured the same 2.6 G pairs/s on the CA workload, profiles/logs/gpurun_out_session17.log:
+            // the pair step is bound by its own dependent instruction chain, ~250 issue slots at ~7 cycles each.)
+            stage_t t1 = stageT();
+            stageR(t1, rA); // rows of step 0
+            t1 = stageT();  // table entry of step 1
+            for (int u = 0; u < U; u += 2) {
+                stageR(t1, rB); // rows of step u + 1 (no-ops past the end: act is false there)
+                t1 = stageT();
+                compute(rA);
+                if (u + 1 < U) {
+                    stageR(t1, rA);
+                    t1 = stageT();
+                    compute(rB);
+                }
+            }
+            red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, valid && live && is_pos && reds_on);
+            pairs += (unsigned)npairs;
+        }
+    }
+    if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
+}
+
 // multi-GPU delta exchange (see dge_sgns_train): cur -= base  ...all-reduce(cur)...  base += cur; cur = base
 __global__ void k_delta_begin(float *__restrict__ c0, const float *__restrict__ b0, float *__restrict__ c1,
                               const float *__restrict__ b1, size_t n) {
@@ -923,12 +1075,13 @@ __global__ void k_delta_end(float *__restrict__ c0, float *__restrict__ b0, floa
 }
 
 typedef void (*sgns_kernel_t)(const sgns_args);
-struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq, items; };
+struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq, items; int items_code; };
+// items_code (reported as phase "sgns_kernel"): 1 k_sgns_items, 2 k_sgns_items_v2, 3 k_sgns_items_g4, 4 k_sgns_items_tp; 0 k_sgns_seq
 
 // Kernel A (exact order): rows of up to 8 float4 slots are held by ONE thread; wider rows give each lane of a
 // 16- or 32-lane group one 128-bit slot (2 or 4 for rows wider than 32 slots).
 // Kernel B (items): groups of 8 / 16 / 32 lanes, one slot per lane (2 or 4 beyond 32 slots).
-static bool pick_variant(int n4, int negative, bool narrow_groups, sgns_variant *out) {
+static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_parallel, sgns_variant *out) {
     if (n4 > 128) return false;
     sgns_kernel_t seq = nullptr, items = nullptr;
     int Gs = 1, Vs = 1;
@@ -951,14 +1104,22 @@ static bool pick_variant(int n4, int negative, bool narrow_groups, sgns_variant 
     // 4-lane groups only for D <= 16 (+54 % at D = 16; at D = 20 / 32 the two-slot build measured -4 % / +5 %, the
     // reductions being the limit either way: profiles/r1s12_sgns_narrow_ab.txt) and only when the staleness bound
     // still lets them fill the GPU (with few items in flight, wider groups mean more warps to hide latency with)
-    if (n4 <= 4 && narrow_groups) { Gi = 4; items = multi ? k_sgns_items_g4<1, true> : k_sgns_items_g4<1, false>; }
+    int code = 2;
+    // target-parallel groups (kernel E) for narrow rows when the staleness bound leaves the GPU latency-bound
+    if (n4 <= 4 && negative <= 7 && target_parallel) {
+        code = 4;
+        if (n4 == 1) { Gi = 8; items = k_sgns_items_tp<1>; }
+        else if (n4 == 2) { Gi = 16; items = k_sgns_items_tp<2>; }
+        else { Gi = 32; items = k_sgns_items_tp<4>; }
+    }
+    else if (n4 <= 4 && narrow_groups) { Gi = 4; code = 3; items = multi ? k_sgns_items_g4<1, true> : k_sgns_items_g4<1, false>; }
     else if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true> : k_sgns_items_v2<8, false>; }
     else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v2<16, true> : k_sgns_items_v2<16, false>; }
     else if (n4 <= 32) { Gi = 32; items = multi ? k_sgns_items_v2<32, true> : k_sgns_items_v2<32, false>; }
-    else if (n4 <= 64) { Gi = 32; Vi = 2; items = k_sgns_items<32, 2>; }
-    else { Gi = 32; Vi = 4; items = k_sgns_items<32, 4>; }
+    else if (n4 <= 64) { Gi = 32; Vi = 2; code = 1; items = k_sgns_items<32, 2>; }
+    else { Gi = 32; Vi = 4; code = 1; items = k_sgns_items<32, 4>; }
     out->G_seq = Gs; out->VPL_seq = Vs; out->seq = seq;
-    out->G_items = Gi; out->VPL_items = Vi; out->items = items;
+    out->G_items = Gi; out->VPL_items = Vi; out->items = items; out->items_code = code;
     return true;
 }
 
@@ -1002,7 +1163,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
     }
     const int32_t n4 = (p->dim + 3) / 4;        // float4 slots that carry data (zero-padded to whole slots)
     const int32_t stride = ((p->dim + 7) / 8) * 8; // row pitch in floats: rows start on 32-byte sector boundaries
-    const int dbg = getenv("DGE_SGNS_DEBUG") ? atoi(getenv("DGE_SGNS_DEBUG")) : 0; // 1: no reductions (timing experiments), 2 / 32: never / always use 4-lane groups for D <= 16 (A/B, tests), 8: item kernel on ONE warp, one item at a time (tests)
+    const int dbg = getenv("DGE_SGNS_DEBUG") ? atoi(getenv("DGE_SGNS_DEBUG")) : 0; // 1: no reductions (timing experiments), 2 / 32: never / always use 4-lane groups for D <= 16 (A/B, tests), 8: item kernel on ONE warp, one item at a time (tests), 64 / 128: always / never use the target-parallel kernel for D <= 16, K <= 7 (A/B, tests)
     sgns_variant var;
     if (n4 > 128) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: dim must be <= 512");
     if (p->neg_table_size >= (1 << 30)) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: neg_table_size must be < 2^30");
@@ -1139,7 +1300,9 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         {   // kernel variant; 4-lane groups need (sentences in flight allowed) >= what fills the GPU with them
             const int64_t allowed = p->concurrency > 0 ? (int64_t)p->concurrency * Lmax : (int64_t)SGNS_STALE_BOUND * V / (p->negative + 1);
             const bool narrow = (dbg & 32) || (!(dbg & 2) && allowed >= (int64_t)ctx->sm_count * 4 * 32);
-            if (!pick_variant(n4, p->negative, narrow, &var)) { dge_free(ctx, d_wtok); return fail("dge_sgns_train: no kernel variant"); }
+            // fewer pairs in flight than the 8-lane kernel needs to fill the GPU (5 blocks x 16 groups per SM): latency-bound
+            const bool tp = (dbg & 64) || (!(dbg & (128 | 32)) && allowed < (int64_t)ctx->sm_count * 5 * 16);
+            if (!pick_variant(n4, p->negative, narrow, tp, &var)) { dge_free(ctx, d_wtok); return fail("dge_sgns_train: no kernel variant"); }
         }
         sgns_kernel_t fn = sequential ? var.seq : var.items;
         const int G = sequential ? var.G_seq : var.G_items;
@@ -1173,6 +1336,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         a.n_groups = (int64_t)blocks * gpb;
         if (!sequential && (dbg & 8)) a.n_groups = 1; // the single warp advances one item at a time
         ctx->phase_ms["sgns_groups"] = (float)a.n_groups;
+        ctx->phase_ms["sgns_kernel"] = (float)(sequential ? 0 : var.items_code);
         // ---- launches.  Single GPU: one launch over all epochs and sentences.  Data-parallel (ctx has a communicator,
         // or sync_rounds > 0): each epoch is cut into `rounds` slices of sentences; after every slice the ranks
         // exchange the SUM of their embedding deltas (cur - base) with one NCCL all-reduce per table over NVLink and

@@ -1,6 +1,7 @@
 """One short pass of the hot path for profiling under ncu (graph build -> walks -> SGNS).
     python scripts/prof_path.py tract 500000 [concurrency]
     python scripts/prof_path.py synth 20000 2000000 [dim]
+    python scripts/prof_path.py ca 2000000 [concurrency] [dim]      (77 community areas x 24, D = 8)
 """
 import os
 import sys
@@ -22,10 +23,16 @@ def main():
     else:
         n_walks = int(sys.argv[2])
         conc = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-        ids, z, L, dim = synth.tract_ids(), synth.poi_latents(), (24 if level == "tract24" else 8), 20
-        fl = host.Flows(ids, synth.planted_flow_tensor(z))
-        host.CrossTimeGraph.numLayer = L
-        gh = host.CrossTimeGraph.constructGraph_tract(fl, ctx=ctx)
+        if level == "ca":
+            ids, z, L, dim = synth.ca_ids(), synth.ca_latents(), 24, (int(sys.argv[4]) if len(sys.argv) > 4 else 8)
+            fl = host.Flows(ids, synth.planted_flow_tensor(z, mean_trips_per_pair_hour=2.0))
+            host.CrossTimeGraph.numLayer = L
+            gh = host.CrossTimeGraph.constructGraph_CA(fl, ctx=ctx)
+        else:
+            ids, z, L, dim = synth.tract_ids(), synth.poi_latents(), (24 if level == "tract24" else 8), 20
+            fl = host.Flows(ids, synth.planted_flow_tensor(z))
+            host.CrossTimeGraph.numLayer = L
+            gh = host.CrossTimeGraph.constructGraph_tract(fl, ctx=ctx)
         gh.initiateAliasTables()
         G = gh._graph
         window = L
@@ -33,7 +40,7 @@ def main():
         corpus = G.walk(n_walks, L, seed=1 + rep)
         m = abi.Model.train(ctx, [corpus], abi.sgns_params(dim=dim, window=window, seed=1, concurrency=conc))
         print("walk ms", ctx.phase_ms("walk"), "steps", corpus.count_tokens(), "sgns ms", ctx.phase_ms("sgns"),
-              "pairs", m.pairs, "groups", ctx.phase_ms("sgns_groups"),
+              "pairs", m.pairs, "groups", ctx.phase_ms("sgns_groups"), "kernel", ctx.phase_ms("sgns_kernel"),
               "Mpairs/s", m.pairs / ctx.phase_ms("sgns") / 1e3, "Msteps/s", corpus.count_tokens() / ctx.phase_ms("walk") / 1e3)
 
 

@@ -1,0 +1,116 @@
+"""GPU parity at BASELINE.json's FULL size (configs[1]: tract x 24, 15,000,000 flow walks, D=20 window=24 K=5),
+through size-independent properties: the oracle cannot replay 3.6e8 steps + 4.1e9 pairs in seconds, so the walks are
+validated edge by edge against the CSR the oracle agrees with bit for bit, their frequencies by chi-square against
+w/outDegree (LayeredGraph.java:54-82,104-116,232-252), the shards by union, and the skip-gram epoch through the
+oracle's pair enumeration (a count over the whole corpus) plus the vocabulary rules of SURVEY A14."""
+import numpy as np
+import pytest
+from scipy import stats
+
+pytestmark = pytest.mark.gpu
+
+N_WALKS = 15_000_000      # DeepWalk.java:102-104 (tract level)
+L = 24
+
+
+def _chi_square(obs, p):
+    """chi-square of observed counts against probabilities p; bins expecting < 5 are pooled, impossible bins must be empty."""
+    n = obs.sum()
+    assert (obs[p == 0] == 0).all()
+    obs, p = obs[p > 0], p[p > 0] / p[p > 0].sum()
+    big = p * n >= 5
+    o, x = obs[big], p[big] * n
+    if (~big).any():
+        o, x = np.append(o, obs[~big].sum()), np.append(x, p[~big].sum() * n)
+    return stats.chisquare(o, x * o.sum() / x.sum())
+
+
+@pytest.fixture(scope="module")
+def full(dge_lib, ctx):
+    import bench
+    w = bench.make_workload("tract24")
+    f = w["flow"]
+    G = dge_lib.Graph(ctx, f["nv"], f["src"], f["dst"], f["w"], f["sources"])
+    corpus = G.walk(N_WALKS, L, seed=2013)
+    tok = corpus.tokens()
+    yield dict(w=w, f=f, G=G, corpus=corpus, tok=tok, tables=G.tables())
+    corpus.free()
+    G.free()
+
+
+def test_every_step_of_the_full_corpus_is_an_edge(full):
+    f, tok, t = full["f"], full["tok"], full["tables"]
+    nv = f["nv"]
+    assert tok.shape == (N_WALKS, L)
+    adj = np.zeros((nv, nv), np.bool_)
+    adj[f["src"], f["dst"]] = True
+    deg = np.diff(t["row_ptr"])
+    is_source = np.zeros(nv, np.bool_)
+    is_source[f["sources"]] = True
+    v_layer = f["v_layer"]
+    pos = np.arange(L, dtype=v_layer.dtype)[None, :]
+    n_tok = 0
+    for lo in range(0, N_WALKS, 1_000_000):
+        c = tok[lo:lo + 1_000_000]
+        valid = c >= 0
+        n_tok += int(valid.sum())
+        assert (c < nv).all()
+        assert np.all(valid[:, :-1] >= valid[:, 1:])                       # padding is a suffix
+        assert is_source[c[:, 0]].all()                                    # LayeredGraph.java:234-242
+        a, b = c[:, :-1], c[:, 1:]
+        step = valid[:, 1:]
+        assert adj[a[step], b[step]].all()                                 # every transition is a CSR edge
+        assert np.array_equal(v_layer[c[valid]], np.broadcast_to(pos, c.shape)[valid])   # layer h -> h+1
+        stop = valid[:, :-1] & ~valid[:, 1:]
+        assert (deg[a[stop]] == 0).all()                                   # a walk only ends early at a dead end (:247-248)
+    assert full["corpus"].count_tokens() == n_tok
+
+
+def test_full_corpus_frequencies_chi_square(full):
+    f, tok, t = full["f"], full["tok"], full["tables"]
+    nv = f["nv"]
+    # source draw: outDegree / sourceWeightSum over 15M draws
+    cnt = np.bincount(tok[:, 0], minlength=nv)[f["sources"]]
+    chi = _chi_square(cnt, t["out_degree"][f["sources"]] / t["source_weight_sum"])
+    assert chi.pvalue > 1e-4, chi
+    # transitions out of the busiest vertex of four different layers
+    for j in (0, 7, 15, 22):
+        col = tok[:, j]
+        v = int(np.argmax(np.bincount(col[col >= 0], minlength=nv)))
+        nxt = tok[col == v, j + 1]
+        b, e = t["row_ptr"][v], t["row_ptr"][v + 1]
+        dests, inv = np.unique(t["col"][b:e], return_inverse=True)
+        pw = np.bincount(inv, weights=t["w"][b:e]) / t["out_degree"][v]
+        obs = np.bincount(np.searchsorted(dests, nxt), minlength=len(dests))
+        assert obs.sum() == len(nxt) and np.array_equal(dests[np.searchsorted(dests, nxt)], nxt)
+        chi = _chi_square(obs, pw)
+        assert chi.pvalue > 1e-4, (j, v, chi)
+
+
+def test_full_corpus_is_the_union_of_its_shards(full):
+    """walk ids [a, b) give the same tokens on any device / in any launch."""
+    G, tok = full["G"], full["tok"]
+    half = N_WALKS // 2
+    for first, n in ((0, half), (half, N_WALKS - half)):
+        c = G.walk(n, L, seed=2013, first_walk_id=first)
+        got = c.tokens()
+        c.free()
+        assert np.array_equal(got, tok[first:first + n])
+
+
+def test_full_size_skipgram_epoch_enumerates_the_oracle_pairs(dge_lib, oracle, ctx, full):
+    f, tok, corpus = full["f"], full["tok"], full["corpus"]
+    kw = dict(dim=20, window=L, negative=5, min_count=2, seed=1)
+    m = dge_lib.Model.train(ctx, [corpus], dge_lib.sgns_params(**kw))       # automatic (full-GPU) schedule
+    syn0, ids = m.vectors()
+    want_pairs = oracle.sgns_count_pairs(tok, f["nv"], oracle.sgns_params(**kw))
+    assert m.pairs == want_pairs
+    # vocabulary: tokens seen at least minWordFrequency times, by descending count
+    cnt = np.bincount(tok[tok >= 0], minlength=f["nv"])
+    assert len(ids) == int((cnt >= 2).sum()) and len(np.unique(ids)) == len(ids)
+    assert (cnt[ids] >= 2).all() and np.all(np.diff(cnt[ids]) <= 0)
+    assert syn0.shape == (len(ids), 20) and np.isfinite(syn0).all()
+    # the epoch moved the rows away from their (U - 0.5) / D start (a rare token may only ever meet zero syn1neg rows)
+    init = oracle.init_syn0(len(ids), 20, 1)
+    assert (np.abs(syn0 - init).max(axis=1) > 0).mean() > 0.99
+    m.free()

@@ -89,7 +89,7 @@ def test_parallel_schedule_learns_the_same_structure(dge_lib, oracle, ctx, dim):
     assert g_gpu > 0.5 * g_ref, (g_gpu, g_ref)
 
 
-@pytest.mark.parametrize("dim,negative", [(8, 5), (8, 10), (20, 5), (20, 12), (32, 5), (64, 5), (100, 7), (128, 5), (128, 20)])
+@pytest.mark.parametrize("dim,negative", [(2, 5), (4, 7), (8, 5), (8, 10), (12, 3), (16, 5), (20, 5), (20, 12), (32, 5), (64, 5), (100, 7), (128, 5), (128, 20)])
 def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negative, monkeypatch):
     """The throughput kernel (work item = (sentence, centre), 128-bit L2 reductions, software pipeline) enumerates
     the oracle's pairs and negatives and applies the same update arithmetic; only the interleaving differs.
@@ -116,7 +116,12 @@ def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negati
         assert m.pairs == ref["pairs"] and np.array_equal(ids, ref["id_of_word"])
         return np.linalg.norm(syn0 - ref["syn0"]) / learned0, np.linalg.norm(syn1 - ref["syn1neg"]) / learned1
 
-    for flags in (["8"] if dim > 16 else ["8", "40"]):    # 40 = 8 | 32: the 4-lane-group kernel for D <= 16
+    flag_sets = ["8"]
+    if dim <= 16:
+        flag_sets.append("40")                      # 8 | 32: the 4-lane-group kernel for D <= 16
+        if negative <= 7:
+            flag_sets.append("72")                  # 8 | 64: the target-parallel kernel (D <= 16, K <= 7)
+    for flags in flag_sets:
         monkeypatch.setenv("DGE_SGNS_DEBUG", flags)
         e0, e1 = rel_err()
         assert e0 < 0.02 and e1 < 0.02, (flags, e0, e1)
