@@ -1050,26 +1050,43 @@ k_sgns_items_tp(const sgns_args a) {
     if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
 }
 
-// multi-GPU delta exchange (see dge_sgns_train): cur -= base  ...all-reduce(cur)...  base += cur; cur = base
+// multi-GPU delta exchange (see dge_sgns_train):  cur -= base  ...all-reduce(cur, touched)...  base += cur / div; cur = base.
+// touched[row] (syn0 rows first, then syn1neg rows) is 1 on a rank whose delta of that row is non-zero; after the
+// all-reduce it counts the ranks that contributed to the row, and div is chosen by the combine rule (DGE_COMBINE_*).
+#define DGE_COMBINE_SUM 0          // base += sum of the deltas: every update applied; diverges when several ranks saturate the same row
+#define DGE_COMBINE_MEAN 1         // base += sum / world: parameter averaging (rows only one rank saw learn world times slower)
+#define DGE_COMBINE_CONTRIBUTORS 2 // base += sum / max(1, ranks that touched the row): the default
+#define DGE_COMBINE_SQRT 3         // base += sum / sqrt(max(1, ranks that touched the row))
 __global__ void k_delta_begin(float *__restrict__ c0, const float *__restrict__ b0, float *__restrict__ c1,
-                              const float *__restrict__ b1, size_t n) {
-    size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4, stride = (size_t)gridDim.x * blockDim.x * 4;
-    for (; i < n; i += stride) { // n is a multiple of 4 (rows are whole float4 slots)
+                              const float *__restrict__ b1, size_t n, int32_t stride, int32_t V, float *__restrict__ touched) {
+    size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4, step = (size_t)gridDim.x * blockDim.x * 4;
+    for (; i < n; i += step) { // n is a multiple of 4 (rows are whole float4 slots)
         float4 x = *reinterpret_cast<float4 *>(c0 + i), y = *reinterpret_cast<const float4 *>(b0 + i);
-        *reinterpret_cast<float4 *>(c0 + i) = make_float4(x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w);
+        x = make_float4(x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w);
+        *reinterpret_cast<float4 *>(c0 + i) = x;
+        const size_t row = i / (size_t)stride;
+        if (x.x != 0.f || x.y != 0.f || x.z != 0.f || x.w != 0.f) touched[row] = 1.f; // same value from every writer
         x = *reinterpret_cast<float4 *>(c1 + i); y = *reinterpret_cast<const float4 *>(b1 + i);
-        *reinterpret_cast<float4 *>(c1 + i) = make_float4(x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w);
+        x = make_float4(x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w);
+        *reinterpret_cast<float4 *>(c1 + i) = x;
+        if (x.x != 0.f || x.y != 0.f || x.z != 0.f || x.w != 0.f) touched[(size_t)V + row] = 1.f;
     }
 }
+__device__ __forceinline__ float combine_div(float contributors, int mode, int world) {
+    const float c = contributors > 1.f ? contributors : 1.f;
+    return mode == DGE_COMBINE_MEAN ? (float)world : (mode == DGE_COMBINE_CONTRIBUTORS ? c : (mode == DGE_COMBINE_SQRT ? sqrtf(c) : 1.f));
+}
 __global__ void k_delta_end(float *__restrict__ c0, float *__restrict__ b0, float *__restrict__ c1, float *__restrict__ b1,
-                            size_t n) {
-    size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4, stride = (size_t)gridDim.x * blockDim.x * 4;
-    for (; i < n; i += stride) {
+                            size_t n, int32_t stride, int32_t V, const float *__restrict__ touched, int mode, int world) {
+    size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4, step = (size_t)gridDim.x * blockDim.x * 4;
+    for (; i < n; i += step) {
+        const size_t row = i / (size_t)stride;
+        const float d0 = combine_div(touched[row], mode, world), d1 = combine_div(touched[(size_t)V + row], mode, world);
         float4 x = *reinterpret_cast<float4 *>(c0 + i), y = *reinterpret_cast<float4 *>(b0 + i);
-        y = make_float4(y.x + x.x, y.y + x.y, y.z + x.z, y.w + x.w);
+        y = make_float4(y.x + __fdiv_rn(x.x, d0), y.y + __fdiv_rn(x.y, d0), y.z + __fdiv_rn(x.z, d0), y.w + __fdiv_rn(x.w, d0));
         *reinterpret_cast<float4 *>(b0 + i) = y; *reinterpret_cast<float4 *>(c0 + i) = y;
         x = *reinterpret_cast<float4 *>(c1 + i); y = *reinterpret_cast<float4 *>(b1 + i);
-        y = make_float4(y.x + x.x, y.y + x.y, y.z + x.z, y.w + x.w);
+        y = make_float4(y.x + __fdiv_rn(x.x, d1), y.y + __fdiv_rn(x.y, d1), y.z + __fdiv_rn(x.z, d1), y.w + __fdiv_rn(x.w, d1));
         *reinterpret_cast<float4 *>(b1 + i) = y; *reinterpret_cast<float4 *>(c1 + i) = y;
     }
 }
@@ -1339,18 +1356,25 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         ctx->phase_ms["sgns_kernel"] = (float)(sequential ? 0 : var.items_code);
         // ---- launches.  Single GPU: one launch over all epochs and sentences.  Data-parallel (ctx has a communicator,
         // or sync_rounds > 0): each epoch is cut into `rounds` slices of sentences; after every slice the ranks
-        // exchange the SUM of their embedding deltas (cur - base) with one NCCL all-reduce per table over NVLink and
-        // all continue from base + sum.  All updates of all ranks are applied (the multi-GPU analogue of Hogwild
-        // threads); averaging the parameters instead would divide the learning rate by the world size.
+        // exchange their embedding deltas (cur - base) with one NCCL all-reduce per table over NVLink and all continue from
+        // base + combined delta.  Combine rule: per ROW, the sum of the deltas divided by the number of ranks that
+        // touched the row -- a row only one rank saw gets that rank's full update, a hub row every rank saw gets the
+        // average.  The plain sum ("all updates applied") is unstable: ranks that each saturate a hot row overshoot by
+        // a factor of world; emulated with the oracle it explodes at world = 8 (|syn0| ~ 1e8) and on 2 GPUs it fell
+        // to a kNN agreement of 0.24 / 0.10 / 0.02 at 6 / 24 / 96 rounds (profiles/r1s20_dp_diagnose.json), while plain
+        // parameter averaging divides the learning rate of every rare row by the world size.
         int rounds = 1;
         if (multi || p->sync_rounds > 0) {
             rounds = p->sync_rounds > 0 ? p->sync_rounds : (int)std::max<int64_t>(4, (max_sent + (1 << 20) - 1) >> 20);
             rounds = (int)std::min<int64_t>(rounds, std::max<int64_t>(1, max_sent));
         }
-        float *base0 = nullptr, *base1 = nullptr;
+        float *base0 = nullptr, *base1 = nullptr, *touched = nullptr;
+        // how the per-rank deltas are combined (A/B and the emulation in oracle/sgns_oracle.c ora_sgns_train_dp)
+        const int combine = getenv("DGE_SGNS_COMBINE") ? atoi(getenv("DGE_SGNS_COMBINE")) : DGE_COMBINE_CONTRIBUTORS;
         if (rounds > 1 || multi) {
-            if (dge_malloc(ctx, &base0, nel) != cudaSuccess || dge_malloc(ctx, &base1, nel) != cudaSuccess) {
-                dge_free(ctx, base0); dge_free(ctx, d_wtok);
+            if (dge_malloc(ctx, &base0, nel) != cudaSuccess || dge_malloc(ctx, &base1, nel) != cudaSuccess ||
+                dge_malloc(ctx, &touched, 2 * (size_t)V) != cudaSuccess) {
+                dge_free(ctx, base0); dge_free(ctx, base1); dge_free(ctx, d_wtok);
                 return fail("dge_sgns_train: cudaMalloc of the delta base failed");
             }
             cudaMemcpyAsync(base0, m->syn0, nel * sizeof(float), cudaMemcpyDeviceToDevice, st);
@@ -1378,10 +1402,12 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
                         ctx->launches++;
                     }
                     cudaEventRecord(e0, st);
-                    k_delta_begin<<<grid_e, 256, 0, st>>>(m->syn0, base0, m->syn1neg, base1, nel);
+                    cudaMemsetAsync(touched, 0, 2 * (size_t)V * sizeof(float), st);
+                    k_delta_begin<<<grid_e, 256, 0, st>>>(m->syn0, base0, m->syn1neg, base1, nel, stride, V, touched);
                     comm_rc = dge_comm_allreduce_sum_f32(ctx, m->syn0, nel);
                     if (comm_rc == DGE_OK) comm_rc = dge_comm_allreduce_sum_f32(ctx, m->syn1neg, nel);
-                    k_delta_end<<<grid_e, 256, 0, st>>>(m->syn0, base0, m->syn1neg, base1, nel);
+                    if (comm_rc == DGE_OK) comm_rc = dge_comm_allreduce_sum_f32(ctx, touched, 2 * (size_t)V);
+                    k_delta_end<<<grid_e, 256, 0, st>>>(m->syn0, base0, m->syn1neg, base1, nel, stride, V, touched, combine, ctx->world);
                     ctx->launches += 2;
                     cudaEventRecord(e1, st);
                     cudaEventSynchronize(e1);
@@ -1394,7 +1420,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         }
         t_sgns.stop();
         ctx->phase_ms["sgns_sync"] = sync_ms;
-        dge_free(ctx, base0); dge_free(ctx, base1);
+        dge_free(ctx, base0); dge_free(ctx, base1); dge_free(ctx, touched);
         if (comm_rc != DGE_OK) { dge_free(ctx, d_wtok); cleanup(); model_release(m); return comm_rc; }
         ce = cudaGetLastError();
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);

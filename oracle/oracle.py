@@ -93,6 +93,8 @@ def lib():
     L.ora_init_syn0.argtypes = [i32, i32, u64, pf32]
     L.ora_sgns_train.restype = vp
     L.ora_sgns_train.argtypes = [pi32, i64, i32, i32, pp, pi64]
+    L.ora_sgns_train_dp.restype = vp
+    L.ora_sgns_train_dp.argtypes = [pi32, i64, i32, i32, pp, i32, i32, i32, pi64]
     L.ora_model_free.argtypes = [vp]
     L.ora_model_vocab_size.argtypes = [vp]
     L.ora_model_get.argtypes = [vp, pf32, pf32, pi32]
@@ -270,6 +272,25 @@ def sgns_train(tokens, n_ids, params):
     n_sent, L = tokens.shape
     pairs = C.c_int64()
     h = lib().ora_sgns_train(_p(tokens, C.c_int32), n_sent, L, n_ids, C.byref(params), C.byref(pairs))
+    V = lib().ora_model_vocab_size(h)
+    syn0 = np.empty((V, params.dim), np.float32)
+    syn1 = np.empty((V, params.dim), np.float32)
+    ids = np.empty(V, np.int32)
+    lib().ora_model_get(h, _p(syn0, C.c_float), _p(syn1, C.c_float), _p(ids, C.c_int32))
+    lib().ora_model_free(h)
+    return dict(syn0=syn0, syn1neg=syn1, id_of_word=ids, pairs=pairs.value)
+
+
+COMBINE_SUM, COMBINE_MEAN, COMBINE_CONTRIBUTORS = 0, 1, 2
+
+
+def sgns_train_dp(tokens, n_ids, params, world, rounds, combine):
+    """Data-parallel emulation of stage 2 (ora_sgns_train_dp): contiguous sentence shards, per-round delta exchange."""
+    tokens = np.ascontiguousarray(tokens, np.int32)
+    n_sent, L = tokens.shape
+    pairs = C.c_int64()
+    h = lib().ora_sgns_train_dp(_p(tokens, C.c_int32), n_sent, L, n_ids, C.byref(params), world, rounds, combine,
+                                C.byref(pairs))
     V = lib().ora_model_vocab_size(h)
     syn0 = np.empty((V, params.dim), np.float32)
     syn1 = np.empty((V, params.dim), np.float32)

@@ -185,6 +185,8 @@ typedef struct {
     int tid, nthreads;
     int count_only;
     int64_t pairs;
+    int64_t s_lo, s_hi; /* sentences [s_lo, s_hi) of this call (s_hi == 0: all) */
+    int32_t only_epoch;  /* >= 0: this epoch only (data-parallel emulation runs an epoch slice by slice) */
 } worker;
 
 static void *worker_run(void *arg) {
@@ -197,8 +199,10 @@ static void *worker_run(void *arg) {
     float *syn0 = w->m ? w->m->syn0 : NULL, *syn1neg = w->m ? w->m->syn1neg : NULL, *syn1 = w->m ? w->m->syn1 : NULL;
     const float idx_scale = (float)E / MAX_EXP / 2.0f;
     int64_t pairs = 0;
+    const int64_t s_lo = w->s_hi > 0 ? w->s_lo : 0, s_hi = w->s_hi > 0 ? w->s_hi : w->n_sent;
     for (int32_t ep = 0; ep < p->epochs; ep++) {
-        for (int64_t s = w->tid; s < w->n_sent; s += w->nthreads) {
+        if (w->only_epoch >= 0 && ep != w->only_epoch) continue;
+        for (int64_t s = s_lo + w->tid; s < s_hi; s += w->nthreads) {
             int32_t n = 0;
             for (int32_t j = 0; j < w->L; j++) {
                 int32_t id = w->tokens[s * w->L + j];
@@ -286,6 +290,7 @@ static int64_t run_workers(const int32_t *tokens, int64_t n_sent, int32_t L, con
         ws[t].tokens = tokens; ws[t].n_sent = n_sent; ws[t].L = L; ws[t].p = p; ws[t].vocab = vocab;
         ws[t].table = table; ws[t].exp_table = exp_table; ws[t].hf = hf; ws[t].m = m;
         ws[t].tid = t; ws[t].nthreads = nt; ws[t].count_only = count_only;
+        ws[t].s_lo = 0; ws[t].s_hi = 0; ws[t].only_epoch = -1;
     }
     if (nt == 1) worker_run(&ws[0]);
     else {
@@ -324,6 +329,94 @@ ora_model *ora_sgns_train(const int32_t *tokens, int64_t n_sent, int32_t L, int3
     if (pairs_out) *pairs_out = pairs;
     if (p->use_hs) huff_free(&hf);
     free(table); free(exp_table);
+    ora_vocab_free(vocab);
+    return m;
+}
+
+/* Data-parallel emulation (checker of the multi-GPU scheme of libdge's stage 2; the reference itself is single
+ * process, its only hint being "model averaging", DeepWalk.java:43).  `world` ranks own contiguous shards of the
+ * sentences (embedding_b200/parallel.py walk_shard), share one vocabulary built from the whole corpus, and keep
+ * replicas of syn0 / syn1neg.  Every epoch is cut into `rounds` slices; in a slice each rank trains sequentially on
+ * its own sentences (local sentence indices for the RNG and the learning-rate schedule, as on the GPUs), then the
+ * replicas are recombined from the per-rank deltas d_r = cur_r - base:
+ *   combine 0: base += sum_r d_r                      (all updates applied)
+ *   combine 1: base += mean_r d_r                     (parameter averaging)
+ *   combine 2: base += sum_r d_r / max(1, #ranks whose delta of that ROW is non-zero)   (average over contributors)
+ */
+ora_model *ora_sgns_train_dp(const int32_t *tokens, int64_t n_sent, int32_t L, int32_t n_ids,
+                             const ora_sgns_params *p, int32_t world, int32_t rounds, int32_t combine,
+                             int64_t *pairs_out) {
+    ora_vocab *vocab = ora_vocab_build(tokens, n_sent * L, n_ids, p->min_count);
+    int32_t V = vocab->V, D = p->dim;
+    size_t n = (size_t)(V ? V : 1) * (size_t)D;
+    ora_model *m = (ora_model *)calloc(1, sizeof(*m));
+    m->V = V; m->dim = D;
+    m->syn0 = (float *)malloc(sizeof(float) * n);
+    m->syn1neg = (float *)calloc(n, sizeof(float));
+    m->syn1 = NULL;
+    m->id_of_word = (int32_t *)malloc(sizeof(int32_t) * (size_t)(V ? V : 1));
+    memcpy(m->id_of_word, vocab->id_of_word, sizeof(int32_t) * (size_t)V);
+    ora_init_syn0(V, D, p->seed, m->syn0);
+    int32_t *table = (int32_t *)malloc(sizeof(int32_t) * (size_t)p->neg_table_size);
+    ora_neg_table(vocab, p->neg_table_size, table);
+    float *exp_table = (float *)malloc(sizeof(float) * (size_t)p->exp_table_size);
+    for (int32_t i = 0; i < p->exp_table_size; i++) {
+        double e = exp(((double)i / (double)p->exp_table_size * 2.0 - 1.0) * (double)MAX_EXP);
+        exp_table[i] = (float)(e / (e + 1.0));
+    }
+    if (world < 1) world = 1;
+    if (rounds < 1) rounds = 1;
+    ora_model *rep = (ora_model *)calloc((size_t)world, sizeof(ora_model));
+    for (int r = 0; r < world; r++) {
+        rep[r].V = V; rep[r].dim = D;
+        rep[r].syn0 = (float *)malloc(sizeof(float) * n);
+        rep[r].syn1neg = (float *)malloc(sizeof(float) * n);
+    }
+    float *acc = (float *)malloc(sizeof(float) * n);
+    int32_t *touched = (int32_t *)malloc(sizeof(int32_t) * (size_t)(V ? V : 1));
+    int64_t pairs = 0;
+    ora_sgns_params q = *p;
+    q.use_hs = 0;
+    for (int32_t ep = 0; ep < p->epochs; ep++) {
+        for (int32_t rd = 0; rd < rounds; rd++) {
+            for (int r = 0; r < world; r++) {
+                memcpy(rep[r].syn0, m->syn0, sizeof(float) * n);
+                memcpy(rep[r].syn1neg, m->syn1neg, sizeof(float) * n);
+                int64_t base = n_sent / world, rem = n_sent % world;
+                int64_t first = r * base + (r < rem ? r : rem), count = base + (r < rem ? 1 : 0);
+                worker w; memset(&w, 0, sizeof(w));
+                w.tokens = tokens + first * L; w.n_sent = count; w.L = L; w.p = &q; w.vocab = vocab;
+                w.table = table; w.exp_table = exp_table; w.hf = NULL; w.m = &rep[r];
+                w.tid = 0; w.nthreads = 1; w.count_only = 0; w.only_epoch = ep;
+                w.s_lo = count * rd / rounds; w.s_hi = count * (rd + 1) / rounds;
+                if (w.s_hi > w.s_lo) { worker_run(&w); pairs += w.pairs; }
+            }
+            for (int t = 0; t < 2; t++) {
+                float *base_t = t == 0 ? m->syn0 : m->syn1neg;
+                memset(acc, 0, sizeof(float) * n);
+                memset(touched, 0, sizeof(int32_t) * (size_t)(V ? V : 1));
+                for (int r = 0; r < world; r++) {
+                    const float *cur = t == 0 ? rep[r].syn0 : rep[r].syn1neg;
+                    for (int32_t v = 0; v < V; v++) {
+                        int nz = 0;
+                        for (int32_t d = 0; d < D; d++) {
+                            float dl = cur[(size_t)v * D + d] - base_t[(size_t)v * D + d];
+                            acc[(size_t)v * D + d] += dl;
+                            nz |= dl != 0.0f;
+                        }
+                        touched[v] += nz;
+                    }
+                }
+                for (int32_t v = 0; v < V; v++) {
+                    float div = combine == 1 ? (float)world : (combine == 2 ? (float)(touched[v] > 1 ? touched[v] : 1) : (combine == 3 ? sqrtf((float)(touched[v] > 1 ? touched[v] : 1)) : 1.0f));
+                    for (int32_t d = 0; d < D; d++) base_t[(size_t)v * D + d] += acc[(size_t)v * D + d] / div;
+                }
+            }
+        }
+    }
+    if (pairs_out) *pairs_out = pairs;
+    for (int r = 0; r < world; r++) { free(rep[r].syn0); free(rep[r].syn1neg); }
+    free(rep); free(acc); free(touched); free(table); free(exp_table);
     ora_vocab_free(vocab);
     return m;
 }

@@ -60,6 +60,12 @@ void ora_model_free(ora_model *m);
 int32_t ora_model_vocab_size(const ora_model *m);
 void ora_model_get(const ora_model *m, float *syn0, float *syn1neg, int32_t *id_of_word);
 
+/* Data-parallel emulation: `world` ranks on contiguous sentence shards, `rounds` delta exchanges per epoch,
+ * combine 0 = sum of deltas, 1 = mean, 2 = per-row average over the ranks that touched the row (see the .c file). */
+ora_model *ora_sgns_train_dp(const int32_t *tokens, int64_t n_sent, int32_t L, int32_t n_ids,
+                             const ora_sgns_params *p, int32_t world, int32_t rounds, int32_t combine,
+                             int64_t *pairs_out);
+
 /* Count pairs only (same enumeration, no arithmetic). */
 int64_t ora_sgns_count_pairs(const int32_t *tokens, int64_t n_sent, int32_t L, int32_t n_ids,
                              const ora_sgns_params *p);

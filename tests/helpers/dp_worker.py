@@ -1,4 +1,4 @@
-"""One rank of the 2-GPU data-parallel skip-gram test (tests/test_comm_gpu.py): `python dp_worker.py rank world dir`.
+"""One rank of the 2-GPU data-parallel skip-gram test (tests/test_comm_gpu.py): `python dp_worker.py rank world dir [rounds]`.
 The NCCL id travels through a file, as a JNI host without torch would do it."""
 import os
 import sys
@@ -13,6 +13,7 @@ from embedding_b200 import abi, parallel, synth  # noqa: E402
 
 def main():
     rank, world, d = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+    rounds = int(sys.argv[4]) if len(sys.argv) > 4 else 6
     ctx = abi.Context(rank)
     idf = os.path.join(d, "nccl_id.bin")
     if rank == 0:
@@ -34,7 +35,7 @@ def main():
     n_walks = 40_000
     first, count = parallel.walk_shard(n_walks, rank, world)
     corpus = G.walk(count, 8, seed=11, first_walk_id=first)          # this rank's shard of the walk ids
-    m = abi.Model.train(ctx, [corpus], abi.sgns_params(dim=32, window=5, negative=5, min_count=2, seed=3, sync_rounds=6))
+    m = abi.Model.train(ctx, [corpus], abi.sgns_params(dim=32, window=5, negative=5, min_count=2, seed=3, sync_rounds=rounds))
     syn0, syn1, ids = m.vectors(want_syn1neg=True)
     np.savez(os.path.join(d, "rank%d.npz" % rank), syn0=syn0, syn1=syn1, ids=ids, pairs=m.pairs,
              rounds=ctx.phase_ms("sgns_rounds"), sync_ms=ctx.phase_ms("sgns_sync"), tok=corpus.tokens())

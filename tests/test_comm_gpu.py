@@ -75,18 +75,19 @@ def _device_count():
 
 @pytest.mark.skipif(_device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
 def test_two_rank_data_parallel_skipgram(dge_lib, tmp_path):
-    """Two processes, one GPU each: walk ids sharded, vocabulary from the all-reduced counts, embedding deltas summed
-    over NCCL.  Both ranks must end with bit-identical tables, the vocabulary must be the one of the whole corpus, and
+    """Two processes, one GPU each: walk ids sharded, vocabulary from the all-reduced counts, embedding deltas combined
+    over NCCL (per row: sum / contributing ranks).  Both ranks must end with bit-identical tables, the vocabulary must be the one of the whole corpus, and
     the embeddings must carry the same neighbourhood structure as a single-GPU run on the whole corpus."""
     from embedding_b200 import evaluation as ev
     worker = os.path.join(ROOT, "tests", "helpers", "dp_worker.py")
-    procs = [subprocess.Popen([sys.executable, worker, str(r), "2", str(tmp_path)]) for r in range(2)]
+    procs = [subprocess.Popen([sys.executable, worker, str(r), "2", str(tmp_path), "24"]) for r in range(2)]
     for p in procs:
         assert p.wait(timeout=600) == 0
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
     assert np.array_equal(r0["ids"], r1["ids"])
     assert np.array_equal(r0["syn0"], r1["syn0"]) and np.array_equal(r0["syn1"], r1["syn1"])
-    assert r0["rounds"] == 6 and np.isfinite(r0["syn0"]).all()
+    assert r0["rounds"] == 24 and np.isfinite(r0["syn0"]).all()
+    assert np.linalg.norm(r0["syn0"], axis=1).mean() < 5       # a diverging combine rule shows up as exploding rows
     whole = np.concatenate([r0["tok"], r1["tok"]])
     nv = 300 * 8
     cnt = np.bincount(whole[whole >= 0], minlength=nv)
@@ -104,5 +105,8 @@ def test_two_rank_data_parallel_skipgram(dge_lib, tmp_path):
     lb = ev.layers_from_model(r0["syn0"], r0["ids"], zeros, np.arange(nv, dtype=np.int32))
     lc = {0: (np.random.default_rng(0).standard_normal(s0.shape), la[0][1])}
     ov, ov_rand = ev.knn_overlap(la, lb, 10), ev.knn_overlap(la, lc, 10)
-    assert ov > 5 * ov_rand and ov > 0.3, (ov, ov_rand)
+    # Calibration (profiles/r1s20_dp_diagnose.json, tests/test_sgns_oracle.py::test_data_parallel_combine_rules): two
+    # single-GPU runs with different seeds agree to 0.50, the oracle's emulation of this exchange (24 rounds, average
+    # over contributors) to 0.41 with the sequential run; the plain sum of deltas fell to 0.10 here.
+    assert ov > 20 * ov_rand and ov > 0.25, (ov, ov_rand)
     ctx.close()

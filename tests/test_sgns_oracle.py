@@ -77,3 +77,32 @@ def test_alpha_schedule(oracle):
     assert abs(f(C.byref(p), 0, 0, 1000) - 0.025) < 1e-9
     assert abs(f(C.byref(p), 0, 500, 1000) - 0.0125) < 1e-9
     assert abs(f(C.byref(p), 0, 999, 1000) - 1e-4) < 1e-9  # floor
+
+
+def test_data_parallel_combine_rules(oracle):
+    """The multi-GPU exchange of stage 2, emulated (ora_sgns_train_dp): with one rank it IS the sequential run; with
+    8 ranks the plain sum of the per-rank deltas diverges on the hub rows, the per-row average over the contributing
+    ranks (what libdge ships, sgns.cu DGE_COMBINE_CONTRIBUTORS) stays bounded and keeps more of the structure."""
+    from embedding_b200 import evaluation as ev, synth
+    g = synth.powerlaw_flow_graph(300, L=8, seed=5, mean_degree=8, cap=64)
+    G = oracle.Graph(g["n_vertices"], g["src"], g["dst"], g["w"], g["sources"])
+    tok = G.walk(40_000, 8, seed=11)
+    nv = g["n_vertices"]
+    zeros, ar = np.zeros(nv, np.int32), np.arange(nv, dtype=np.int32)
+    kw = dict(dim=32, window=5, negative=5, min_count=2, seed=3, threads=1)
+
+    def layers(m):
+        return ev.layers_from_model(m["syn0"], m["id_of_word"], zeros, ar)
+
+    ref = oracle.sgns_train(tok, nv, oracle.sgns_params(**kw))
+    one = oracle.sgns_train_dp(tok, nv, oracle.sgns_params(**kw), 1, 6, oracle.COMBINE_SUM)
+    assert one["pairs"] == ref["pairs"] and np.allclose(one["syn0"], ref["syn0"], atol=2e-3)  # rounding of (cur - base) + base, amplified by 1.8e6 dependent updates
+    summed = oracle.sgns_train_dp(tok, nv, oracle.sgns_params(**kw), 8, 24, oracle.COMBINE_SUM)
+    contrib = oracle.sgns_train_dp(tok, nv, oracle.sgns_params(**kw), 8, 24, oracle.COMBINE_CONTRIBUTORS)
+    norm = lambda m: float(np.linalg.norm(m["syn0"], axis=1).mean())
+    assert norm(ref) < 3 and norm(contrib) < 3
+    assert norm(summed) > 100                                    # overshoot by a factor of world on every hub row
+    a, b = ev.knn_overlap(layers(ref), layers(contrib), 10), ev.knn_overlap(layers(ref), layers(summed), 10)
+    assert a > 2 * b, (a, b)
+    two = oracle.sgns_train_dp(tok, nv, oracle.sgns_params(**kw), 2, 24, oracle.COMBINE_CONTRIBUTORS)
+    assert ev.knn_overlap(layers(ref), layers(two), 10) > 0.3
