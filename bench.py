@@ -409,7 +409,7 @@ def run_gpu_arm(args, w, rank, world, dist):
                 warmup=args.warmup, ms_per_step=(t_walk + t_sgns) / args.steps * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f64 (alias tables, walk draws) / f32 (SGNS)", data="synthetic",
                 config=dict(workload=w["desc"], l2="inputs of a step (>= 1.5 GB of tokens) exceed the 126 MB L2; every step uses a new seed",
-                            parallelism=("1 GPU" if world == 1 else "walk ids sharded by rank, no collective; SGNS data-parallel, NCCL all-reduce of summed embedding deltas"
+                            parallelism=("1 GPU" if world == 1 else "walk ids sharded by rank, no collective; SGNS data-parallel, NCCL all-reduce of the embedding deltas (per row: sum / contributing ranks)"
                                          if data_parallel else "walk ids sharded by rank, no collective; SGNS replicas only"),
                             timing="CUDA events on the library stream per stage (dge_timer_start/stop), max over ranks"),
                 e2e=stages["walk"]["e2e"],

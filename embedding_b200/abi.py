@@ -76,6 +76,7 @@ def lib():
     L.dge_sgns_train.argtypes = [vp, P(vp), i32, P(SgnsParams), P(vp)]
     L.dge_model_shape.argtypes = [vp, pi32, pi32, pi64]
     L.dge_model_vectors.argtypes = [vp, pf32, pf32, pi32]
+    L.dge_model_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), pi64]
     L.dge_model_write_vec.argtypes = [vp, pi32, pi32, C.c_char_p]
     L.dge_model_free.argtypes = [vp]
     L.dge_model_free.restype = None
@@ -481,6 +482,12 @@ class Model:
         _check(lib().dge_model_vectors(self._h, _ptr(syn0, C.c_float), _ptr(syn1, C.c_float), _ptr(ids, C.c_int32)),
                self.ctx._h)
         return (syn0, syn1, ids) if want_syn1neg else (syn0, ids)
+
+    def stats(self):
+        """(mean |syn0 row|, max |element| of both tables, non-finite elements) computed on the device."""
+        norm, mx, bad = C.c_double(), C.c_double(), C.c_int64()
+        _check(lib().dge_model_stats(self._h, C.byref(norm), C.byref(mx), C.byref(bad)), self.ctx._h)
+        return dict(mean_row_norm=norm.value, max_abs=mx.value, nonfinite=bad.value)
 
     def write_vec(self, path, label_layer, label_region):
         ll = np.ascontiguousarray(label_layer, np.int32)

@@ -3,7 +3,8 @@
 // The reference has no multi-device path at all (its only hint is the commented-out "cross-device access is used
 // for faster model averaging over pcie", DeepWalk.java:43).  Here the walk stage shards by walk id without any
 // collective; the skip-gram stage on the large synthetic configs is data-parallel over corpus shards and exchanges
-// the SUM OF THE PER-GPU EMBEDDING DELTAS over NVLink every few thousand sentences (sgns.cu calls dge_comm_* below).
+// the per-GPU embedding deltas over NVLink every few thousand sentences, combined per row by the number of ranks that
+// touched the row (sgns.cu calls dge_comm_* below; DESIGN.md 3.4 for why not the plain sum).
 //
 // NCCL is bound lazily with dlopen: libdge.so has no link-time dependency on it, a single-GPU host never loads
 // it, and inside a process that already carries a libnccl.so.2 (e.g. torch.distributed in bench.py) the same

@@ -1091,6 +1091,34 @@ __global__ void k_delta_end(float *__restrict__ c0, float *__restrict__ b0, floa
     }
 }
 
+// dge_model_stats: one warp per row of each table; acc[0] += |syn0 row|, acc[1] = max |element| (non-negative doubles
+// order like their bit patterns), bad += non-finite elements
+__global__ void k_model_stats(const float *__restrict__ syn0, const float *__restrict__ syn1neg, int32_t V, int32_t dim,
+                              int32_t stride, double *acc, unsigned long long *bad) {
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = warp; r < 2 * (int64_t)V; r += n_warps) {
+        const float *row = (r < V ? syn0 + r * stride : syn1neg + (r - V) * stride);
+        float ss = 0.f, mx = 0.f;
+        unsigned nb = 0;
+        for (int d = lane; d < dim; d += 32) {
+            const float x = __ldcg(row + d);
+            if (isfinite(x)) { ss += x * x; mx = fmaxf(mx, fabsf(x)); }
+            else nb++;
+        }
+        for (int o = 16; o; o >>= 1) {
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            nb += __shfl_xor_sync(0xffffffffu, nb, o);
+        }
+        if (lane == 0) {
+            if (r < V) atomicAdd(&acc[0], (double)sqrtf(ss));
+            atomicMax(reinterpret_cast<unsigned long long *>(&acc[1]), (unsigned long long)__double_as_longlong((double)mx));
+            if (nb) atomicAdd(bad, (unsigned long long)nb);
+        }
+    }
+}
+
 typedef void (*sgns_kernel_t)(const sgns_args);
 struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq, items; int items_code; };
 // items_code (reported as phase "sgns_kernel"): 1 k_sgns_items, 2 k_sgns_items_v2, 3 k_sgns_items_g4, 4 k_sgns_items_tp; 0 k_sgns_seq
@@ -1458,6 +1486,32 @@ int dge_model_vectors(const dge_model *m, float *syn0, float *syn1neg, int32_t *
     if (id_of_word) DGE_CUDA(ctx, cudaMemcpyAsync(id_of_word, m->id_of_word, sizeof(int32_t) * (size_t)m->V, cudaMemcpyDeviceToHost, ctx->stream));
     t.stop();
     DGE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DGE_OK;
+}
+
+int dge_model_stats(const dge_model *m, double *mean_row_norm, double *max_abs, int64_t *n_nonfinite) {
+    if (!m) return dge_fail(nullptr, DGE_E_INVALID, "dge_model_stats: model is NULL");
+    dge_ctx *ctx = m->ctx;
+    DGE_CUDA(ctx, cudaSetDevice(ctx->device));
+    double h[3] = {0.0, 0.0, 0.0}; // sum of row norms, max |element|, non-finite count (as raw bits of an u64)
+    if (m->V > 0) {
+        double *d = nullptr;
+        DGE_CUDA(ctx, dge_malloc(ctx, &d, 3));
+        cudaMemsetAsync(d, 0, 3 * sizeof(double), ctx->stream);
+        k_model_stats<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(m->syn0, m->syn1neg, m->V, m->dim, m->stride, d,
+                                                                 reinterpret_cast<unsigned long long *>(d + 2));
+        ctx->launches++;
+        cudaError_t e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        dge_free(ctx, d);
+        if (e != cudaSuccess) return dge_fail(ctx, DGE_E_CUDA, std::string("dge_model_stats: ") + cudaGetErrorString(e));
+    }
+    unsigned long long nb;
+    memcpy(&nb, &h[2], sizeof(nb));
+    if (mean_row_norm) *mean_row_norm = m->V > 0 ? h[0] / (double)m->V : 0.0;
+    if (max_abs) *max_abs = h[1];
+    if (n_nonfinite) *n_nonfinite = (int64_t)nb;
     return DGE_OK;
 }
 

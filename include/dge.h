@@ -70,8 +70,8 @@ int dge_timer_stop(dge_ctx *ctx, float *ms);
 /* ------------------------------------------------------------------ multi-GPU (one process per GPU)
  * The reference is single-device (only a commented-out hint, DeepWalk.java:43).  Walks shard by walk id with no
  * collective (first_walk_id of dge_walk).  Stage 2 becomes data-parallel when the ctx carries a communicator:
- * every rank trains on its own corpora and dge_sgns_train exchanges the sum of the embedding deltas with NCCL
- * all-reduces over NVLink (sync_rounds per epoch).  The host moves the opaque id from rank 0 to the other ranks
+ * every rank trains on its own corpora and dge_sgns_train exchanges the embedding deltas with NCCL all-reduces over
+ * NVLink (sync_rounds per epoch); per row the summed delta is divided by the number of ranks that touched the row.  The host moves the opaque id from rank 0 to the other ranks
  * by any means it has (a file, a socket, MPI, torch.distributed). */
 #define DGE_COMM_ID_BYTES 128
 int dge_comm_unique_id(void *id, size_t bytes);
@@ -223,6 +223,10 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
 int dge_model_shape(const dge_model *m, int32_t *vocab_size, int32_t *dim, int64_t *pairs_trained);
 /* syn0 / syn1neg [V*dim] row-major by vocabulary index; id_of_word[V] maps back to corpus ids. NULLs ok. */
 int dge_model_vectors(const dge_model *m, float *syn0, float *syn1neg, int32_t *id_of_word);
+/* Health of the trained tables without downloading them (no reference counterpart; DL4J has none): mean Euclidean
+ * norm of the syn0 rows, largest |element| of syn0 and syn1neg, number of non-finite elements.  A diverging
+ * multi-GPU exchange shows up here as exploding norms.  NULLs ok. */
+int dge_model_stats(const dge_model *m, double *mean_row_norm, double *max_abs, int64_t *n_nonfinite);
 /* `.vec` text (writeWordVectors, consumers python/embeddingEvaluation_tract.py:139-166): no header, one line
  * per vocabulary word "<layer>-<region> v1 ... vD".  label arrays are indexed by corpus id. */
 int dge_model_write_vec(const dge_model *m, const int32_t *label_layer, const int32_t *label_region,

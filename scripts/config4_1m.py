@@ -71,9 +71,11 @@ def main():
         ms = ctx.phase_ms("sgns")
         sg.append(dict(ms=ms, pairs=m.pairs, V=m.V, pairs_per_s=m.pairs / ms * 1e3, algorithmic_gbs=m.pairs * 8.0 * a.dim * 7 / ms / 1e6,
                        sync_rounds=ctx.phase_ms("sgns_rounds"), sync_ms=ctx.phase_ms("sgns_sync")))
+        sg[-1].update(m.stats())      # a diverging delta exchange shows up as exploding row norms
         if rank == 0:
-            print("sgns rep %d: V=%d, %.1f ms, %d pairs, %.1f M pairs/s per GPU, sync %.1f ms in %s rounds" %
-                  (rep, m.V, ms, m.pairs, m.pairs / ms / 1e3, sg[-1]["sync_ms"], sg[-1]["sync_rounds"]), flush=True)
+            print("sgns rep %d: V=%d, %.1f ms, %d pairs, %.1f M pairs/s per GPU, sync %.1f ms in %s rounds, mean |syn0 row| %.3f, max |x| %.2f, non-finite %d" %
+                  (rep, m.V, ms, m.pairs, m.pairs / ms / 1e3, sg[-1]["sync_ms"], sg[-1]["sync_rounds"], sg[-1]["mean_row_norm"],
+                   sg[-1]["max_abs"], sg[-1]["nonfinite"]), flush=True)
         m.free()
     res["sgns"] = sg
     if rank == 0:

@@ -1,5 +1,5 @@
 """GPU tests of the multi-GPU row: the NCCL communicator of a ctx and the data-parallel skip-gram
-(sum-of-deltas all-reduce).  The 1-GPU cases run the same code path with a world of one; the 2-rank case needs two
+(delta all-reduce, per row divided by the contributing ranks).  The 1-GPU cases run the same code path with a world of one; the 2-rank case needs two
 GPUs on the box (gpurun --gpus 2) and is skipped otherwise."""
 import os
 import subprocess

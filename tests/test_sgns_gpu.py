@@ -154,6 +154,19 @@ def test_vec_file_format(dge_lib, ctx, tmp_path):
         assert np.array_equal(np.array(parts[1:], np.float32), syn0[wd])
 
 
+def test_model_stats_match_numpy(dge_lib, ctx):
+    tok = community_corpus(400)
+    c = dge_lib.Corpus.from_tokens(ctx, tok, 20)
+    for dim in (8, 20, 100):
+        m = dge_lib.Model.train(ctx, [c], dge_lib.sgns_params(dim=dim, window=5, min_count=1))
+        syn0, syn1, _ = m.vectors(want_syn1neg=True)
+        st = m.stats()
+        assert st["nonfinite"] == 0
+        assert np.isclose(st["mean_row_norm"], np.linalg.norm(syn0.astype(np.float64), axis=1).mean(), rtol=1e-5)
+        assert np.isclose(st["max_abs"], max(np.abs(syn0).max(), np.abs(syn1).max()), rtol=1e-6)
+        m.free()
+
+
 def test_sgns_error_behaviour(dge_lib, ctx):
     c = dge_lib.Corpus.from_tokens(ctx, np.zeros((2, 2), np.int32), 1)
     with pytest.raises(dge_lib.DgeError):
