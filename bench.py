@@ -383,7 +383,11 @@ def run_gpu_arm(args, w, rank, world, dist):
     resident_note = ("graph and embedding tables are L2-resident at this size; HBM is not the binding limit (SURVEY 8(d)); the "
                      "binding limit of the item kernel is the L2's 128-bit reduction throughput: 34.5 G rows/s load+reduce "
                      "for this access shape (scripts/red_microbench.cu, profiles/r1s7_red_microbench.txt) = 5.76 G pairs/s"
-                     if w["name"] != "synth100k" else
+                     if w["name"] not in ("synth100k", "ca") else
+                     "graph and embedding tables are L2-resident (V = 1 848 rows of 32 bytes): neither HBM nor the L2 reduction rate binds; "
+                     "the staleness bound (8 * V / (K + 1) = 2 464 pairs in flight, DESIGN.md 3.3) leaves ~8 warps per SM and the epoch "
+                     "is latency-bound: pairs / pairs in flight x ~1 700 cycles per pair step (profiles/r1s16_sgns_ca_tp.json)"
+                     if w["name"] == "ca" else
                      "tables are 1.2 GB each, but the walk corpus is skewed: most row traffic hits L2 (ncu: 82 % hit rate), so "
                      "algorithmic bytes/s can exceed the HBM peak; see traffic for the measured DRAM bytes")
     stages = dict(

@@ -39,6 +39,10 @@ public final class DgeNative {
     public static native long sgnsTrain(long ctx, long[] corpora, int dim, int window, int negative, int minCount,
                                         int epochs, float lr, float minLr, long seed);
     public static native void modelWriteVec(long model, int[] labelLayer, int[] labelRegion, String path);
+    /** in-memory access to the trained tables (syn1negOrNull / idOfWordOrNull may be null) -> dge_model_vectors. */
+    public static native void modelVectors(long model, float[] syn0, float[] syn1negOrNull, int[] idOfWordOrNull);
+    /** {mean |syn0 row|, max |element|, non-finite elements} computed on the device -> dge_model_stats. */
+    public static native double[] modelStats(long model);
     public static native void modelFree(long model);
 
     /** CommunityAreas.mapTripsIntoCommunities / Tracts.mapTripsIntoTracts (counting) -> dge_flows_create / _add_trips. */

@@ -68,6 +68,28 @@ JNIEXPORT jlong JNICALL Java_embedding_DgeNative_sgnsTrain(JNIEnv *env, jclass c
     return (jlong)(intptr_t)m;
 }
 
+JNIEXPORT void JNICALL Java_embedding_DgeNative_modelVectors(JNIEnv *env, jclass c, jlong jm, jfloatArray j0, jfloatArray j1,
+        jintArray jids) {
+    jfloat *s0 = (*env)->GetPrimitiveArrayCritical(env, j0, NULL);
+    jfloat *s1 = j1 ? (*env)->GetPrimitiveArrayCritical(env, j1, NULL) : NULL;
+    jint *ids = jids ? (*env)->GetPrimitiveArrayCritical(env, jids, NULL) : NULL;
+    int rc = dge_model_vectors((const dge_model *)(intptr_t)jm, s0, s1, (int32_t *)ids);
+    if (ids) (*env)->ReleasePrimitiveArrayCritical(env, jids, ids, 0);
+    if (s1) (*env)->ReleasePrimitiveArrayCritical(env, j1, s1, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, j0, s0, 0);
+    if (rc != DGE_OK) throw_dge(env, NULL);
+}
+
+JNIEXPORT jdoubleArray JNICALL Java_embedding_DgeNative_modelStats(JNIEnv *env, jclass c, jlong jm) {
+    double v[3] = {0, 0, 0};
+    int64_t bad = 0;
+    if (dge_model_stats((const dge_model *)(intptr_t)jm, &v[0], &v[1], &bad) != DGE_OK) { throw_dge(env, NULL); return NULL; }
+    v[2] = (double)bad;
+    jdoubleArray out = (*env)->NewDoubleArray(env, 3);
+    if (out) (*env)->SetDoubleArrayRegion(env, out, 0, 3, v);
+    return out;
+}
+
 JNIEXPORT jlong JNICALL Java_embedding_DgeNative_flowsCreate(JNIEnv *env, jclass c, jlong jctx, jint n, jintArray jF) {
     dge_ctx *ctx = (dge_ctx *)(intptr_t)jctx;
     jint *F = jF ? (*env)->GetPrimitiveArrayCritical(env, jF, NULL) : NULL;
