@@ -649,6 +649,227 @@ k_sgns_items_v2(const sgns_args a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Kernel C': kernel C with the rows of a unit staged in SHARED MEMORY by cp.async instead of registers.
+// EXPERIMENTAL (DGE_SGNS_DEBUG bit 256; never chosen by default; not yet measured on the GPU).  Motivation, from
+// the ncu source page of kernel C on tract x 24 (profiles/r1_stalls_sgns15_tract24.txt): 40.6 % of all stall samples
+// sit on ONE instruction, the first FMUL that consumes the rows requested earlier in the same unit -- the warps wait
+// for L2.  A second row buffer in REGISTERS cost a resident block (128 registers, 4 blocks/SM) and lost 6 %
+// (profiles/r1s6_sgns_builds.txt).  cp.async.cg (LDGSTS, L2 only) keeps the rows of unit u+1 in flight through the
+// whole compute of unit u without holding a register: per group 2 stages x 6 rows x G slots x 16 B.  Every lane
+// reads back exactly the slots it copied itself, so cp.async.wait_group is the only synchronisation needed.
+__device__ __forceinline__ void cp_async16_if(uint32_t smem_addr, uint64_t gptr, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+                 ::"r"(smem_addr), "l"(gptr), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds4(uint32_t smem_addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(smem_addr));
+    return r;
+}
+
+__device__ __forceinline__ float sgns_g_lane(float tot, float label, float alpha, float g_hi, float g_lo, const float *s_exp,
+                                             int E, float idx_scale);
+template <int G, bool MULTI>
+__global__ void __launch_bounds__(128, 5)
+k_sgns_items_v3(const sgns_args a) {
+    static_assert(G == 8 || G == 16 || G == 32, "lane groups of 8, 16 or 32");
+    extern __shared__ __align__(16) int32_t smem_v3[];
+    int32_t *const smem = smem_v3;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int GPW = 32 / G;
+    constexpr bool MERGE_SYN0 = GPW > 1;
+    constexpr int ROWS = SGNS_CH + 1;                 // slot 0: syn0[last]; 1..5: the negatives' syn1neg rows
+    constexpr int STAGE_BYTES = ROWS * G * 16;        // one unit of one group
+    // dynamic shared memory: [row stages of every group][sigmoid table][staged sentence of every group]
+    const int groups_per_block = blockDim.x / G;
+    float *s_exp = reinterpret_cast<float *>(reinterpret_cast<char *>(smem) + (size_t)groups_per_block * 2 * STAGE_BYTES);
+    const int gpw_eff = (a.dbg & 8) ? 1 : GPW;
+    const int lane = threadIdx.x % G;
+    const int gw = (threadIdx.x & 31) / G;
+    int32_t *mytok = reinterpret_cast<int32_t *>(s_exp + a.exp_table_size) + (threadIdx.x / G) * a.Lmax;
+    const uint32_t my_rows = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)(threadIdx.x / G) * 2u * STAGE_BYTES + (uint32_t)lane * 16u;
+    for (int i = threadIdx.x; i < a.exp_table_size; i += blockDim.x) s_exp[i] = a.exp_table[i];
+    for (int i = threadIdx.x; i < groups_per_block * 2 * STAGE_BYTES / 4; i += blockDim.x) smem[i] = 0; // finite stale values
+    __syncthreads();
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int E = a.exp_table_size;
+    const float idx_scale = (float)E / SGNS_MAX_EXP / 2.0f;
+    const int win = a.window;
+    const int64_t N = a.n_sent;
+    const int Lmax = a.Lmax;
+    const int64_t item_lo = a.s_lo * Lmax, n_items = a.s_hi * Lmax;
+    const double inv_total = 1.0 / (double)((int64_t)a.epochs * N);
+    const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
+    const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int K = a.V >= 2 ? a.negative : 0;
+    const int NCH = MULTI ? max(1, (K + SGNS_CH - 1) / SGNS_CH) : 1;
+    const bool live = lane < a.n4;
+    const uint32_t pitch = (uint32_t)a.stride * 4u;
+    const char *base0 = reinterpret_cast<const char *>(a.syn0) + (live ? lane : 0) * 16;
+    const char *base1 = reinterpret_cast<const char *>(a.syn1neg) + (live ? lane : 0) * 16;
+    const int L8 = lane & 7;
+    const bool up4 = (lane & 4) != 0, up2 = (lane & 2) != 0, up1 = (lane & 1) != 0;
+    const float my_label = L8 == SGNS_CH ? 1.f : 0.f;
+    const bool reds_on = !(a.dbg & 1);
+    unsigned long long pairs = 0;
+
+    struct stage_t { int32_t last; bool act; uint64_t nsk; int32_t traw; int j; };
+    struct stage_r { int32_t last; bool act; int j; int32_t mine; }; // the targets are re-broadcast from `mine` where needed
+
+    for (int ep = a.ep_lo; ep < a.ep_hi; ep++) {
+        for (int64_t base = item_lo + warp_id * gpw_eff; base < n_items; base += a.n_groups) {
+            const int64_t item = base + gw;
+            bool valid = item < n_items && gw < gpw_eff;
+            const int64_t s = valid ? item / Lmax : 0;
+            const int i = valid ? (int)(item - s * Lmax) : 0;
+            const long long s_first = __shfl_sync(FULL, (long long)s, 0);
+            const bool same_s = MERGE_SYN0 && __all_sync(FULL, valid && (long long)s == s_first);
+            __syncwarp();
+            int n_tok = 0;
+            for (int j = lane; j < Lmax; j += G) { const int32_t tk = a.wtok[(int64_t)j * N + s]; mytok[j] = tk; n_tok += tk >= 0; }
+            __syncwarp();
+#pragma unroll
+            for (int o = G >> 1; o > 0; o >>= 1) n_tok += __shfl_xor_sync(FULL, n_tok, o);
+            const int32_t w1 = mytok[i];
+            valid = valid && w1 >= 0;
+            if (!__any_sync(FULL, valid)) continue;
+            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * N + s) * inv_total);
+            if (alpha < a.min_lr) alpha = a.min_lr;
+            const float g_hi = (my_label - 1.f) * alpha, g_lo = my_label * alpha;
+            const uint64_t S = sgns_sentence_rng(a.seed, ep, s);
+            const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
+            const int lo = valid ? i - win + b : 1, hi = valid ? i + win - b : 0;
+            const int c_min = __reduce_min_sync(FULL, valid ? max(lo, 0) : Lmax);
+            const int c_max = __reduce_max_sync(FULL, valid ? min(hi, n_tok - 1) : -1);
+            if (c_max < c_min) continue;
+            float4 cur = zero4, d1 = zero4, neu = zero4, v0p = zero4;
+            ldcg4_into(cur, row_addr(base1, (uint32_t)w1, pitch), valid && live);
+            int npairs = 0;
+            int cT = c_min, jT = 0;
+            uint64_t hc = 0;
+            int hcb = -1;
+
+            auto stageT = [&]() {
+                stage_t t;
+                t.j = jT;
+                t.last = cT < Lmax ? mytok[cT] : -1;
+                t.act = cT >= lo && cT <= hi && cT != i && t.last >= 0 && t.last != w1;
+                if (cT / G != hcb) { hcb = cT / G; hc = sgns_pair_rng(S, i, hcb * G + lane); }
+                const uint64_t ns0 = shfl64(hc, cT & (G - 1), G);
+                const int kk = jT * SGNS_CH + lane;
+                const bool drawer = lane < SGNS_CH && kk < K;
+                const int kc = drawer ? kk : 0;
+                t.nsk = a.lcg_a[kc] * ns0 + a.lcg_c[kc];
+                t.traw = -2;
+                if (drawer && t.act) t.traw = a.neg_table[mod48(t.nsk >> 16, tsize, inv_tsize)];
+                if (MULTI) { if (++jT == NCH) { jT = 0; cT++; } }
+                else cT++;
+                return t;
+            };
+            // resolve the negatives, start the asynchronous copies of all rows of the unit into stage `st`
+            auto stageR = [&](const stage_t &t, stage_r &r, int st) {
+                r.last = t.last; r.act = t.act; r.j = t.j;
+                int32_t tt = t.traw;
+                const bool redraw = tt != -2 && (tt <= 0 || tt >= a.V);
+                if (__any_sync(FULL, redraw)) {
+                    if (redraw) tt = (int32_t)mod64(t.nsk, vm1, inv_vm1) + 1;
+                }
+                r.mine = (tt != -2 && tt != w1) ? tt : -1;
+                const uint32_t dst = my_rows + (uint32_t)st * STAGE_BYTES;
+                if (!MULTI || t.j == 0) cp_async16_if(dst, row_addr(base0, (uint32_t)t.last, pitch), t.act && live);
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) {
+                    const int32_t tg = __shfl_sync(FULL, r.mine, k, G);
+                    cp_async16_if(dst + (uint32_t)(k + 1) * G * 16, row_addr(base1, (uint32_t)tg, pitch), tg >= 0 && live);
+                }
+                cp_async_commit();
+            };
+            auto compute = [&](const stage_r &r, int st) {
+                if (!__any_sync(FULL, r.act)) return;
+                const uint32_t src = my_rows + (uint32_t)st * STAGE_BYTES;
+                const bool first = !MULTI || r.j == 0;
+                if (first) { npairs += r.act; neu = zero4; }
+                if (first) v0p = lds4(src); // MULTI: later chunks of the pair keep the copy (their stage slot 0 is not refilled)
+                const float4 v0 = v0p;
+                // rows are read from shared memory where they are used (twice: dot product, then neu1e) instead of being
+                // held in registers across the reduction
+                float dk[SGNS_CH];
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) dk[k] = dot4(v0, lds4(src + (uint32_t)(k + 1) * G * 16));
+                const float d0 = dk[0], d1v = dk[1], d2 = dk[2], d3 = dk[3], d4 = dk[4], d5 = first ? dot4(v0, cur) : 0.f;
+                float e0 = (up4 ? d4 : d0) + __shfl_xor_sync(FULL, up4 ? d0 : d4, 4);
+                float e1 = (up4 ? d5 : d1v) + __shfl_xor_sync(FULL, up4 ? d1v : d5, 4);
+                float e2 = (up4 ? 0.f : d2) + __shfl_xor_sync(FULL, up4 ? d2 : 0.f, 4);
+                float e3 = (up4 ? 0.f : d3) + __shfl_xor_sync(FULL, up4 ? d3 : 0.f, 4);
+                float f0 = (up2 ? e2 : e0) + __shfl_xor_sync(FULL, up2 ? e0 : e2, 2);
+                float f1 = (up2 ? e3 : e1) + __shfl_xor_sync(FULL, up2 ? e1 : e3, 2);
+                float tot = (up1 ? f1 : f0) + __shfl_xor_sync(FULL, up1 ? f0 : f1, 1);
+                if (G >= 16) tot += __shfl_xor_sync(FULL, tot, 8);
+                if (G >= 32) tot += __shfl_xor_sync(FULL, tot, 16);
+                float g = sgns_g_lane(tot, my_label, alpha, g_hi, g_lo, s_exp, E, idx_scale);
+                {
+                    const bool mine_ok = L8 < SGNS_CH ? r.mine >= 0 : (L8 == SGNS_CH && r.act && first);
+                    if (!mine_ok) g = 0.f;
+                }
+                float gk[SGNS_CH + 1];
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) gk[k] = __shfl_sync(FULL, g, k, G);
+                gk[SGNS_CH] = first ? __shfl_sync(FULL, g, SGNS_CH, G) : 0.f;
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) {
+                    axpy4(neu, gk[k], lds4(src + (uint32_t)(k + 1) * G * 16));
+                    const int32_t tg = __shfl_sync(FULL, r.mine, k, G); // gk[k] != 0 implies tg >= 0
+                    red_add4_if(row_addr(base1, (uint32_t)tg, pitch), scale4(gk[k], v0), gk[k] != 0.f && live && reds_on);
+                }
+                if (first) {
+                    axpy4(neu, gk[SGNS_CH], cur);
+                    axpy4(d1, gk[SGNS_CH], v0);
+                    axpy4(cur, gk[SGNS_CH], v0);
+                }
+                if (!MULTI || r.j == NCH - 1) {
+                    if (same_s) {
+                        float4 ns = neu;
+#pragma unroll
+                        for (int o = G; o < 32; o <<= 1) {
+                            ns.x += __shfl_xor_sync(FULL, ns.x, o); ns.y += __shfl_xor_sync(FULL, ns.y, o);
+                            ns.z += __shfl_xor_sync(FULL, ns.z, o); ns.w += __shfl_xor_sync(FULL, ns.w, o);
+                        }
+                        red_add4_if(row_addr(base0, (uint32_t)r.last, pitch), ns, gw == 0 && live && reds_on);
+                    } else {
+                        red_add4_if(row_addr(base0, (uint32_t)r.last, pitch), neu, r.act && live && reds_on);
+                    }
+                }
+            };
+
+            const int U = (c_max - c_min + 1) * NCH;
+            stage_r rA, rB;
+            stage_t t1 = stageT();
+            stageR(t1, rA, 0); // copies of unit 0 -> stage 0
+            t1 = stageT();     // table entries of unit 1
+            for (int u = 0; u < U; u += 2) {
+                stageR(t1, rB, 1); // copies of unit u + 1 -> stage 1 (nothing is copied past the end: act is false there)
+                t1 = stageT();
+                cp_async_wait<1>(); // everything but the newest group has landed: stage 0 is readable
+                compute(rA, 0);
+                if (u + 1 < U) {
+                    stageR(t1, rA, 0);
+                    t1 = stageT();
+                    cp_async_wait<1>();
+                    compute(rB, 1);
+                }
+            }
+            cp_async_wait<0>(); // no copy of this item may land in a stage the next item is already filling
+            red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, valid && live && reds_on);
+            pairs += (unsigned)npairs;
+        }
+    }
+    if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Kernel D: the item kernel for NARROW rows (up to 8 float4 slots: D <= 32, i.e. the reference's own D = 8 and
 // D = 20).  Same draws and arithmetic as kernel C; a group is 4 lanes holding VPL = 1 or 2 slots each (slot
 // lane + 4v), so 8 items run in lockstep per warp instead of 4 and the per-unit overhead (pair hash, negative
@@ -1121,12 +1342,13 @@ __global__ void k_model_stats(const float *__restrict__ syn0, const float *__res
 
 typedef void (*sgns_kernel_t)(const sgns_args);
 struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq, items; int items_code; };
-// items_code (reported as phase "sgns_kernel"): 1 k_sgns_items, 2 k_sgns_items_v2, 3 k_sgns_items_g4, 4 k_sgns_items_tp; 0 k_sgns_seq
+// items_code (reported as phase "sgns_kernel"): 1 k_sgns_items, 2 k_sgns_items_v2, 3 k_sgns_items_g4, 4 k_sgns_items_tp,
+// 5 k_sgns_items_v3 (experimental); 0 k_sgns_seq
 
 // Kernel A (exact order): rows of up to 8 float4 slots are held by ONE thread; wider rows give each lane of a
 // 16- or 32-lane group one 128-bit slot (2 or 4 for rows wider than 32 slots).
 // Kernel B (items): groups of 8 / 16 / 32 lanes, one slot per lane (2 or 4 beyond 32 slots).
-static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_parallel, sgns_variant *out) {
+static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_parallel, bool staged_rows, sgns_variant *out) {
     if (n4 > 128) return false;
     sgns_kernel_t seq = nullptr, items = nullptr;
     int Gs = 1, Vs = 1;
@@ -1158,6 +1380,12 @@ static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_p
         else { Gi = 32; items = k_sgns_items_tp<4>; }
     }
     else if (n4 <= 4 && narrow_groups) { Gi = 4; code = 3; items = multi ? k_sgns_items_g4<1, true> : k_sgns_items_g4<1, false>; }
+    else if (n4 <= 32 && staged_rows) { // experimental: rows of a unit staged in shared memory by cp.async (kernel C')
+        code = 5;
+        if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v3<8, true> : k_sgns_items_v3<8, false>; }
+        else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v3<16, true> : k_sgns_items_v3<16, false>; }
+        else { Gi = 32; items = multi ? k_sgns_items_v3<32, true> : k_sgns_items_v3<32, false>; }
+    }
     else if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true> : k_sgns_items_v2<8, false>; }
     else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v2<16, true> : k_sgns_items_v2<16, false>; }
     else if (n4 <= 32) { Gi = 32; items = multi ? k_sgns_items_v2<32, true> : k_sgns_items_v2<32, false>; }
@@ -1208,7 +1436,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
     }
     const int32_t n4 = (p->dim + 3) / 4;        // float4 slots that carry data (zero-padded to whole slots)
     const int32_t stride = ((p->dim + 7) / 8) * 8; // row pitch in floats: rows start on 32-byte sector boundaries
-    const int dbg = getenv("DGE_SGNS_DEBUG") ? atoi(getenv("DGE_SGNS_DEBUG")) : 0; // 1: no reductions (timing experiments), 2 / 32: never / always use 4-lane groups for D <= 16 (A/B, tests), 8: item kernel on ONE warp, one item at a time (tests), 64 / 128: always / never use the target-parallel kernel for D <= 16, K <= 7 (A/B, tests)
+    const int dbg = getenv("DGE_SGNS_DEBUG") ? atoi(getenv("DGE_SGNS_DEBUG")) : 0; // 1: no reductions (timing experiments), 2 / 32: never / always use 4-lane groups for D <= 16 (A/B, tests), 8: item kernel on ONE warp, one item at a time (tests), 64 / 128: always / never use the target-parallel kernel for D <= 16, K <= 7 (A/B, tests), 256: experimental kernel C' (rows staged in shared memory by cp.async) where kernel C would run
     sgns_variant var;
     if (n4 > 128) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: dim must be <= 512");
     if (p->neg_table_size >= (1 << 30)) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: neg_table_size must be < 2^30");
@@ -1347,7 +1575,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             const bool narrow = (dbg & 32) || (!(dbg & 2) && allowed >= (int64_t)ctx->sm_count * 4 * 32);
             // fewer pairs in flight than the 8-lane kernel needs to fill the GPU (5 blocks x 16 groups per SM): latency-bound
             const bool tp = (dbg & 64) || (!(dbg & (128 | 32)) && allowed < (int64_t)ctx->sm_count * 5 * 16);
-            if (!pick_variant(n4, p->negative, narrow, tp, &var)) { dge_free(ctx, d_wtok); return fail("dge_sgns_train: no kernel variant"); }
+            if (!pick_variant(n4, p->negative, narrow, tp, (dbg & 256) != 0, &var)) { dge_free(ctx, d_wtok); return fail("dge_sgns_train: no kernel variant"); }
         }
         sgns_kernel_t fn = sequential ? var.seq : var.items;
         const int G = sequential ? var.G_seq : var.G_items;
@@ -1360,7 +1588,8 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         int gpb = threads / G;
         // dynamic shared memory: the sigmoid table, plus (pipelined item kernel) one staged sentence per group
         auto smem_for = [&](int thr) {
-            return sizeof(float) * (size_t)p->exp_table_size + (sequential ? 0 : sizeof(int32_t) * (size_t)(thr / G) * (size_t)Lmax);
+            return sizeof(float) * (size_t)p->exp_table_size + (sequential ? 0 : sizeof(int32_t) * (size_t)(thr / G) * (size_t)Lmax) +
+                   (!sequential && var.items_code == 5 ? (size_t)thr * 2 * (SGNS_CH + 1) * 16 : 0); // kernel C': two row stages per lane
         };
         size_t smem = smem_for(threads);
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

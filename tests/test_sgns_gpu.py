@@ -2,6 +2,8 @@
 oracle/sgns_oracle.h); what is checked: (i) identical vocabulary / pair / negative enumeration and fp32-
 tolerance agreement with the CPU oracle in a sequential schedule, (ii) the parallel Hogwild schedule reaches
 the same embedding quality."""
+import os
+
 import numpy as np
 import pytest
 
@@ -121,6 +123,8 @@ def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negati
         flag_sets.append("40")                      # 8 | 32: the 4-lane-group kernel for D <= 16
         if negative <= 7:
             flag_sets.append("72")                  # 8 | 64: the target-parallel kernel (D <= 16, K <= 7)
+    if os.environ.get("DGE_TEST_EXPERIMENTAL") and dim <= 128:
+        flag_sets.append("264")                     # 8 | 256: kernel C' (rows staged in shared memory by cp.async), not yet measured
     for flags in flag_sets:
         monkeypatch.setenv("DGE_SGNS_DEBUG", flags)
         e0, e1 = rel_err()
