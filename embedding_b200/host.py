@@ -552,3 +552,60 @@ class DeepWalk:
         os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)
         model.write_vec(out, labels[0], labels[1])                                   # :82
         return model
+
+    _sample_scale = 1.0                # test hook (not in the reference): scales the per-level numSamples of checkInputFile
+
+    @classmethod
+    def main(cls, argv, flows, spatial_weights, ctx=None):
+        """DeepWalk.main :120-140: `[regionLevel] [spatialGF] [Year]` with the reference's defaults, then
+        checkInputFile + learnEmbedding.  The reference deserialises the flow maps and reads the shapefiles itself
+        (absent here), so the host hands in `flows` and the spatial weight matrix.  Exceptions are reported
+        and swallowed like the reference's printStackTrace() (:137-139); returns the model or None."""
+        import traceback
+        regionLevel, spatialGF = "tract", "usespatial"                                 # :116-118
+        if len(argv) > 0:
+            regionLevel = argv[0]
+        if len(argv) > 1:
+            spatialGF = argv[1]
+        if len(argv) > 2:
+            cls.Year = int(argv[2])
+        try:
+            if regionLevel not in ("tract", "CA") or spatialGF not in ("usespatial", "nospatial", "onlyspatial"):
+                raise ValueError("usage: DeepWalk [tract|CA] [usespatial|nospatial|onlyspatial] [Year]")
+            ctx = ctx or default_context()
+            made = cls._check_input_scaled(regionLevel, spatialGF, flows, spatial_weights, ctx)
+            ids = np.asarray(flows.region_ids)
+            n = len(ids)
+            pos = {int(r): i for i, r in enumerate(ids)}
+            L = LayeredGraph.numLayer
+            corpora = []
+            if "crosstime" in made:                                                    # FileSentenceIterator order
+                g, c = made["crosstime"]
+                c.relabel((g.v_layer.astype(np.int64) * n + np.array([pos[int(r)] for r in g.v_region])).astype(np.int32), L * n)
+                corpora.append(c)
+            if "spatial" in made:
+                g, c = made["spatial"]
+                c.relabel(np.array([pos[int(r)] for r in g.v_region], np.int32), L * n, position_stride=n)
+                corpora.append(c)
+            labels = ((np.arange(L * n) // n).astype(np.int32), ids[np.arange(L * n) % n].astype(np.int32))
+            return cls.learnEmbedding(regionLevel, spatialGF, corpora, labels, ctx=ctx)
+        except Exception:                                                              # :137-139
+            traceback.print_exc()
+            return None
+
+    @classmethod
+    def _check_input_scaled(cls, regionLevel, spatialGF, flows, spatial_weights, ctx):
+        """checkInputFile with the per-level sizes multiplied by _sample_scale (1.0 = the reference's sizes)."""
+        if cls._sample_scale == 1.0:
+            return cls.checkInputFile(regionLevel, spatialGF, flows, spatial_weights, ctx)
+        out = {}
+        k = cls._sample_scale
+        if spatialGF in ("usespatial", "onlyspatial"):
+            SpatialGraph.numSamples, SpatialGraph.numLayer = (int(600_000 * k), 8) if regionLevel == "tract" else (int(80_000 * k), 24)
+            out["spatial"] = SpatialGraph.outputSampleSequence(regionLevel, flows.region_ids, spatial_weights,
+                                                               cls._seq_path(regionLevel, "spatial"), ctx)
+        if spatialGF in ("nospatial", "usespatial"):
+            CrossTimeGraph.numSamples, CrossTimeGraph.numLayer = (int(15_000_000 * k), 8) if regionLevel == "tract" else (int(8_000_000 * k), 24)
+            out["crosstime"] = CrossTimeGraph.outputSampleSequence(regionLevel, flows, cls._seq_path(regionLevel, "crosstime"), ctx=ctx)
+        return out
+

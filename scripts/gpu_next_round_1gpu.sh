@@ -2,7 +2,7 @@
 # Next round, one GPU: A/B of the experimental skip-gram kernel C' (rows of a unit staged in shared memory by cp.async,
 # DGE_SGNS_DEBUG=256) against kernel C -- parity first, then timing on the bench workload and the synthetic one.
 mkdir -p gpurun_out
-DGE_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_sgns_gpu.py -m gpu -q -k item_kernel --tb=short 2>&1 | tail -6
+DGE_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_sgns_gpu.py tests/test_pipeline_gpu.py -m gpu -q -k "item_kernel or deepwalk_main" --tb=short 2>&1 | tail -6
 for dbg in 0 256; do
   echo "== tract24 4M walks DGE_SGNS_DEBUG=$dbg"; DGE_SGNS_DEBUG=$dbg timeout 300 python scripts/prof_path.py tract24 4000000 2>&1 | tail -1
   echo "== tract8 4M walks DGE_SGNS_DEBUG=$dbg";  DGE_SGNS_DEBUG=$dbg timeout 300 python scripts/prof_path.py tract 4000000 2>&1 | tail -1
