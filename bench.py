@@ -305,9 +305,14 @@ def run_gpu_arm(args, w, rank, world, dist):
     n_tok_sp = (sp["n_walks"] * L) if sp else 0
     pin_flow = abi.PinnedArray((f["n_walks"], L), np.int32)
     pin_sp = abi.PinnedArray((sp["n_walks"], L), np.int32) if sp else None
+    # --tokens16 (off until verified on a GPU): the walk stage hands 16-bit tokens to the host
+    tok16 = bool(args.tokens16) and f["nv"] <= 65535 and (sp is None or sp["nv"] <= 65535)
+    pin16_flow = abi.PinnedArray((f["n_walks"], L), np.uint16) if tok16 else None
+    pin16_sp = abi.PinnedArray((sp["n_walks"], L), np.uint16) if (tok16 and sp) else None
     e_walk_ms, e_sg_ms, e_pairs = [], [], []
     h2d_walk = len(f["src"]) * 16 + len(f["sources"]) * 4 + ((len(sp["src"]) * 16 + sp["nv"] * 12) if sp else 0)
-    d2h_walk = (n_tok_flow + n_tok_sp) * 4
+    d2h_walk = (n_tok_flow + n_tok_sp) * (2 if tok16 else 4)
+    h2d_sgns = (n_tok_flow + n_tok_sp) * 4
     G.free()
     if S is not None:
         S.free()
@@ -318,10 +323,19 @@ def run_gpu_arm(args, w, rank, world, dist):
         t0 = time.perf_counter()
         G, S = build_graphs()                                 # host COO -> device CSR + alias tables
         c1, c2, _ = walk(G, S, seed=2000 + it)
-        c1.tokens(pin_flow.array)                             # device -> pinned host
-        if c2 is not None:
-            c2.tokens(pin_sp.array)
+        if tok16:
+            c1.tokens_u16(pin16_flow.array)                   # device -> pinned host, 16-bit tokens
+            if c2 is not None:
+                c2.tokens_u16(pin16_sp.array)
+        else:
+            c1.tokens(pin_flow.array)                         # device -> pinned host
+            if c2 is not None:
+                c2.tokens(pin_sp.array)
         t1 = time.perf_counter()
+        if tok16:                                             # untimed: the int32 host corpus stage 2 starts from
+            c1.tokens(pin_flow.array)
+            if c2 is not None:
+                c2.tokens(pin_sp.array)
         c1.free()
         if c2 is not None:
             c2.free()
@@ -394,7 +408,7 @@ def run_gpu_arm(args, w, rank, world, dist):
         walk=dict(value=tot_steps / t_walk, unit="steps/s", ms_per_step=t_walk / args.steps * 1e3, kernel="k_walk_alias",
                   kernel_ms=wk_ms,
                   e2e=dict(value=e_tot_steps / e_t_walk, unit="steps/s", h2d_bytes_per_step=int(h2d_walk), d2h_bytes_per_step=int(d2h_walk),
-                           includes="dge_graph_build from host COO + dge_walk + dge_corpus_tokens to pinned host"),
+                           includes="dge_graph_build from host COO + dge_walk + dge_corpus_tokens%s to pinned host" % ("_u16" if tok16 else "")),
                   roofline=dict(bound="hbm", achieved=walk_ach, peak=peak, unit="GB/s", frac=walk_ach / peak,
                                 traffic=ncu_traffic(w["name"], "k_walk_alias"), bytes_per_unit=WALK_BYTES_PER_STEP, peak_source=peak_src,
                                 note=resident_note),
@@ -402,7 +416,7 @@ def run_gpu_arm(args, w, rank, world, dist):
         sgns=dict(value=tot_pairs / t_sgns, unit="pairs/s", ms_per_step=t_sgns / args.steps * 1e3, kernel=sg_kernel,
                   kernel_ms=sk_ms, groups_in_flight=ctx.phase_ms("sgns_groups"), sync_rounds=ctx.phase_ms("sgns_rounds"),
                   sync_ms=ctx.phase_ms("sgns_sync"),
-                  e2e=dict(value=e_tot_pairs / e_t_sgns, unit="pairs/s", h2d_bytes_per_step=int(d2h_walk), d2h_bytes_per_step=int(d2h_sgns),
+                  e2e=dict(value=e_tot_pairs / e_t_sgns, unit="pairs/s", h2d_bytes_per_step=int(h2d_sgns), d2h_bytes_per_step=int(d2h_sgns),
                            includes="dge_corpus_from_tokens from pinned host + dge_sgns_train + dge_model_vectors to host"),
                   roofline=dict(bound="hbm", achieved=sgns_ach, peak=peak, unit="GB/s", frac=sgns_ach / peak,
                                 traffic=ncu_traffic(w["name"], "k_sgns_items"), bytes_per_unit=sgns_bytes_per_pair(dim, neg),
@@ -438,6 +452,7 @@ def main():
     ap.add_argument("--workload", default="tract24")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: device-resident loop only")
+    ap.add_argument("--tokens16", action="store_true", help="walk e2e downloads 16-bit tokens (dge_corpus_tokens_u16; id space < 65536)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -65,6 +65,7 @@ def lib():
     L.dge_corpus_from_tokens.argtypes = [vp, pi32, i64, i32, i32, P(vp)]
     L.dge_corpus_shape.argtypes = [vp, pi64, pi32, pi32]
     L.dge_corpus_tokens.argtypes = [vp, pi32]
+    L.dge_corpus_tokens_u16.argtypes = [vp, P(C.c_uint16)]
     L.dge_corpus_count_tokens.argtypes = [vp, pi64]
     L.dge_corpus_relabel.argtypes = [vp, pi32, i32, i32]
     L.dge_corpus_write_seq.argtypes = [vp, pi32, pi32, C.c_int, C.c_char_p, C.c_int]
@@ -416,6 +417,14 @@ class Corpus:
             out = np.empty((self.n_walks, self.L), np.int32)
         assert out.dtype == np.int32 and out.size == self.n_walks * self.L and out.flags.c_contiguous
         _check(lib().dge_corpus_tokens(self._h, _ptr(out, C.c_int32)), self.ctx._h)
+        return out
+
+    def tokens_u16(self, out=None):
+        """Walk-major tokens as uint16 (0xFFFF = padding); only for id spaces below 65 535."""
+        if out is None:
+            out = np.empty((self.n_walks, self.L), np.uint16)
+        assert out.dtype == np.uint16 and out.size == self.n_walks * self.L and out.flags.c_contiguous
+        _check(lib().dge_corpus_tokens_u16(self._h, _ptr(out, C.c_uint16)), self.ctx._h)
         return out
 
     def relabel(self, id_map, new_n_ids, position_stride=0):

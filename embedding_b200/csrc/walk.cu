@@ -121,6 +121,23 @@ __global__ void k_tokens_to_walk_major(const int32_t *__restrict__ tok, int64_t 
         if (i < n && j < L) out[i * L + j] = tile[threadIdx.x][r];
     }
 }
+// same transposition, narrowed to 16 bits (0xFFFF = padding); n_ids <= 65535 is checked by the caller
+__global__ void k_tokens_to_walk_major_u16(const int32_t *__restrict__ tok, int64_t n, int32_t L, uint16_t *__restrict__ out) {
+    __shared__ int32_t tile[32][33];
+    int64_t i0 = (int64_t)blockIdx.x * 32;
+    int32_t j0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int64_t i = i0 + threadIdx.x;
+        int32_t j = j0 + r;
+        if (i < n && j < L) tile[r][threadIdx.x] = tok[(int64_t)j * n + i];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int64_t i = i0 + r;
+        int32_t j = j0 + threadIdx.x;
+        if (i < n && j < L) out[i * L + j] = (uint16_t)tile[threadIdx.x][r]; // -1 -> 0xFFFF
+    }
+}
 __global__ void k_tokens_to_pos_major(const int32_t *__restrict__ in, int64_t n, int32_t L, int32_t *__restrict__ tok) {
     __shared__ int32_t tile[32][33];
     int64_t i0 = (int64_t)blockIdx.x * 32;
@@ -304,6 +321,29 @@ int dge_corpus_tokens(const dge_corpus *c, int32_t *tokens) {
     if (e == cudaSuccess) e = cudaGetLastError();
     dge_free(ctx, stage);
     if (e != cudaSuccess) return dge_fail(ctx, DGE_E_CUDA, std::string("dge_corpus_tokens: ") + cudaGetErrorString(e));
+    return DGE_OK;
+}
+
+int dge_corpus_tokens_u16(const dge_corpus *c, uint16_t *tokens) {
+    if (!c) return dge_fail(nullptr, DGE_E_INVALID, "dge_corpus_tokens_u16: corpus is NULL");
+    dge_ctx *ctx = c->ctx;
+    if (c->n_ids > 65535) return dge_fail(ctx, DGE_E_LIMIT, "dge_corpus_tokens_u16: the id space does not fit 16 bits (0xFFFF is the padding)");
+    size_t total = (size_t)c->n * (size_t)c->L;
+    if (total == 0) return DGE_OK;
+    if (!tokens) return dge_fail(ctx, DGE_E_INVALID, "dge_corpus_tokens_u16: tokens is NULL");
+    DGE_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint16_t *stage = nullptr;
+    DGE_CUDA(ctx, dge_malloc(ctx, &stage, total));
+    dge_phase_timer t(ctx, "tokens_d2h");
+    dim3 grid((unsigned)((c->n + 31) / 32), (unsigned)((c->L + 31) / 32)), block(32, 8);
+    k_tokens_to_walk_major_u16<<<grid, block, 0, ctx->stream>>>(c->tok, c->n, c->L, stage);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(tokens, stage, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream);
+    t.stop();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    dge_free(ctx, stage);
+    if (e != cudaSuccess) return dge_fail(ctx, DGE_E_CUDA, std::string("dge_corpus_tokens_u16: ") + cudaGetErrorString(e));
     return DGE_OK;
 }
 

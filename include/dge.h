@@ -168,6 +168,10 @@ int dge_corpus_from_tokens(dge_ctx *ctx, const int32_t *tokens, int64_t n_walks,
 int dge_corpus_shape(const dge_corpus *c, int64_t *n_walks, int32_t *L, int32_t *n_ids);
 /* tokens[n_walks * L] walk-major, -1 padded after a dead end (Java: sampleNextVertex() == null). */
 int dge_corpus_tokens(const dge_corpus *c, int32_t *tokens);
+/* Same, as 16-bit tokens (0xFFFF = padding) for id spaces below 65 535 -- every reference-scale graph (CA: 1 848
+ * vertices, tract x 24: 19 224).  The download of the walk corpus is bound by the PCIe link, so half the
+ * bytes is half the time; a JNI host receives a short[] / ShortBuffer.  DGE_E_LIMIT when n_ids > 65 535. */
+int dge_corpus_tokens_u16(const dge_corpus *c, uint16_t *tokens);
 /* In-place change of id space: token t at walk position j becomes id_map[t] + j * position_stride; the
  * corpus then reports new_n_ids.  This is how the host puts both corpora of the "usespatial" run into ONE
  * vocabulary, exactly as the token strings do in the reference: a cross-time token "<h>-<region>"

@@ -30,6 +30,8 @@ public final class DgeNative {
     /** the loop of CrossTimeGraph.sampleSequenceHelper / SpatialGraph.outputSampleSequence -> dge_walk. */
     public static native long walk(long graph, long nWalks, long firstWalkId, int numLayer, long seed, int sampler);
     public static native void corpusTokens(long corpus, int[] tokensOut);
+    /** 16-bit tokens (0xFFFF = padding) for id spaces below 65 535: half the PCIe bytes -> dge_corpus_tokens_u16. */
+    public static native void corpusTokensU16(long corpus, short[] tokensOut);
     public static native void corpusRelabel(long corpus, int[] idMap, int newNIds, int positionStride);
     public static native void corpusWriteSeq(long corpus, int[] labelLayer, int[] labelRegion, boolean positionPrefix,
                                              String path, boolean append);

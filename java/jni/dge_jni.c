@@ -51,6 +51,13 @@ JNIEXPORT jlong JNICALL Java_embedding_DgeNative_walk(JNIEnv *env, jclass c, jlo
     return (jlong)(intptr_t)corpus;
 }
 
+JNIEXPORT void JNICALL Java_embedding_DgeNative_corpusTokensU16(JNIEnv *env, jclass c, jlong jc, jshortArray jout) {
+    jshort *out = (*env)->GetPrimitiveArrayCritical(env, jout, NULL);
+    int rc = dge_corpus_tokens_u16((const dge_corpus *)(intptr_t)jc, (uint16_t *)out);
+    (*env)->ReleasePrimitiveArrayCritical(env, jout, out, 0);
+    if (rc != DGE_OK) throw_dge(env, NULL);
+}
+
 JNIEXPORT jlong JNICALL Java_embedding_DgeNative_sgnsTrain(JNIEnv *env, jclass c, jlong jctx, jlongArray jcorp, jint dim,
         jint window, jint negative, jint minCount, jint epochs, jfloat lr, jfloat minLr, jlong seed) {
     dge_ctx *ctx = (dge_ctx *)(intptr_t)jctx;

@@ -1,5 +1,7 @@
 """GPU parity, stage 1b: walks.  With the same counter-based Philox stream the CUDA walks are identical to the
 oracle's edge by edge; statistically they follow the reference's transition distribution (chi-square)."""
+import os
+
 import numpy as np
 import pytest
 from scipy import stats
@@ -99,6 +101,19 @@ def test_every_step_is_an_edge_and_layers_advance(dge_lib, ctx):
     sub = tok[:: 50]
     pair = sub[:, :-1].astype(np.int64) * g["n_vertices"] + sub[:, 1:]
     assert np.isin(pair.ravel(), key).all()
+
+
+@pytest.mark.skipif(not os.environ.get("DGE_TEST_EXPERIMENTAL"), reason="16-bit token download: written after the round's GPU budget ended, first run next round")
+def test_tokens_u16_equal_tokens(dge_lib, ctx):
+    g = small_graph(seed=12)
+    G = dge_lib.Graph(ctx, g["n_vertices"], g["src"], g["dst"], g["w"], g["sources"])
+    for n, L in ((1, 1), (33, 7), (50_000, 24)):
+        c = G.walk(n, L, seed=4)
+        a, b = c.tokens(), c.tokens_u16()
+        assert np.array_equal(np.where(a < 0, 0xFFFF, a).astype(np.uint16), b)
+    big = dge_lib.Corpus.from_tokens(ctx, np.array([[70_000, -1]], np.int32), 70_001)
+    with pytest.raises(dge_lib.DgeError):
+        big.tokens_u16()                      # id space does not fit 16 bits
 
 
 def test_corpus_roundtrip_relabel_and_seq_format(dge_lib, ctx, tmp_path):
