@@ -77,7 +77,7 @@ def make_workload(name, rank=0):
         host.CrossTimeGraph.numLayer = L
         g = host.CrossTimeGraph.constructGraph_CA(fl) if name == "ca" else host.CrossTimeGraph.constructGraph_tract(fl)
         nv, src, dst, wt = g._bulk
-        sp = host.SpatialGraph.constructGraph(ids, synth.spatial_weights(len(ids)))
+        sp = host.SpatialGraph.constructGraph(ids, synth.planted_spatial_weights(z))
         snv, ssrc, sdst, swt = sp._bulk
         n = len(ids)
         pos = {int(r): i for i, r in enumerate(ids)}
@@ -272,7 +272,8 @@ def run_gpu_arm(args, w, rank, world, dist):
     for it in range(args.warmup + args.steps):
         if it == args.warmup:
             sync_all()
-            clocks.start()
+            if not args.no_clock_sampler:
+                clocks.start()
             launches0 = ctx.kernel_launches()
         # device time of each stage: CUDA events on the ctx stream (the stream every libdge kernel runs on)
         ctx.timer_start()
@@ -452,6 +453,7 @@ def main():
     ap.add_argument("--workload", default="tract24")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: device-resident loop only")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="experiment: do not poll nvidia-smi during the device-resident loop")
     ap.add_argument("--tokens16", action="store_true", help="walk e2e downloads 16-bit tokens (dge_corpus_tokens_u16; id space < 65536)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -14,6 +14,11 @@ LIB_PATH = os.path.join(_HERE, "libdge.so")
 
 SAMPLER_ALIAS, SAMPLER_CDF = 0, 1
 SCHEDULE_ITEMS, SCHEDULE_SENTENCE = 0, 1
+COMBINE_DEFAULT, COMBINE_MEAN, COMBINE_CONTRIBUTORS, COMBINE_SQRT, COMBINE_ALIGNED, COMBINE_SUM = 0, 1, 2, 3, 4, 5
+TRANSPORT_AUTO, TRANSPORT_PEER, TRANSPORT_NCCL = 0, 1, 2
+# dge_sgns_params.flags (include/dge.h DGE_SGNS_F_*): kernel-selection / measurement hooks for tests and A/B runs
+F_NO_UPDATES, F_NO_NARROW, F_ONE_WARP, F_NARROW, F_TARGET_PARALLEL, F_NO_TARGET_PARALLEL, F_STAGED_ROWS, F_PLAIN_STORES = \
+    1, 2, 8, 32, 64, 128, 256, 512
 COMM_ID_BYTES = 128
 
 class DgeError(RuntimeError):
@@ -25,7 +30,8 @@ class DgeError(RuntimeError):
 class SgnsParams(C.Structure):
     _fields_ = [("dim", C.c_int32), ("window", C.c_int32), ("negative", C.c_int32), ("min_count", C.c_int32),
                 ("epochs", C.c_int32), ("neg_table_size", C.c_int32), ("exp_table_size", C.c_int32),
-                ("concurrency", C.c_int32), ("schedule", C.c_int32), ("sync_rounds", C.c_int32), ("lr", C.c_float), ("min_lr", C.c_float), ("seed", C.c_uint64)]
+                ("concurrency", C.c_int32), ("schedule", C.c_int32), ("sync_rounds", C.c_int32), ("combine", C.c_int32),
+                ("transport", C.c_int32), ("flags", C.c_uint32), ("lr", C.c_float), ("min_lr", C.c_float), ("seed", C.c_uint64)]
 
 
 _lib = None
@@ -449,8 +455,12 @@ class Corpus:
 
 
 def sgns_params(**kw):
+    """dge_sgns_default_params + overrides.  A/B scripts may set DGE_SGNS_FLAGS in the environment: it is read HERE, on
+    the host side, and travels in the explicit `flags` field -- the library itself never reads the environment."""
     p = SgnsParams()
     lib().dge_sgns_default_params(C.byref(p))
+    if "flags" not in kw and os.environ.get("DGE_SGNS_FLAGS"):
+        kw = dict(kw, flags=int(os.environ["DGE_SGNS_FLAGS"]))
     for k, v in kw.items():
         if not hasattr(p, k):
             raise TypeError("unknown SGNS parameter %r" % k)

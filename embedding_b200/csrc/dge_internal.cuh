@@ -85,6 +85,7 @@ struct dge_model {
     int64_t pairs = 0;   // (centre, context) updates executed
     int64_t words = 0;   // in-vocabulary tokens of the corpus
     float *syn0 = nullptr, *syn1neg = nullptr; // device [V*stride]
+    bool plain_alloc = false;                  // tables from cudaMalloc (mappable by peer ranks) instead of the ctx pool
     int32_t *id_of_word = nullptr;             // device [V]
 };
 
@@ -92,6 +93,17 @@ struct dge_model {
 int dge_comm_allreduce_sum_f32(dge_ctx *ctx, float *buf, size_t n);
 int dge_comm_allreduce_sum_u64(dge_ctx *ctx, unsigned long long *buf, size_t n);
 int dge_comm_allreduce_max_u64(dge_ctx *ctx, unsigned long long *buf, size_t n);
+int dge_comm_allgather_u64(dge_ctx *ctx, const unsigned long long *mine, int n_per_rank, unsigned long long *out_host);
+int dge_comm_agree(dge_ctx *ctx, int local_status, const char *what);
+// data-parallel exchange of the skip-gram replicas (comm.cu)
+#define DGE_DP_MAX_WORLD 16
+struct dge_dp;
+int dge_dp_begin(dge_ctx *ctx, float *syn0, float *syn1neg, int32_t V, int32_t stride, int32_t n4, int combine, int transport,
+                 dge_dp **out);
+int dge_dp_exchange(dge_dp *dp, int local_error, bool check, int *any_error);
+void dge_dp_end(dge_dp *dp);
+float dge_dp_ms(const dge_dp *dp);
+bool dge_dp_uses_peer_memory(const dge_dp *dp);
 
 // ---- error plumbing
 void dge_set_error(dge_ctx *ctx, const std::string &msg);

@@ -41,6 +41,9 @@ struct sgns_args {
     int64_t n_groups;
     int32_t ep_lo, ep_hi;     // epochs [ep_lo, ep_hi) and sentences [s_lo, s_hi) of this launch (multi-GPU rounds
     int64_t s_lo, s_hi;       // launch one slice at a time; a single-GPU run is one launch over everything)
+    int64_t s_off, n_global;  // data-parallel shard: global index of local sentence 0 and the global sentence count.  RNG keys
+                              // and the learning-rate schedule use GLOBAL sentence indices, so the shards of all ranks
+                              // enumerate exactly the pairs and negatives of a single-GPU run over the whole corpus
     uint64_t lcg_a[SGNS_MAX_NEG], lcg_c[SGNS_MAX_NEG]; // (k+1)-step jump of the negative-sampling LCG
     int32_t dbg;
 };
@@ -62,7 +65,7 @@ __host__ __device__ static inline uint64_t sgns_pair_rng(uint64_t S, int32_t i, 
     return mix64(S ^ (0xD6E8FEB86659FD93ULL * (uint64_t)((int64_t)i * 65536 + c + 1)));
 }
 __device__ __forceinline__ float sgns_alpha(const sgns_args &a, int ep, int64_t s) {
-    double progress = (double)((int64_t)ep * a.n_sent + s) / (double)((int64_t)a.epochs * a.n_sent);
+    double progress = (double)((int64_t)ep * a.n_global + a.s_off + s) / (double)((int64_t)a.epochs * a.n_global);
     float alpha = a.lr * (float)(1.0 - progress);
     return alpha < a.min_lr ? a.min_lr : alpha;
 }
@@ -179,7 +182,7 @@ k_sgns_seq(const sgns_args a) {
             int n = 0;
             while (n < a.Lmax && a.wtok[(int64_t)n * N + s] >= 0) n++;
             const float alpha = sgns_alpha(a, ep, s);
-            const uint64_t S = sgns_sentence_rng(a.seed, ep, s);
+            const uint64_t S = sgns_sentence_rng(a.seed, ep, s + a.s_off);
             for (int i = 0; i < n; i++) {
                 const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
                 const int32_t w1 = a.wtok[(int64_t)i * N + s];
@@ -291,7 +294,7 @@ k_sgns_items(const sgns_args a) {
     const int win = a.window;
     const int64_t N = a.n_sent;
     const int64_t item_lo = a.s_lo * a.Lmax, n_items = a.s_hi * a.Lmax; // items [item_lo, n_items) of this launch
-    const double inv_total = 1.0 / (double)((int64_t)a.epochs * N);
+    const double inv_total = 1.0 / (double)((int64_t)a.epochs * a.n_global);
     const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
     const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -315,9 +318,9 @@ k_sgns_items(const sgns_args a) {
             const int32_t w1 = a.wtok[(int64_t)i * N + s]; // (s, i) = (0, 0) when the item is out of range: in bounds
             valid = valid && w1 >= 0;
             if (!__any_sync(FULL, valid)) continue;
-            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * N + s) * inv_total);
+            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * a.n_global + a.s_off + s) * inv_total);
             if (alpha < a.min_lr) alpha = a.min_lr;
-            const uint64_t S = sgns_sentence_rng(a.seed, ep, s);
+            const uint64_t S = sgns_sentence_rng(a.seed, ep, s + a.s_off);
             const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
             const int lo = i - win + b, hi = i + win - b; // inclusive context range (SkipGram.skipGram)
             float4 *pw = reinterpret_cast<float4 *>(a.syn1neg + (int64_t)(valid ? w1 : 0) * a.stride);
@@ -458,7 +461,17 @@ __device__ __forceinline__ void ldcg4_into(float4 &r, uint64_t p, bool pred) {
 // After this rebuild the kernel runs at ~2/3 of what the memory system itself delivers for its access pattern
 // (random 80-byte-row 128-bit loads + reductions, scripts/red_microbench.cu, profiles/r1s7_red_microbench.txt):
 // the reductions, not the instruction stream, are the limit now.
-template <int G, bool MULTI>
+// PLAIN = true is the atomic-free build north_star's wording asks for ("Hogwild-style atomic-free row updates"): every
+// row update is a plain 128-bit store of (row as loaded + its update) instead of an L2 reduction, so an update that
+// lands between a group's load and its store is LOST (classic Hogwild).  Selected only by DGE_SGNS_F_PLAIN_STORES
+// (A/B: throughput and downstream metric against the reduction build); never the default.
+__device__ __forceinline__ void stcg4_if(uint64_t p, const float4 &v, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p st.global.cg.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+                 ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ float4 add4(const float4 &a, const float4 &b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+template <int G, bool MULTI, bool PLAIN>
 __global__ void __launch_bounds__(128, 5)
 k_sgns_items_v2(const sgns_args a) {
     static_assert(G == 8 || G == 16 || G == 32, "lane groups of 8, 16 or 32");
@@ -480,7 +493,7 @@ k_sgns_items_v2(const sgns_args a) {
     const int64_t N = a.n_sent;
     const int Lmax = a.Lmax;
     const int64_t item_lo = a.s_lo * Lmax, n_items = a.s_hi * Lmax; // items [item_lo, n_items) of this launch
-    const double inv_total = 1.0 / (double)((int64_t)a.epochs * N);
+    const double inv_total = 1.0 / (double)((int64_t)a.epochs * a.n_global);
     const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
     const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -518,10 +531,10 @@ k_sgns_items_v2(const sgns_args a) {
             const int32_t w1 = mytok[i];
             valid = valid && w1 >= 0;
             if (!__any_sync(FULL, valid)) continue;
-            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * N + s) * inv_total);
+            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * a.n_global + a.s_off + s) * inv_total);
             if (alpha < a.min_lr) alpha = a.min_lr;
             const float g_hi = (my_label - 1.f) * alpha, g_lo = my_label * alpha; // saturated sigmoid: dot > 6, dot < -6
-            const uint64_t S = sgns_sentence_rng(a.seed, ep, s);
+            const uint64_t S = sgns_sentence_rng(a.seed, ep, s + a.s_off);
             const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
             // inclusive context range (SkipGram.skipGram); an invalid item gets the empty range
             const int lo = valid ? i - win + b : 1, hi = valid ? i + win - b : 0;
@@ -608,7 +621,8 @@ k_sgns_items_v2(const sgns_args a) {
 #pragma unroll
                 for (int k = 0; k < SGNS_CH; k++) {
                     axpy4(neu, gk[k], r.row[k]);
-                    red_add4_if(row_addr(base1, (uint32_t)r.tg[k], pitch), scale4(gk[k], v0), gk[k] != 0.f && live && !(a.dbg & 1));
+                    if (PLAIN) { float4 nr = r.row[k]; axpy4(nr, gk[k], v0); stcg4_if(row_addr(base1, (uint32_t)r.tg[k], pitch), nr, gk[k] != 0.f && live && !(a.dbg & 1)); }
+                    else red_add4_if(row_addr(base1, (uint32_t)r.tg[k], pitch), scale4(gk[k], v0), gk[k] != 0.f && live && !(a.dbg & 1));
                 }
                 if (first) { // positive target: the item's private, always-current copy of syn1neg[w1]
                     axpy4(neu, gk[SGNS_CH], cur);
@@ -623,9 +637,15 @@ k_sgns_items_v2(const sgns_args a) {
                             ns.x += __shfl_xor_sync(FULL, ns.x, o); ns.y += __shfl_xor_sync(FULL, ns.y, o);
                             ns.z += __shfl_xor_sync(FULL, ns.z, o); ns.w += __shfl_xor_sync(FULL, ns.w, o);
                         }
+                        if (PLAIN) { // the first active group holds a valid copy of the row and stores row + sum
+                            const unsigned am = __ballot_sync(FULL, r.act);
+                            const int first_gw = am ? (__ffs(am) - 1) / G : -1;
+                            stcg4_if(row_addr(base0, (uint32_t)r.last, pitch), add4(v0, ns), gw == first_gw && live && !(a.dbg & 1));
+                        } else
                         red_add4_if(row_addr(base0, (uint32_t)r.last, pitch), ns, gw == 0 && live && !(a.dbg & 1));
                     } else {
-                        red_add4_if(row_addr(base0, (uint32_t)r.last, pitch), neu, r.act && live && !(a.dbg & 1));
+                        if (PLAIN) stcg4_if(row_addr(base0, (uint32_t)r.last, pitch), add4(v0, neu), r.act && live && !(a.dbg & 1));
+                        else red_add4_if(row_addr(base0, (uint32_t)r.last, pitch), neu, r.act && live && !(a.dbg & 1));
                     }
                 }
             };
@@ -641,6 +661,11 @@ k_sgns_items_v2(const sgns_args a) {
                 t1 = stageT();    // table lookups of unit u+1 (independent work while the rows arrive)
                 compute(rA);
             }
+            if (PLAIN) { // re-read the row and store row + the item's accumulated delta (a short load-to-store window)
+                float4 now = zero4;
+                ldcg4_into(now, row_addr(base1, (uint32_t)w1, pitch), valid && live);
+                stcg4_if(row_addr(base1, (uint32_t)w1, pitch), add4(now, d1), valid && live && !(a.dbg & 1));
+            } else
             red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, valid && live && !(a.dbg & 1));
             pairs += (unsigned)npairs;
         }
@@ -671,8 +696,10 @@ __device__ __forceinline__ float4 lds4(uint32_t smem_addr) {
 
 __device__ __forceinline__ float sgns_g_lane(float tot, float label, float alpha, float g_hi, float g_lo, const float *s_exp,
                                              int E, float idx_scale);
-template <int G, bool MULTI>
-__global__ void __launch_bounds__(128, 5)
+// BLK = resident blocks per SM the register allocation is made for (5: 96 registers, no spill to speak of; 6: 80; 7: 72
+// with a few dozen bytes of spill -- more warps to hide the L2 latency with; A/B by DGE_SGNS_F_BLOCKS_*).
+template <int G, bool MULTI, int BLK>
+__global__ void __launch_bounds__(128, BLK)
 k_sgns_items_v3(const sgns_args a) {
     static_assert(G == 8 || G == 16 || G == 32, "lane groups of 8, 16 or 32");
     extern __shared__ __align__(16) int32_t smem_v3[];
@@ -700,7 +727,7 @@ k_sgns_items_v3(const sgns_args a) {
     const int64_t N = a.n_sent;
     const int Lmax = a.Lmax;
     const int64_t item_lo = a.s_lo * Lmax, n_items = a.s_hi * Lmax;
-    const double inv_total = 1.0 / (double)((int64_t)a.epochs * N);
+    const double inv_total = 1.0 / (double)((int64_t)a.epochs * a.n_global);
     const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
     const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -736,10 +763,10 @@ k_sgns_items_v3(const sgns_args a) {
             const int32_t w1 = mytok[i];
             valid = valid && w1 >= 0;
             if (!__any_sync(FULL, valid)) continue;
-            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * N + s) * inv_total);
+            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * a.n_global + a.s_off + s) * inv_total);
             if (alpha < a.min_lr) alpha = a.min_lr;
             const float g_hi = (my_label - 1.f) * alpha, g_lo = my_label * alpha;
-            const uint64_t S = sgns_sentence_rng(a.seed, ep, s);
+            const uint64_t S = sgns_sentence_rng(a.seed, ep, s + a.s_off);
             const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
             const int lo = valid ? i - win + b : 1, hi = valid ? i + win - b : 0;
             const int c_min = __reduce_min_sync(FULL, valid ? max(lo, 0) : Lmax);
@@ -913,7 +940,7 @@ k_sgns_items_g4(const sgns_args a) {
     const int64_t N = a.n_sent;
     const int Lmax = a.Lmax;
     const int64_t item_lo = a.s_lo * Lmax, n_items = a.s_hi * Lmax;
-    const double inv_total = 1.0 / (double)((int64_t)a.epochs * N);
+    const double inv_total = 1.0 / (double)((int64_t)a.epochs * a.n_global);
     const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
     const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -954,11 +981,11 @@ k_sgns_items_g4(const sgns_args a) {
             const int32_t w1 = mytok[i];
             valid = valid && w1 >= 0;
             if (!__any_sync(FULL, valid)) continue;
-            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * N + s) * inv_total);
+            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * a.n_global + a.s_off + s) * inv_total);
             if (alpha < a.min_lr) alpha = a.min_lr;
             const float gB_hi = (labelB - 1.f) * alpha, gB_lo = labelB * alpha; // saturated sigmoid (value B)
             const float gA_hi = -alpha;                                         // value A is always a negative: label 0
-            const uint64_t S = sgns_sentence_rng(a.seed, ep, s);
+            const uint64_t S = sgns_sentence_rng(a.seed, ep, s + a.s_off);
             const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
             const int lo = valid ? i - win + b : 1, hi = valid ? i + win - b : 0;
             // context positions any group of the warp can pair with: units outside [c_min, c_max] are skipped
@@ -1152,7 +1179,7 @@ k_sgns_items_tp(const sgns_args a) {
     const int64_t N = a.n_sent;
     const int Lmax = a.Lmax;
     const int64_t item_lo = a.s_lo * Lmax, n_items = a.s_hi * Lmax;
-    const double inv_total = 1.0 / (double)((int64_t)a.epochs * N);
+    const double inv_total = 1.0 / (double)((int64_t)a.epochs * a.n_global);
     const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
     const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1185,10 +1212,10 @@ k_sgns_items_tp(const sgns_args a) {
             const int32_t w1 = mytok[i];
             valid = valid && w1 >= 0;
             if (!__any_sync(FULL, valid)) continue;
-            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * N + s) * inv_total);
+            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * a.n_global + a.s_off + s) * inv_total);
             if (alpha < a.min_lr) alpha = a.min_lr;
             const float g_hi = (label - 1.f) * alpha, g_lo = label * alpha; // saturated sigmoid: dot > 6, dot < -6
-            const uint64_t S = sgns_sentence_rng(a.seed, ep, s);
+            const uint64_t S = sgns_sentence_rng(a.seed, ep, s + a.s_off);
             const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
             const int lo = valid ? i - win + b : 1, hi = valid ? i + win - b : 0; // inclusive context range; empty if invalid
             const int c_min = __reduce_min_sync(FULL, valid ? max(lo, 0) : Lmax);
@@ -1271,47 +1298,6 @@ k_sgns_items_tp(const sgns_args a) {
     if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
 }
 
-// multi-GPU delta exchange (see dge_sgns_train):  cur -= base  ...all-reduce(cur, touched)...  base += cur / div; cur = base.
-// touched[row] (syn0 rows first, then syn1neg rows) is 1 on a rank whose delta of that row is non-zero; after the
-// all-reduce it counts the ranks that contributed to the row, and div is chosen by the combine rule (DGE_COMBINE_*).
-#define DGE_COMBINE_SUM 0          // base += sum of the deltas: every update applied; diverges when several ranks saturate the same row
-#define DGE_COMBINE_MEAN 1         // base += sum / world: parameter averaging (rows only one rank saw learn world times slower)
-#define DGE_COMBINE_CONTRIBUTORS 2 // base += sum / max(1, ranks that touched the row): the default
-#define DGE_COMBINE_SQRT 3         // base += sum / sqrt(max(1, ranks that touched the row))
-__global__ void k_delta_begin(float *__restrict__ c0, const float *__restrict__ b0, float *__restrict__ c1,
-                              const float *__restrict__ b1, size_t n, int32_t stride, int32_t V, float *__restrict__ touched) {
-    size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4, step = (size_t)gridDim.x * blockDim.x * 4;
-    for (; i < n; i += step) { // n is a multiple of 4 (rows are whole float4 slots)
-        float4 x = *reinterpret_cast<float4 *>(c0 + i), y = *reinterpret_cast<const float4 *>(b0 + i);
-        x = make_float4(x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w);
-        *reinterpret_cast<float4 *>(c0 + i) = x;
-        const size_t row = i / (size_t)stride;
-        if (x.x != 0.f || x.y != 0.f || x.z != 0.f || x.w != 0.f) touched[row] = 1.f; // same value from every writer
-        x = *reinterpret_cast<float4 *>(c1 + i); y = *reinterpret_cast<const float4 *>(b1 + i);
-        x = make_float4(x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w);
-        *reinterpret_cast<float4 *>(c1 + i) = x;
-        if (x.x != 0.f || x.y != 0.f || x.z != 0.f || x.w != 0.f) touched[(size_t)V + row] = 1.f;
-    }
-}
-__device__ __forceinline__ float combine_div(float contributors, int mode, int world) {
-    const float c = contributors > 1.f ? contributors : 1.f;
-    return mode == DGE_COMBINE_MEAN ? (float)world : (mode == DGE_COMBINE_CONTRIBUTORS ? c : (mode == DGE_COMBINE_SQRT ? sqrtf(c) : 1.f));
-}
-__global__ void k_delta_end(float *__restrict__ c0, float *__restrict__ b0, float *__restrict__ c1, float *__restrict__ b1,
-                            size_t n, int32_t stride, int32_t V, const float *__restrict__ touched, int mode, int world) {
-    size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4, step = (size_t)gridDim.x * blockDim.x * 4;
-    for (; i < n; i += step) {
-        const size_t row = i / (size_t)stride;
-        const float d0 = combine_div(touched[row], mode, world), d1 = combine_div(touched[(size_t)V + row], mode, world);
-        float4 x = *reinterpret_cast<float4 *>(c0 + i), y = *reinterpret_cast<float4 *>(b0 + i);
-        y = make_float4(y.x + __fdiv_rn(x.x, d0), y.y + __fdiv_rn(x.y, d0), y.z + __fdiv_rn(x.z, d0), y.w + __fdiv_rn(x.w, d0));
-        *reinterpret_cast<float4 *>(b0 + i) = y; *reinterpret_cast<float4 *>(c0 + i) = y;
-        x = *reinterpret_cast<float4 *>(c1 + i); y = *reinterpret_cast<float4 *>(b1 + i);
-        y = make_float4(y.x + __fdiv_rn(x.x, d1), y.y + __fdiv_rn(x.y, d1), y.z + __fdiv_rn(x.z, d1), y.w + __fdiv_rn(x.w, d1));
-        *reinterpret_cast<float4 *>(b1 + i) = y; *reinterpret_cast<float4 *>(c1 + i) = y;
-    }
-}
-
 // dge_model_stats: one warp per row of each table; acc[0] += |syn0 row|, acc[1] = max |element| (non-negative doubles
 // order like their bit patterns), bad += non-finite elements
 __global__ void k_model_stats(const float *__restrict__ syn0, const float *__restrict__ syn1neg, int32_t V, int32_t dim,
@@ -1348,7 +1334,7 @@ struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq,
 // Kernel A (exact order): rows of up to 8 float4 slots are held by ONE thread; wider rows give each lane of a
 // 16- or 32-lane group one 128-bit slot (2 or 4 for rows wider than 32 slots).
 // Kernel B (items): groups of 8 / 16 / 32 lanes, one slot per lane (2 or 4 beyond 32 slots).
-static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_parallel, bool staged_rows, sgns_variant *out) {
+static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_parallel, bool staged_rows, bool plain_stores, int blk, sgns_variant *out) {
     if (n4 > 128) return false;
     sgns_kernel_t seq = nullptr, items = nullptr;
     int Gs = 1, Vs = 1;
@@ -1382,13 +1368,24 @@ static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_p
     else if (n4 <= 4 && narrow_groups) { Gi = 4; code = 3; items = multi ? k_sgns_items_g4<1, true> : k_sgns_items_g4<1, false>; }
     else if (n4 <= 32 && staged_rows) { // experimental: rows of a unit staged in shared memory by cp.async (kernel C')
         code = 5;
-        if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v3<8, true> : k_sgns_items_v3<8, false>; }
-        else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v3<16, true> : k_sgns_items_v3<16, false>; }
-        else { Gi = 32; items = multi ? k_sgns_items_v3<32, true> : k_sgns_items_v3<32, false>; }
+        if (n4 <= 8) {
+            Gi = 8;
+            if (blk == 6) items = multi ? k_sgns_items_v3<8, true, 6> : k_sgns_items_v3<8, false, 6>;
+            else if (blk == 7) items = multi ? k_sgns_items_v3<8, true, 7> : k_sgns_items_v3<8, false, 7>;
+            else items = multi ? k_sgns_items_v3<8, true, 5> : k_sgns_items_v3<8, false, 5>;
+        }
+        else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v3<16, true, 5> : k_sgns_items_v3<16, false, 5>; }
+        else { Gi = 32; items = multi ? k_sgns_items_v3<32, true, 5> : k_sgns_items_v3<32, false, 5>; }
     }
-    else if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true> : k_sgns_items_v2<8, false>; }
-    else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v2<16, true> : k_sgns_items_v2<16, false>; }
-    else if (n4 <= 32) { Gi = 32; items = multi ? k_sgns_items_v2<32, true> : k_sgns_items_v2<32, false>; }
+    else if (n4 <= 32 && plain_stores) { // experiment: atomic-free row stores (lost updates allowed)
+        code = 6;
+        if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true, true> : k_sgns_items_v2<8, false, true>; }
+        else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v2<16, true, true> : k_sgns_items_v2<16, false, true>; }
+        else { Gi = 32; items = multi ? k_sgns_items_v2<32, true, true> : k_sgns_items_v2<32, false, true>; }
+    }
+    else if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true, false> : k_sgns_items_v2<8, false, false>; }
+    else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v2<16, true, false> : k_sgns_items_v2<16, false, false>; }
+    else if (n4 <= 32) { Gi = 32; items = multi ? k_sgns_items_v2<32, true, false> : k_sgns_items_v2<32, false, false>; }
     else if (n4 <= 64) { Gi = 32; Vi = 2; code = 1; items = k_sgns_items<32, 2>; }
     else { Gi = 32; Vi = 4; code = 1; items = k_sgns_items<32, 4>; }
     out->G_seq = Gs; out->VPL_seq = Vs; out->seq = seq;
@@ -1398,55 +1395,130 @@ static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_p
 
 static void model_release(dge_model *m) {
     if (!m) return;
-    dge_free(m->ctx, m->syn0); dge_free(m->ctx, m->syn1neg); dge_free(m->ctx, m->id_of_word);
+    if (m->plain_alloc) { // data-parallel run: cudaMalloc'ed so that the other ranks could map them (cudaIpc)
+        cudaStreamSynchronize(m->ctx->stream);
+        cudaFree(m->syn0); cudaFree(m->syn1neg);
+    } else { dge_free(m->ctx, m->syn0); dge_free(m->ctx, m->syn1neg); }
+    dge_free(m->ctx, m->id_of_word);
     delete m;
+}
+
+// device temporaries of one call: released (stream-ordered) on every way out
+struct sgns_scratch {
+    dge_ctx *ctx;
+    std::vector<void *> ptrs;
+    explicit sgns_scratch(dge_ctx *c) : ctx(c) {}
+    ~sgns_scratch() { for (void *q : ptrs) dge_free(ctx, q); }
+    template <typename T> cudaError_t get(T **q, size_t n) {
+        cudaError_t e = dge_malloc(ctx, q, n);
+        if (e == cudaSuccess) ptrs.push_back(*q); else *q = nullptr;
+        return e;
+    }
+};
+
+static int sgns_check_params(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_corpora, const dge_sgns_params *p) {
+    if (!corpora || !p || n_corpora < 1 || n_corpora > SGNS_MAX_CORPORA)
+        return dge_fail(ctx, DGE_E_INVALID, "dge_sgns_train: need 1..4 corpora and params");
+    if (p->negative > SGNS_MAX_NEG) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: negative must be <= 32");
+    if (p->dim < 1 || p->window < 1 || p->negative < 0 || p->epochs < 1 || p->neg_table_size < 1 ||
+        p->exp_table_size < 2 || p->min_count < 0 || p->concurrency < 0 || p->sync_rounds < 0 ||
+        p->combine < DGE_COMBINE_DEFAULT || p->combine > DGE_COMBINE_SUM || p->transport < DGE_TRANSPORT_AUTO ||
+        p->transport > DGE_TRANSPORT_NCCL || (p->schedule != DGE_SCHEDULE_ITEMS && p->schedule != DGE_SCHEDULE_SENTENCE))
+        return dge_fail(ctx, DGE_E_INVALID, "dge_sgns_train: invalid hyper-parameter");
+    if ((p->dim + 3) / 4 > 128) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: dim must be <= 512");
+    if (p->neg_table_size >= (1 << 30)) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: neg_table_size must be < 2^30");
+    const int32_t n_ids = corpora[0] ? corpora[0]->n_ids : 0;
+    for (int i = 0; i < n_corpora; i++) {
+        if (!corpora[i]) return dge_fail(ctx, DGE_E_INVALID, "dge_sgns_train: NULL corpus");
+        if (corpora[i]->ctx != ctx) return dge_fail(ctx, DGE_E_INVALID, "dge_sgns_train: corpus belongs to another ctx");
+        if (corpora[i]->n_ids != n_ids) return dge_fail(ctx, DGE_E_INVALID, "dge_sgns_train: corpora have different id spaces");
+    }
+    return DGE_OK;
 }
 
 extern "C" {
 
 void dge_sgns_default_params(dge_sgns_params *p) {
     if (!p) return;
+    memset(p, 0, sizeof(*p));
     p->dim = 20; p->window = 8; p->negative = 5; p->min_count = 2; p->epochs = 1;
     p->neg_table_size = 100000; p->exp_table_size = 1000; p->concurrency = 0; p->schedule = DGE_SCHEDULE_ITEMS;
-    p->sync_rounds = 0;
+    p->sync_rounds = 0; p->combine = DGE_COMBINE_DEFAULT; p->transport = DGE_TRANSPORT_AUTO; p->flags = 0;
     p->lr = 0.025f; p->min_lr = 1e-4f; p->seed = 1;
 }
 
 int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_corpora, const dge_sgns_params *p,
                    dge_model **out) {
     if (!ctx) return dge_fail(nullptr, DGE_E_INVALID, "dge_sgns_train: ctx is NULL");
-    if (!out) return dge_fail(ctx, DGE_E_INVALID, "dge_sgns_train: out is NULL");
-    *out = nullptr;
-    if (!corpora || !p || n_corpora < 1 || n_corpora > SGNS_MAX_CORPORA)
-        return dge_fail(ctx, DGE_E_INVALID, "dge_sgns_train: need 1..4 corpora and params");
-    if (p->negative > SGNS_MAX_NEG) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: negative must be <= 32");
-    if (p->dim < 1 || p->window < 1 || p->negative < 0 || p->epochs < 1 || p->neg_table_size < 1 ||
-        p->exp_table_size < 2 || p->min_count < 0 || p->concurrency < 0 || p->sync_rounds < 0 ||
-        (p->schedule != DGE_SCHEDULE_ITEMS && p->schedule != DGE_SCHEDULE_SENTENCE))
-        return dge_fail(ctx, DGE_E_INVALID, "dge_sgns_train: invalid hyper-parameter");
-    int32_t n_ids = corpora[0] ? corpora[0]->n_ids : 0;
-    int32_t Lmax = 0;
+    const bool multi = ctx->comm != nullptr && ctx->world > 1;
+    int local = DGE_OK;
+    if (!out) local = dge_fail(ctx, DGE_E_INVALID, "dge_sgns_train: out is NULL");
+    else *out = nullptr;
+    if (local == DGE_OK) local = sgns_check_params(ctx, corpora, n_corpora, p);
+    if (!multi && local != DGE_OK) return local;
+    cudaSetDevice(ctx->device);
+    int32_t n_ids = 0, Lmax = 0;
     int64_t n_sent = 0;
-    for (int i = 0; i < n_corpora; i++) {
-        if (!corpora[i]) return dge_fail(ctx, DGE_E_INVALID, "dge_sgns_train: NULL corpus");
-        if (corpora[i]->ctx != ctx) return dge_fail(ctx, DGE_E_INVALID, "dge_sgns_train: corpus belongs to another ctx");
-        if (corpora[i]->n_ids != n_ids) return dge_fail(ctx, DGE_E_INVALID, "dge_sgns_train: corpora have different id spaces");
-        Lmax = std::max(Lmax, corpora[i]->L);
-        n_sent += corpora[i]->n;
+    if (local == DGE_OK) {
+        n_ids = corpora[0]->n_ids;
+        for (int i = 0; i < n_corpora; i++) { Lmax = std::max(Lmax, corpora[i]->L); n_sent += corpora[i]->n; }
+    }
+    // ---- data-parallel: the call is COLLECTIVE.  Every rank learns every rank's status, parameters and shard size
+    // before anything else happens, so that a bad argument or a disagreement makes ALL ranks return the same error
+    // (instead of leaving the others hung in the next collective), and the global sentence order is known.
+    int64_t s_off = 0, n_global = n_sent, max_sent = n_sent;
+    if (multi) {
+        enum { NF = 20 };
+        unsigned long long mine[NF];
+        memset(mine, 0, sizeof(mine));
+        mine[0] = (unsigned long long)(-(long long)local);
+        if (local == DGE_OK) {
+            uint32_t lrb, mlrb;
+            memcpy(&lrb, &p->lr, 4); memcpy(&mlrb, &p->min_lr, 4);
+            const unsigned long long f[] = {(unsigned long long)n_ids, (unsigned long long)Lmax, (unsigned long long)p->dim,
+                (unsigned long long)p->window, (unsigned long long)p->negative, (unsigned long long)p->min_count,
+                (unsigned long long)p->epochs, (unsigned long long)p->neg_table_size, (unsigned long long)p->exp_table_size,
+                (unsigned long long)p->concurrency, (unsigned long long)p->schedule, (unsigned long long)p->sync_rounds,
+                (unsigned long long)p->combine, (unsigned long long)p->transport, (unsigned long long)p->flags, lrb, mlrb, p->seed};
+            for (int i = 0; i < 18; i++) mine[1 + i] = f[i];
+            mine[19] = (unsigned long long)n_sent;
+        }
+        std::vector<unsigned long long> all((size_t)ctx->world * NF);
+        int rc = dge_comm_allgather_u64(ctx, mine, NF, all.data());
+        if (rc != DGE_OK) return rc;
+        for (int r = 0; r < ctx->world; r++)
+            if (all[(size_t)r * NF] != 0) {
+                if (local != DGE_OK) return local;
+                return dge_fail(ctx, -(int)all[(size_t)r * NF], "dge_sgns_train: rank " + std::to_string(r) + " rejected its arguments; every rank returns");
+            }
+        static const char *names[] = {"n_ids", "walk length", "dim", "window", "negative", "min_count", "epochs", "neg_table_size",
+                                      "exp_table_size", "concurrency", "schedule", "sync_rounds", "combine", "transport", "flags", "lr", "min_lr", "seed"};
+        for (int r = 1; r < ctx->world; r++)
+            for (int i = 0; i < 18; i++)
+                if (all[(size_t)r * NF + 1 + i] != all[1 + i])
+                    return dge_fail(ctx, DGE_E_INVALID, std::string("dge_sgns_train: rank ") + std::to_string(r) + " disagrees with rank 0 on " + names[i] +
+                                                            " (data-parallel training needs identical parameters on every rank)");
+        n_global = 0; max_sent = 0;
+        for (int r = 0; r < ctx->world; r++) {
+            const int64_t ns = (int64_t)all[(size_t)r * NF + 19];
+            if (r < ctx->rank) s_off += ns;
+            n_global += ns;
+            max_sent = std::max(max_sent, ns);
+        }
     }
     const int32_t n4 = (p->dim + 3) / 4;        // float4 slots that carry data (zero-padded to whole slots)
     const int32_t stride = ((p->dim + 7) / 8) * 8; // row pitch in floats: rows start on 32-byte sector boundaries
-    const int dbg = getenv("DGE_SGNS_DEBUG") ? atoi(getenv("DGE_SGNS_DEBUG")) : 0; // 1: no reductions (timing experiments), 2 / 32: never / always use 4-lane groups for D <= 16 (A/B, tests), 8: item kernel on ONE warp, one item at a time (tests), 64 / 128: always / never use the target-parallel kernel for D <= 16, K <= 7 (A/B, tests), 256: experimental kernel C' (rows staged in shared memory by cp.async) where kernel C would run
+    const int dbg = (int)p->flags;              // DGE_SGNS_F_* (dge.h)
     sgns_variant var;
-    if (n4 > 128) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: dim must be <= 512");
-    if (p->neg_table_size >= (1 << 30)) return dge_fail(ctx, DGE_E_LIMIT, "dge_sgns_train: neg_table_size must be < 2^30");
-    DGE_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    sgns_scratch tmp(ctx);
 
     // ---- vocabulary: device histogram, host ranking (descending count, ties ascending id)
     dge_phase_timer t_vocab(ctx, "vocab");
     unsigned long long *d_cnt = nullptr;
-    DGE_CUDA(ctx, dge_malloc(ctx, &d_cnt, (size_t)n_ids + 2));
+    local = tmp.get(&d_cnt, (size_t)n_ids + 2) == cudaSuccess ? DGE_OK : dge_fail(ctx, DGE_E_CUDA, "dge_sgns_train: cudaMalloc of the histogram failed");
+    if (multi) local = dge_comm_agree(ctx, local, "dge_sgns_train (histogram)");
+    if (local != DGE_OK) return local;
     cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * ((size_t)n_ids + 2), st);
     for (int i = 0; i < n_corpora; i++) {
         int64_t total = corpora[i]->n * (int64_t)corpora[i]->L;
@@ -1456,24 +1528,17 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         }
     }
     // multi-GPU: every rank holds a shard of the corpus; the vocabulary is built from the global counts so that all
-    // ranks index the same words identically.  Slot n_ids carries max(local sentences) (rounds must agree).
-    const bool multi = ctx->comm != nullptr && ctx->world > 1;
-    int64_t max_sent = n_sent;
+    // ranks index the same words identically
     if (multi) {
         int rc = dge_comm_allreduce_sum_u64(ctx, d_cnt, (size_t)n_ids);
-        unsigned long long h_ns = (unsigned long long)n_sent;
-        if (rc == DGE_OK) {
-            cudaMemcpyAsync(d_cnt + n_ids, &h_ns, sizeof(h_ns), cudaMemcpyHostToDevice, st);
-            rc = dge_comm_allreduce_max_u64(ctx, d_cnt + n_ids, 1);
-        }
-        if (rc != DGE_OK) { dge_free(ctx, d_cnt); return rc; }
+        if (rc != DGE_OK) return rc;
     }
     std::vector<unsigned long long> cnt((size_t)n_ids + 2);
     cudaError_t ce = cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(unsigned long long) * ((size_t)n_ids + 1), cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-    dge_free(ctx, d_cnt);
-    if (ce != cudaSuccess) return dge_fail(ctx, DGE_E_CUDA, std::string("dge_sgns_train: histogram: ") + cudaGetErrorString(ce));
-    if (multi) max_sent = (int64_t)cnt[n_ids];
+    local = ce == cudaSuccess ? DGE_OK : dge_fail(ctx, DGE_E_CUDA, std::string("dge_sgns_train: histogram: ") + cudaGetErrorString(ce));
+    if (multi) local = dge_comm_agree(ctx, local, "dge_sgns_train (histogram read-back)");
+    if (local != DGE_OK) return local;
     std::vector<int32_t> order;
     order.reserve(n_ids);
     for (int32_t i = 0; i < n_ids; i++)
@@ -1509,21 +1574,21 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
 
     dge_model *m = new dge_model();
     m->ctx = ctx; m->V = V; m->dim = p->dim; m->stride = stride;
-    int32_t *d_word_of_id = nullptr, *d_table = nullptr;
+    int32_t *d_word_of_id = nullptr, *d_table = nullptr, *d_wtok = nullptr;
     float *d_exp = nullptr;
     unsigned long long *d_pairs = nullptr;
-    auto cleanup = [&]() { dge_free(ctx, d_word_of_id); dge_free(ctx, d_table); dge_free(ctx, d_exp); dge_free(ctx, d_pairs); };
-    auto fail = [&](const std::string &msg) {
-        cleanup();
-        model_release(m);
-        return dge_fail(ctx, DGE_E_CUDA, msg);
-    };
-    size_t nel = (size_t)(V ? V : 1) * (size_t)stride;
-    if (dge_malloc(ctx, &m->syn0, nel) != cudaSuccess || dge_malloc(ctx, &m->syn1neg, nel) != cudaSuccess ||
-        dge_malloc(ctx, &m->id_of_word, (size_t)V) != cudaSuccess || dge_malloc(ctx, &d_word_of_id, (size_t)n_ids) != cudaSuccess ||
-        dge_malloc(ctx, &d_table, (size_t)p->neg_table_size) != cudaSuccess ||
-        dge_malloc(ctx, &d_exp, (size_t)p->exp_table_size) != cudaSuccess || dge_malloc(ctx, &d_pairs, 2) != cudaSuccess)
-        return fail("dge_sgns_train: cudaMalloc failed");
+    const size_t nel = (size_t)(V ? V : 1) * (size_t)stride;
+    const bool train = V > 0 && (n_sent > 0 || multi);
+    // the replicas of a data-parallel run come from cudaMalloc so that the other ranks can map them (cudaIpc over NVLink)
+    m->plain_alloc = multi;
+    bool ok = (multi ? (cudaMalloc((void **)&m->syn0, nel * sizeof(float)) == cudaSuccess && cudaMalloc((void **)&m->syn1neg, nel * sizeof(float)) == cudaSuccess)
+                     : (dge_malloc(ctx, &m->syn0, nel) == cudaSuccess && dge_malloc(ctx, &m->syn1neg, nel) == cudaSuccess));
+    ok = ok && dge_malloc(ctx, &m->id_of_word, (size_t)V) == cudaSuccess && tmp.get(&d_word_of_id, (size_t)n_ids) == cudaSuccess &&
+         tmp.get(&d_table, (size_t)p->neg_table_size) == cudaSuccess && tmp.get(&d_exp, (size_t)p->exp_table_size) == cudaSuccess &&
+         tmp.get(&d_pairs, 2) == cudaSuccess && (!train || tmp.get(&d_wtok, (size_t)n_sent * (size_t)Lmax) == cudaSuccess);
+    local = ok ? DGE_OK : dge_fail(ctx, DGE_E_CUDA, std::string("dge_sgns_train: cudaMalloc failed (") + cudaGetErrorString(cudaGetLastError()) + ")");
+    if (multi) local = dge_comm_agree(ctx, local, "dge_sgns_train (tables)");
+    if (local != DGE_OK) { model_release(m); return local; }
     cudaMemsetAsync(m->syn0, 0, nel * sizeof(float), st);
     cudaMemsetAsync(m->syn1neg, 0, nel * sizeof(float), st);
     cudaMemsetAsync(d_pairs, 0, 2 * sizeof(unsigned long long), st);
@@ -1536,12 +1601,11 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         k_init_syn0<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(m->syn0, V, p->dim, stride, p->seed);
         ctx->launches++;
     }
+    ctx->phase_ms["sgns_rounds"] = 0.f; ctx->phase_ms["sgns_sync"] = 0.f; ctx->phase_ms["sgns_transport"] = 0.f;
 
-    int32_t *d_wtok = nullptr;
-    if (V > 0 && (n_sent > 0 || multi)) {
+    if (train) {
         // ---- compacted corpus in vocabulary indices (position-major, all corpora concatenated)
         dge_phase_timer t_prep(ctx, "compact");
-        if (dge_malloc(ctx, &d_wtok, (size_t)n_sent * (size_t)Lmax) != cudaSuccess) return fail("dge_sgns_train: cudaMalloc corpus failed");
         int64_t first = 0;
         for (int i = 0; i < n_corpora; i++) {
             if (corpora[i]->n > 0) {
@@ -1555,7 +1619,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
 
         sgns_args a;
         memset(&a, 0, sizeof(a));
-        a.wtok = d_wtok; a.n_sent = n_sent;
+        a.wtok = d_wtok; a.n_sent = n_sent; a.s_off = s_off; a.n_global = std::max<int64_t>(1, n_global);
         a.neg_table = d_table; a.exp_table = d_exp;
         a.syn0 = m->syn0; a.syn1neg = m->syn1neg;
         a.V = V; a.dim = p->dim; a.stride = stride; a.n4 = n4; a.window = p->window; a.negative = p->negative; a.epochs = p->epochs;
@@ -1575,7 +1639,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             const bool narrow = (dbg & 32) || (!(dbg & 2) && allowed >= (int64_t)ctx->sm_count * 4 * 32);
             // fewer pairs in flight than the 8-lane kernel needs to fill the GPU (5 blocks x 16 groups per SM): latency-bound
             const bool tp = (dbg & 64) || (!(dbg & (128 | 32)) && allowed < (int64_t)ctx->sm_count * 5 * 16);
-            if (!pick_variant(n4, p->negative, narrow, tp, (dbg & 256) != 0, &var)) { dge_free(ctx, d_wtok); return fail("dge_sgns_train: no kernel variant"); }
+            pick_variant(n4, p->negative, narrow, tp, (dbg & 256) != 0, (dbg & 512) != 0, (dbg >> 12) & 15, &var); // n4 <= 128 was checked
         }
         sgns_kernel_t fn = sequential ? var.seq : var.items;
         const int G = sequential ? var.G_seq : var.G_items;
@@ -1597,7 +1661,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
         if (per_sm < 1) per_sm = 1;
         const int64_t full_groups = (int64_t)ctx->sm_count * per_sm * gpb;
-        const int64_t units = sequential ? n_sent : n_sent * (int64_t)Lmax;
+        const int64_t units = sequential ? std::max<int64_t>(1, n_sent) : std::max<int64_t>(1, n_sent * (int64_t)Lmax);
         int64_t want;
         if (p->concurrency > 0) want = sequential ? (int64_t)p->concurrency : (int64_t)p->concurrency * Lmax;
         else if (sequential) want = full_groups;
@@ -1611,35 +1675,23 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         if (!sequential && (dbg & 8)) a.n_groups = 1; // the single warp advances one item at a time
         ctx->phase_ms["sgns_groups"] = (float)a.n_groups;
         ctx->phase_ms["sgns_kernel"] = (float)(sequential ? 0 : var.items_code);
-        // ---- launches.  Single GPU: one launch over all epochs and sentences.  Data-parallel (ctx has a communicator,
-        // or sync_rounds > 0): each epoch is cut into `rounds` slices of sentences; after every slice the ranks
-        // exchange their embedding deltas (cur - base) with one NCCL all-reduce per table over NVLink and all continue from
-        // base + combined delta.  Combine rule: per ROW, the sum of the deltas divided by the number of ranks that
-        // touched the row -- a row only one rank saw gets that rank's full update, a hub row every rank saw gets the
-        // average.  The plain sum ("all updates applied") is unstable: ranks that each saturate a hot row overshoot by
-        // a factor of world; emulated with the oracle it explodes at world = 8 (|syn0| ~ 1e8) and on 2 GPUs it fell
-        // to a kNN agreement of 0.24 / 0.10 / 0.02 at 6 / 24 / 96 rounds (profiles/r1s20_dp_diagnose.json), while plain
-        // parameter averaging divides the learning rate of every rare row by the world size.
+        // ---- launches.  Single GPU: one launch over all epochs and sentences.  Data-parallel (the ctx has a
+        // communicator; or sync_rounds > 0, where the exchange is the identity): each epoch is cut into `rounds` slices
+        // of the local sentences; after every slice the replicas are recombined from the per-rank deltas
+        // (comm.cu dge_dp_exchange: one peer-memory kernel over NVLink, or NCCL all-reduces; rule p->combine).
         int rounds = 1;
         if (multi || p->sync_rounds > 0) {
-            rounds = p->sync_rounds > 0 ? p->sync_rounds : (int)std::max<int64_t>(4, (max_sent + (1 << 20) - 1) >> 20);
+            rounds = p->sync_rounds > 0 ? p->sync_rounds : (int)std::max<int64_t>(8, (max_sent + (1 << 18) - 1) >> 18);
             rounds = (int)std::min<int64_t>(rounds, std::max<int64_t>(1, max_sent));
         }
-        float *base0 = nullptr, *base1 = nullptr, *touched = nullptr;
-        // how the per-rank deltas are combined (A/B and the emulation in oracle/sgns_oracle.c ora_sgns_train_dp)
-        const int combine = getenv("DGE_SGNS_COMBINE") ? atoi(getenv("DGE_SGNS_COMBINE")) : DGE_COMBINE_CONTRIBUTORS;
-        if (rounds > 1 || multi) {
-            if (dge_malloc(ctx, &base0, nel) != cudaSuccess || dge_malloc(ctx, &base1, nel) != cudaSuccess ||
-                dge_malloc(ctx, &touched, 2 * (size_t)V) != cudaSuccess) {
-                dge_free(ctx, base0); dge_free(ctx, base1); dge_free(ctx, d_wtok);
-                return fail("dge_sgns_train: cudaMalloc of the delta base failed");
-            }
-            cudaMemcpyAsync(base0, m->syn0, nel * sizeof(float), cudaMemcpyDeviceToDevice, st);
-            cudaMemcpyAsync(base1, m->syn1neg, nel * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        dge_dp *dp = nullptr;
+        if (multi) {
+            const int rc = dge_dp_begin(ctx, m->syn0, m->syn1neg, V, stride, n4, p->combine == DGE_COMBINE_DEFAULT ? DGE_COMBINE_ALIGNED : p->combine,
+                                        p->transport, &dp);
+            if (rc != DGE_OK) { model_release(m); return rc; }   // collective: every rank takes this way out
         }
         ctx->phase_ms["sgns_rounds"] = (float)rounds;
-        float sync_ms = 0.f;
-        int comm_rc = DGE_OK;
+        int rc = DGE_OK, any_error = 0;
         dge_phase_timer t_sgns(ctx, "sgns");
         smem = smem_for(threads);
         if (rounds == 1 && !multi) {
@@ -1647,50 +1699,40 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             fn<<<blocks, threads, smem, st>>>(a);
             ctx->launches++;
         } else {
-            cudaEvent_t e0, e1;
-            cudaEventCreate(&e0); cudaEventCreate(&e1);
-            const int grid_e = ctx->sm_count * 8;
-            for (int ep = 0; ep < p->epochs && comm_rc == DGE_OK; ep++) {
-                for (int r = 0; r < rounds && comm_rc == DGE_OK; r++) {
+            for (int ep = 0; ep < p->epochs && rc == DGE_OK && !any_error; ep++) {
+                for (int r = 0; r < rounds && rc == DGE_OK && !any_error; r++) {
                     a.ep_lo = ep; a.ep_hi = ep + 1;
                     a.s_lo = n_sent * r / rounds; a.s_hi = n_sent * (r + 1) / rounds;
+                    int launch_err = 0;
                     if (a.s_hi > a.s_lo) {
                         fn<<<blocks, threads, smem, st>>>(a);
                         ctx->launches++;
+                        launch_err = cudaGetLastError() != cudaSuccess;
                     }
-                    cudaEventRecord(e0, st);
-                    cudaMemsetAsync(touched, 0, 2 * (size_t)V * sizeof(float), st);
-                    k_delta_begin<<<grid_e, 256, 0, st>>>(m->syn0, base0, m->syn1neg, base1, nel, stride, V, touched);
-                    comm_rc = dge_comm_allreduce_sum_f32(ctx, m->syn0, nel);
-                    if (comm_rc == DGE_OK) comm_rc = dge_comm_allreduce_sum_f32(ctx, m->syn1neg, nel);
-                    if (comm_rc == DGE_OK) comm_rc = dge_comm_allreduce_sum_f32(ctx, touched, 2 * (size_t)V);
-                    k_delta_end<<<grid_e, 256, 0, st>>>(m->syn0, base0, m->syn1neg, base1, nel, stride, V, touched, combine, ctx->world);
-                    ctx->launches += 2;
-                    cudaEventRecord(e1, st);
-                    cudaEventSynchronize(e1);
-                    float ms = 0.f;
-                    cudaEventElapsedTime(&ms, e0, e1);
-                    sync_ms += ms;
+                    // every exchange agrees on the error status (a rank in trouble raises it, all ranks stop together);
+                    // the host waits for it every round: the rounds are tens of milliseconds long
+                    if (dp) rc = dge_dp_exchange(dp, launch_err, true, &any_error);
+                    else if (launch_err) any_error = 1;
                 }
             }
-            cudaEventDestroy(e0); cudaEventDestroy(e1);
         }
         t_sgns.stop();
-        ctx->phase_ms["sgns_sync"] = sync_ms;
-        dge_free(ctx, base0); dge_free(ctx, base1); dge_free(ctx, touched);
-        if (comm_rc != DGE_OK) { dge_free(ctx, d_wtok); cleanup(); model_release(m); return comm_rc; }
+        if (dp) { ctx->phase_ms["sgns_sync"] = dge_dp_ms(dp); dge_dp_end(dp); }
+        if (rc != DGE_OK) { model_release(m); return rc; }
         ce = cudaGetLastError();
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-        if (ce != cudaSuccess) { dge_free(ctx, d_wtok); return fail(std::string("dge_sgns_train: kernel: ") + cudaGetErrorString(ce)); }
+        local = (ce != cudaSuccess || any_error)
+                    ? dge_fail(ctx, DGE_E_CUDA, std::string("dge_sgns_train: kernel: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "a rank reported a launch failure"))
+                    : DGE_OK;
+        if (multi) local = dge_comm_agree(ctx, local, "dge_sgns_train (training)");
+        if (local != DGE_OK) { model_release(m); return local; }
         unsigned long long h_pairs[2] = {0, 0};
         cudaMemcpy(h_pairs, d_pairs, sizeof(h_pairs), cudaMemcpyDeviceToHost);
         m->pairs = (int64_t)h_pairs[0];
         m->words = (int64_t)h_pairs[1];
     }
-    dge_free(ctx, d_wtok);
     ce = cudaStreamSynchronize(st);
-    if (ce != cudaSuccess) return fail(std::string("dge_sgns_train: ") + cudaGetErrorString(ce));
-    cleanup();
+    if (ce != cudaSuccess) { model_release(m); return dge_fail(ctx, DGE_E_CUDA, std::string("dge_sgns_train: ") + cudaGetErrorString(ce)); }
     *out = m;
     return DGE_OK;
 }

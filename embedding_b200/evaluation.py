@@ -123,6 +123,33 @@ def knn_overlap(layers_a, layers_b, k=10):
     return float(np.mean(vals)) if vals else float("nan")
 
 
+def knn_table(layers, region_ids, n_layers, k=10):
+    """The k nearest neighbours (cosine, as pairwiseEstimator :169-196) of every region in every layer as one array
+    [n_layers, n_regions, k] of positions in `region_ids` (int16; -1 = the region has no row in that layer): a compact
+    fingerprint of an embedding's neighbourhood structure (committed for the oracle, tests/golden/)."""
+    pos = {int(r): i for i, r in enumerate(region_ids)}
+    out = np.full((n_layers, len(region_ids), k), -1, np.int16)
+    for h, (f, r) in layers.items():
+        m = len(r)
+        if m <= k or not (0 <= h < n_layers):
+            continue
+        idx = np.array([pos[int(x)] for x in r])
+        D = cosine_distance_matrix(f)
+        D[np.arange(m), np.arange(m)] = np.inf
+        nb = np.argsort(D, axis=1, kind="stable")[:, :k]
+        out[h, idx] = idx[nb]
+    return out
+
+
+def knn_table_overlap(a, b):
+    """Mean |kNN_a(r) & kNN_b(r)| / k over the (layer, region) rows present in both tables."""
+    both = (a[:, :, 0] >= 0) & (b[:, :, 0] >= 0)
+    A, B = a[both], b[both]
+    k = A.shape[1]
+    hits = (A[:, :, None] == B[:, None, :]).any(-1).sum(-1)
+    return float(hits.mean() / k) if len(A) else float("nan")
+
+
 def ca_classification_accuracy(layers, labels, region_ids, cv=10):
     """binaryClassification_CA.py:33-58 with the per-layer embeddings as features: mean 10-fold accuracy of a
     decision tree and an SVC over layers and label sets (labels: {name: [77 binary]})."""

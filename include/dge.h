@@ -70,9 +70,13 @@ int dge_timer_stop(dge_ctx *ctx, float *ms);
 /* ------------------------------------------------------------------ multi-GPU (one process per GPU)
  * The reference is single-device (only a commented-out hint, DeepWalk.java:43).  Walks shard by walk id with no
  * collective (first_walk_id of dge_walk).  Stage 2 becomes data-parallel when the ctx carries a communicator:
- * every rank trains on its own corpora and dge_sgns_train exchanges the embedding deltas with NCCL all-reduces over
- * NVLink (sync_rounds per epoch); per row the summed delta is divided by the number of ranks that touched the row.  The host moves the opaque id from rank 0 to the other ranks
- * by any means it has (a file, a socket, MPI, torch.distributed). */
+ * every rank trains on its own corpora (global sentence order = rank 0's sentences, then rank 1's, ...: the ranks
+ * together enumerate exactly the pairs and negatives of a single-GPU run over the whole corpus) and dge_sgns_train
+ * exchanges the embedding deltas sync_rounds times per epoch -- one kernel over NVLink peer memory (the replicas of all
+ * ranks are mapped with cudaIpc), or NCCL all-reduces where peer mapping is unavailable; the per-row combine rule is
+ * dge_sgns_params.combine.  dge_sgns_train is then COLLECTIVE: every rank must call it with the same parameters
+ * (checked; a failure on one rank makes every rank return an error).  The host moves the opaque id from rank 0 to
+ * the other ranks by any means it has (a file, a socket, MPI, torch.distributed). */
 #define DGE_COMM_ID_BYTES 128
 int dge_comm_unique_id(void *id, size_t bytes);
 int dge_comm_init(dge_ctx *ctx, int rank, int world, const void *id, size_t bytes);
@@ -200,6 +204,27 @@ void dge_corpus_free(dge_corpus *c);
  * (DL4J 0.7.2, external) and WordVectorSerializer.writeWordVectors :82. */
 enum { DGE_SCHEDULE_ITEMS = 0,     /* work item = (sentence, centre); row updates are 128-bit L2 reductions */
        DGE_SCHEDULE_SENTENCE = 1 }; /* work item = sentence; plain atomic-free row stores (classic Hogwild) */
+/* How the deltas d_r = (replica of rank r) - (common base) of one embedding row are combined at an exchange:
+ * base += sum_r d_r / div.  SUM applies every update but overshoots when several ranks saturate the same row (it
+ * diverges at world = 8); MEAN is parameter averaging (a row only one rank saw learns world times slower);
+ * CONTRIBUTORS divides by the number of ranks whose delta is non-zero; SQRT by its square root; ALIGNED (default) by
+ * max(1, |sum_r d_r|^2 / sum_r |d_r|^2), which is 1 for orthogonal deltas (independent information: summed) and the
+ * number of contributors for parallel ones (every rank made the same move: averaged).  DESIGN.md 3.4. */
+enum { DGE_COMBINE_DEFAULT = 0, DGE_COMBINE_MEAN = 1, DGE_COMBINE_CONTRIBUTORS = 2, DGE_COMBINE_SQRT = 3,
+       DGE_COMBINE_ALIGNED = 4, DGE_COMBINE_SUM = 5 };
+enum { DGE_TRANSPORT_AUTO = 0, DGE_TRANSPORT_PEER = 1, DGE_TRANSPORT_NCCL = 2 };
+/* dge_sgns_params.flags (tests, A/B measurements; every one of them changes speed or schedule, none the arithmetic of
+ * an update, except NO_UPDATES which trains nothing and PLAIN_STORES which may lose updates) */
+enum { DGE_SGNS_F_NO_UPDATES = 1,     /* timing experiment: compute everything, send no row update */
+       DGE_SGNS_F_NO_NARROW = 2,      /* never use the 4-lane-group kernel for D <= 16 */
+       DGE_SGNS_F_ONE_WARP = 8,       /* item kernel on ONE warp, one item at a time, corpus order (arithmetic check) */
+       DGE_SGNS_F_NARROW = 32,        /* always use the 4-lane-group kernel for D <= 16 */
+       DGE_SGNS_F_TARGET_PARALLEL = 64,    /* always use the target-parallel kernel for D <= 16, K <= 7 */
+       DGE_SGNS_F_NO_TARGET_PARALLEL = 128,
+       DGE_SGNS_F_STAGED_ROWS = 256,  /* item kernel with the rows of the next unit staged in shared memory (cp.async) */
+       DGE_SGNS_F_PLAIN_STORES = 512, /* atomic-free item kernel: plain 128-bit row stores instead of L2 reductions */
+       DGE_SGNS_F_BLOCKS_6 = 6 << 12, /* with STAGED_ROWS, rows of up to 8 slots: register allocation for 6 / 7 resident */
+       DGE_SGNS_F_BLOCKS_7 = 7 << 12  /* blocks per SM instead of 5 */ };
 typedef struct {
     int32_t dim;            /* layerSize(...)         DeepWalk.java:62-66,74 */
     int32_t window;         /* windowSize(numLayer)   :74 */
@@ -212,8 +237,14 @@ typedef struct {
                                the vocabulary size); 1 = one sentence at a time in the oracle's
                                exact order (parity tests); N = N sentences in flight */
     int32_t schedule;       /* DGE_SCHEDULE_ITEMS (default) or DGE_SCHEDULE_SENTENCE */
-    int32_t sync_rounds;    /* multi-GPU only: delta all-reduces per epoch; 0 = automatic (one per ~2^20 local
-                               sentences, at least 4).  Ignored without a communicator of world > 1. */
+    int32_t sync_rounds;    /* multi-GPU only: exchanges of the embedding deltas per epoch; 0 = automatic (one per
+                               ~2^18 local sentences, at least 8).  Without a communicator of world > 1 a value > 0
+                               still cuts the epoch into that many launches (same arithmetic, exchange = identity). */
+    int32_t combine;        /* multi-GPU only: DGE_COMBINE_* rule for the per-rank deltas of a row; 0 = default
+                               (DGE_COMBINE_ALIGNED).  Must agree on all ranks (checked). */
+    int32_t transport;      /* multi-GPU only: DGE_TRANSPORT_AUTO (peer-memory kernel over NVLink when the replicas can
+                               be mapped, else NCCL), _PEER (fail if they cannot), _NCCL */
+    uint32_t flags;         /* DGE_SGNS_F_*: kernel-selection / measurement hooks for tests and A/B runs; 0 in production */
     float lr;               /* 0.025 */
     float min_lr;           /* 1e-4 */
     uint64_t seed;

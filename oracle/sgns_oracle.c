@@ -187,6 +187,9 @@ typedef struct {
     int64_t pairs;
     int64_t s_lo, s_hi; /* sentences [s_lo, s_hi) of this call (s_hi == 0: all) */
     int32_t only_epoch;  /* >= 0: this epoch only (data-parallel emulation runs an epoch slice by slice) */
+    int64_t sent_offset; /* data-parallel shard: global index of local sentence 0 (RNG keys and the learning-rate */
+    int64_t n_total;     /* schedule use GLOBAL sentence indices, so the shards enumerate exactly the pairs and  */
+                         /* negatives of the single-process run over the whole corpus); 0 = n_sent              */
 } worker;
 
 static void *worker_run(void *arg) {
@@ -210,8 +213,8 @@ static void *worker_run(void *arg) {
                 int32_t wd = w->vocab->word_of_id[id];
                 if (wd >= 0) sent[n++] = wd;
             }
-            float alpha = ora_alpha(p, ep, s, w->n_sent);
-            const uint64_t S = ora_sentence_rng(p->seed, ep, s);
+            float alpha = ora_alpha(p, ep, s + w->sent_offset, w->n_total > 0 ? w->n_total : w->n_sent);
+            const uint64_t S = ora_sentence_rng(p->seed, ep, s + w->sent_offset);
             for (int32_t i = 0; i < n; i++) {
                 uint64_t r = ora_position_rng(S, i);
                 int32_t b = (int32_t)(uint32_t)r % win; /* ((int) nextRandom) % window, may be negative */
@@ -337,15 +340,36 @@ ora_model *ora_sgns_train(const int32_t *tokens, int64_t n_sent, int32_t L, int3
  * process, its only hint being "model averaging", DeepWalk.java:43).  `world` ranks own contiguous shards of the
  * sentences (embedding_b200/parallel.py walk_shard), share one vocabulary built from the whole corpus, and keep
  * replicas of syn0 / syn1neg.  Every epoch is cut into `rounds` slices; in a slice each rank trains sequentially on
- * its own sentences (local sentence indices for the RNG and the learning-rate schedule, as on the GPUs), then the
- * replicas are recombined from the per-rank deltas d_r = cur_r - base:
+ * its own sentences (GLOBAL sentence indices for the RNG and the learning-rate schedule, as on the GPUs: the shards
+ * together enumerate exactly the pairs and negatives of the sequential run), then the replicas are recombined from the
+ * per-rank deltas d_r = cur_r - base, per ROW:
  *   combine 0: base += sum_r d_r                      (all updates applied)
  *   combine 1: base += mean_r d_r                     (parameter averaging)
- *   combine 2: base += sum_r d_r / max(1, #ranks whose delta of that ROW is non-zero)   (average over contributors)
+ *   combine 2: base += sum_r d_r / max(1, #ranks whose delta of that row is non-zero)   (average over contributors)
+ *   combine 3: base += sum_r d_r / sqrt(max(1, #contributors))
+ *   combine 4: base += sum_r d_r / max(1, |sum_r d_r|^2 / sum_r |d_r|^2)                (alignment-weighted)
+ *              deltas that point the same way (every rank pushed the row towards the same optimum: adding them
+ *              overshoots) are averaged, deltas that are orthogonal (independent information) are summed; the
+ *              divisor lies in [1, #contributors].
+ * combine + 16 (DELAYED): the combined delta of slice t reaches the replicas one slice late, while they already
+ * trained slice t + 1 from their own state (the exchange overlapped with compute): replica_r += combined_t - d_r,t.
  */
+static float combine_div(int combine, int world, int touched, double sq_of_sum, double sum_of_sq) {
+    const float c = (float)(touched > 1 ? touched : 1);
+    switch (combine) {
+        case 1: return (float)world;
+        case 2: return c;
+        case 3: return sqrtf(c);
+        case 4: { if (!(sum_of_sq > 0.0)) return 1.0f; float a = (float)(sq_of_sum / sum_of_sq); return a > 1.0f ? a : 1.0f; }
+        default: return 1.0f;
+    }
+}
+
 ora_model *ora_sgns_train_dp(const int32_t *tokens, int64_t n_sent, int32_t L, int32_t n_ids,
                              const ora_sgns_params *p, int32_t world, int32_t rounds, int32_t combine,
                              int64_t *pairs_out) {
+    const int delayed = (combine & 16) != 0;
+    combine &= 15;
     ora_vocab *vocab = ora_vocab_build(tokens, n_sent * L, n_ids, p->min_count);
     int32_t V = vocab->V, D = p->dim;
     size_t n = (size_t)(V ? V : 1) * (size_t)D;
@@ -366,57 +390,109 @@ ora_model *ora_sgns_train_dp(const int32_t *tokens, int64_t n_sent, int32_t L, i
     }
     if (world < 1) world = 1;
     if (rounds < 1) rounds = 1;
+    /* per rank: the replica (cur) and its base = the replica minus the local progress not yet handed to an exchange */
     ora_model *rep = (ora_model *)calloc((size_t)world, sizeof(ora_model));
+    float **bas[2], **own[2], **pown[2];
+    for (int t = 0; t < 2; t++) {
+        bas[t] = (float **)calloc((size_t)world, sizeof(float *));
+        own[t] = (float **)calloc((size_t)world, sizeof(float *));
+        pown[t] = (float **)calloc((size_t)world, sizeof(float *));
+    }
     for (int r = 0; r < world; r++) {
         rep[r].V = V; rep[r].dim = D;
         rep[r].syn0 = (float *)malloc(sizeof(float) * n);
         rep[r].syn1neg = (float *)malloc(sizeof(float) * n);
+        memcpy(rep[r].syn0, m->syn0, sizeof(float) * n);
+        memcpy(rep[r].syn1neg, m->syn1neg, sizeof(float) * n);
+        for (int t = 0; t < 2; t++) {
+            bas[t][r] = (float *)malloc(sizeof(float) * n);
+            memcpy(bas[t][r], t == 0 ? m->syn0 : m->syn1neg, sizeof(float) * n);
+            own[t][r] = (float *)malloc(sizeof(float) * n);
+            pown[t][r] = (float *)calloc(n, sizeof(float));
+        }
     }
-    float *acc = (float *)malloc(sizeof(float) * n);
+    float *acc = (float *)malloc(sizeof(float) * n);      /* combined delta of the newest exchange */
+    float *pend[2] = {(float *)calloc(n, sizeof(float)), (float *)calloc(n, sizeof(float))}; /* delayed: in flight */
+    int have_pending = 0;
     int32_t *touched = (int32_t *)malloc(sizeof(int32_t) * (size_t)(V ? V : 1));
+    double *sumsq = (double *)malloc(sizeof(double) * (size_t)(V ? V : 1));
     int64_t pairs = 0;
     ora_sgns_params q = *p;
     q.use_hs = 0;
     for (int32_t ep = 0; ep < p->epochs; ep++) {
         for (int32_t rd = 0; rd < rounds; rd++) {
             for (int r = 0; r < world; r++) {
-                memcpy(rep[r].syn0, m->syn0, sizeof(float) * n);
-                memcpy(rep[r].syn1neg, m->syn1neg, sizeof(float) * n);
                 int64_t base = n_sent / world, rem = n_sent % world;
                 int64_t first = r * base + (r < rem ? r : rem), count = base + (r < rem ? 1 : 0);
                 worker w; memset(&w, 0, sizeof(w));
                 w.tokens = tokens + first * L; w.n_sent = count; w.L = L; w.p = &q; w.vocab = vocab;
                 w.table = table; w.exp_table = exp_table; w.hf = NULL; w.m = &rep[r];
                 w.tid = 0; w.nthreads = 1; w.count_only = 0; w.only_epoch = ep;
+                w.sent_offset = first; w.n_total = n_sent;
                 w.s_lo = count * rd / rounds; w.s_hi = count * (rd + 1) / rounds;
                 if (w.s_hi > w.s_lo) { worker_run(&w); pairs += w.pairs; }
             }
+            const int last = ep == p->epochs - 1 && rd == rounds - 1;
             for (int t = 0; t < 2; t++) {
-                float *base_t = t == 0 ? m->syn0 : m->syn1neg;
+                /* a delayed exchange lands now, one slice late: replica and base += combined - own */
+                if (have_pending) {
+                    for (int r = 0; r < world; r++) {
+                        float *cur = t == 0 ? rep[r].syn0 : rep[r].syn1neg;
+                        for (size_t i = 0; i < n; i++) { const float c = pend[t][i] - pown[t][r][i]; cur[i] += c; bas[t][r][i] += c; }
+                    }
+                }
+                /* snapshot: own = cur - base (the local progress of this slice); base = cur */
                 memset(acc, 0, sizeof(float) * n);
                 memset(touched, 0, sizeof(int32_t) * (size_t)(V ? V : 1));
+                memset(sumsq, 0, sizeof(double) * (size_t)(V ? V : 1));
                 for (int r = 0; r < world; r++) {
                     const float *cur = t == 0 ? rep[r].syn0 : rep[r].syn1neg;
                     for (int32_t v = 0; v < V; v++) {
                         int nz = 0;
+                        double sq = 0.0;
                         for (int32_t d = 0; d < D; d++) {
-                            float dl = cur[(size_t)v * D + d] - base_t[(size_t)v * D + d];
-                            acc[(size_t)v * D + d] += dl;
+                            const size_t i = (size_t)v * D + d;
+                            const float dl = cur[i] - bas[t][r][i];
+                            own[t][r][i] = dl;
+                            bas[t][r][i] = cur[i];
+                            acc[i] += dl;
+                            sq += (double)dl * (double)dl;
                             nz |= dl != 0.0f;
                         }
                         touched[v] += nz;
+                        sumsq[v] += sq;
                     }
                 }
                 for (int32_t v = 0; v < V; v++) {
-                    float div = combine == 1 ? (float)world : (combine == 2 ? (float)(touched[v] > 1 ? touched[v] : 1) : (combine == 3 ? sqrtf((float)(touched[v] > 1 ? touched[v] : 1)) : 1.0f));
-                    for (int32_t d = 0; d < D; d++) base_t[(size_t)v * D + d] += acc[(size_t)v * D + d] / div;
+                    double sq_of_sum = 0.0;
+                    for (int32_t d = 0; d < D; d++) sq_of_sum += (double)acc[(size_t)v * D + d] * (double)acc[(size_t)v * D + d];
+                    const float div = combine_div(combine, world, touched[v], sq_of_sum, sumsq[v]);
+                    for (int32_t d = 0; d < D; d++) acc[(size_t)v * D + d] /= div;
+                }
+                if (delayed && !last) { /* in flight during the next slice */
+                    memcpy(pend[t], acc, sizeof(float) * n);
+                    for (int r = 0; r < world; r++) memcpy(pown[t][r], own[t][r], sizeof(float) * n);
+                } else {
+                    for (int r = 0; r < world; r++) {
+                        float *cur = t == 0 ? rep[r].syn0 : rep[r].syn1neg;
+                        for (size_t i = 0; i < n; i++) { const float c = acc[i] - own[t][r][i]; cur[i] += c; bas[t][r][i] += c; }
+                    }
                 }
             }
+            have_pending = delayed && !last;
         }
     }
+    /* the replicas agree up to fp32 rounding of (cur += combined - own); rank 0's copy is the result (the GPUs broadcast it) */
+    memcpy(m->syn0, rep[0].syn0, sizeof(float) * n);
+    memcpy(m->syn1neg, rep[0].syn1neg, sizeof(float) * n);
     if (pairs_out) *pairs_out = pairs;
-    for (int r = 0; r < world; r++) { free(rep[r].syn0); free(rep[r].syn1neg); }
-    free(rep); free(acc); free(touched); free(table); free(exp_table);
+    for (int r = 0; r < world; r++) {
+        free(rep[r].syn0); free(rep[r].syn1neg);
+        for (int t = 0; t < 2; t++) { free(bas[t][r]); free(own[t][r]); free(pown[t][r]); }
+    }
+    for (int t = 0; t < 2; t++) { free(bas[t]); free(own[t]); free(pown[t]); }
+    free(rep); free(pend[0]); free(pend[1]);
+    free(acc); free(touched); free(sumsq); free(table); free(exp_table);
     ora_vocab_free(vocab);
     return m;
 }

@@ -4,7 +4,9 @@
 //   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o scripts/bin/red_microbench scripts/red_microbench.cu
 //   scripts/bin/red_microbench
 // Shapes: G lanes per row, `live` of them active, row pitch in bytes, V rows.  Every warp-level instruction
-// touches 32/G random rows.  mode 0 = red only, 1 = load only, 2 = load + red of the same row.
+// touches 32/G random rows.  mode 0 = red only, 1 = load only, 2 = load + red of the same row,
+// 3 = the row update staged in shared memory and sent as ONE TMA bulk reduction per row by one lane
+// (cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32: no per-lane LSU reduction at all), 4 = load + 3.
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -18,6 +20,10 @@ __device__ __forceinline__ float4 ld4(const float4 *p) {
     return r;
 }
 
+__device__ __forceinline__ void bulk_red(float *gptr, uint32_t smem_addr, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gptr), "r"(smem_addr), "r"(bytes) : "memory");
+}
+
 template <int G, int MODE>
 __global__ void __launch_bounds__(128) k(float *table, uint32_t V, uint32_t pitch, int live, int iters, float *sink) {
     const int lane = threadIdx.x % G;
@@ -25,18 +31,36 @@ __global__ void __launch_bounds__(128) k(float *table, uint32_t V, uint32_t pitc
     uint32_t s = gid * 2654435761u + 12345u;
     float acc = 0.f;
     char *base = reinterpret_cast<char *>(table) + (lane < live ? lane : 0) * 16;
+    __shared__ __align__(128) float4 stage[2][6][128]; // [double buffer][row of the unit][thread]: group g's row at [..][g * G]
+    const uint32_t my_stage = (uint32_t)__cvta_generic_to_shared(&stage[0][0][threadIdx.x]);
     for (int it = 0; it < iters; it++) {
+        if (MODE >= 3) { // the stage written two units ago must have been read by the TMA engine
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+        }
 #pragma unroll
         for (int u = 0; u < 6; u++) { // 6 rows per "pair", like K+1 targets
             s = s * 1664525u + 1013904223u;
             uint32_t row = (uint32_t)(((uint64_t)(s >> 4) * V) >> 28);
             float4 *p = reinterpret_cast<float4 *>(base + (uint64_t)row * pitch);
-            if (lane < live) {
-                if (MODE >= 1) { float4 v = ld4(p); acc += v.x + v.y + v.z + v.w; }
-                if (MODE != 1) red4(p, 1e-9f);
+            if (MODE < 3) {
+                if (lane < live) {
+                    if (MODE >= 1) { float4 v = ld4(p); acc += v.x + v.y + v.z + v.w; }
+                    if (MODE != 1) red4(p, 1e-9f);
+                }
+            } else {
+                float4 v = make_float4(1e-9f, 1e-9f, 1e-9f, 1e-9f);
+                if (lane < live && MODE == 4) { float4 x = ld4(p); acc += x.x + x.y + x.z + x.w; }
+                const uint32_t dst = my_stage + (uint32_t)(((it & 1) * 6 + u) * 128 * 16);
+                if (lane < live) asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) bulk_red(reinterpret_cast<float *>(p), dst, (uint32_t)live * 16u);
             }
         }
+        if (MODE >= 3 && lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
+    if (MODE >= 3 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (acc == 123.456f) *sink = acc;
 }
 
@@ -55,7 +79,7 @@ static void run(const char *name, float *table, uint32_t V, uint32_t pitch, int 
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     double rows = (double)blocks * 128 / G * iters * 6;
-    double lane_ops = rows * live * (MODE == 2 ? 2 : 1);
+    double lane_ops = rows * live * (MODE == 2 || MODE == 4 ? 2 : 1);
     printf("%-34s G=%2d live=%2d pitch=%4u V=%8u mode=%d : %8.1f M rows/s  %8.1f G lane-ops/s  %7.1f GB/s  (%.2f ms)\n", name, G, live, pitch,
            V, MODE, rows / ms / 1e3, lane_ops / ms / 1e6, lane_ops * 16 / ms / 1e6, ms);
     cudaFree(sink);
@@ -76,6 +100,8 @@ int main() {
     run<8, 0>("tract24 rows: red", small, Vs, 96, 5, sms);
     run<8, 1>("tract24 rows: load", small, Vs, 96, 5, sms);
     run<8, 2>("tract24 rows: load+red", small, Vs, 96, 5, sms);
+    run<8, 3>("tract24 rows: TMA bulk red", small, Vs, 96, 5, sms);
+    run<8, 4>("tract24 rows: load+bulk red", small, Vs, 96, 5, sms);
     run<8, 0>("128 B rows, 8/8 live: red", small, Vs, 128, 8, sms);
     run<8, 0>("32 B rows (CA D=8), 2/8 live: red", small, Vs, 32, 2, sms);
     run<4, 0>("64 B rows, G=4 4/4 live: red", small, Vs, 64, 4, sms);
@@ -83,7 +109,11 @@ int main() {
     run<32, 0>("512 B rows, uniform 2.4M: red", big, Vb, 512, 32, sms);
     run<32, 1>("512 B rows, uniform 2.4M: load", big, Vb, 512, 32, sms);
     run<32, 2>("512 B rows, uniform 2.4M: load+red", big, Vb, 512, 32, sms);
+    run<32, 3>("512 B rows, uniform 2.4M: bulk red", big, Vb, 512, 32, sms);
+    run<32, 4>("512 B rows, uniform 2.4M: ld+bulk", big, Vb, 512, 32, sms);
     run<32, 0>("512 B rows, 100K hot rows: red", big, 100000, 512, 32, sms);
+    run<32, 3>("512 B rows, 100K hot: bulk red", big, 100000, 512, 32, sms);
+    run<32, 4>("512 B rows, 100K hot: ld+bulk red", big, 100000, 512, 32, sms);
     run<32, 2>("512 B rows, 100K hot rows: ld+red", big, 100000, 512, 32, sms);
     return 0;
 }

@@ -80,7 +80,6 @@ def test_deepwalk_entry_points_write_reference_formats(dge_lib, ctx, tmp_path, t
     assert np.allclose(f0[0], syn0[0], rtol=1e-6) and r0[0] == lab_region[idw[0]]
 
 
-@pytest.mark.skipif(not os.environ.get("DGE_TEST_EXPERIMENTAL"), reason="DeepWalk.main mirror: written after the round's GPU budget ended, first run next round")
 def test_deepwalk_main_runs_the_whole_path(dge_lib, ctx, tmp_path, tract_setup):
     """DeepWalk.main [regionLevel] [spatialGF] [Year] (DeepWalk.java:120-140) through the host mirror at 0.2 % of the
     reference's corpus sizes: both .seq files and the .vec file appear under ../miscs/<Year>/ with the reference's names."""

@@ -92,10 +92,10 @@ def test_parallel_schedule_learns_the_same_structure(dge_lib, oracle, ctx, dim):
 
 
 @pytest.mark.parametrize("dim,negative", [(2, 5), (4, 7), (8, 5), (8, 10), (12, 3), (16, 5), (20, 5), (20, 12), (32, 5), (64, 5), (100, 7), (128, 5), (128, 20)])
-def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negative, monkeypatch):
+def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negative):
     """The throughput kernel (work item = (sentence, centre), 128-bit L2 reductions, software pipeline) enumerates
     the oracle's pairs and negatives and applies the same update arithmetic; only the interleaving differs.
-    Run on ONE warp, one item at a time (DGE_SGNS_DEBUG=8: items strictly in corpus order) the interleaving is
+    Run on ONE warp, one item at a time (flags = DGE_SGNS_F_ONE_WARP: items strictly in corpus order) the interleaving is
     the oracle's up to the prefetch of a pair's rows, so the learned change of both tables must agree with the
     sequential oracle to ~1 %: any slip in the dot products, the sigmoid table, the negative draws or the row
     addressing is an O(1) error here.  With sentences in flight the deviation grows like sqrt(stale fraction)."""
@@ -118,18 +118,18 @@ def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negati
         assert m.pairs == ref["pairs"] and np.array_equal(ids, ref["id_of_word"])
         return np.linalg.norm(syn0 - ref["syn0"]) / learned0, np.linalg.norm(syn1 - ref["syn1neg"]) / learned1
 
-    flag_sets = ["8"]
+    L = dge_lib
+    flag_sets = [L.F_ONE_WARP]
     if dim <= 16:
-        flag_sets.append("40")                      # 8 | 32: the 4-lane-group kernel for D <= 16
+        flag_sets.append(L.F_ONE_WARP | L.F_NARROW)                  # the 4-lane-group kernel for D <= 16
         if negative <= 7:
-            flag_sets.append("72")                  # 8 | 64: the target-parallel kernel (D <= 16, K <= 7)
-    if os.environ.get("DGE_TEST_EXPERIMENTAL") and dim <= 128:
-        flag_sets.append("264")                     # 8 | 256: kernel C' (rows staged in shared memory by cp.async), not yet measured
+            flag_sets.append(L.F_ONE_WARP | L.F_TARGET_PARALLEL)     # the target-parallel kernel (D <= 16, K <= 7)
+    if dim <= 128:
+        flag_sets.append(L.F_ONE_WARP | L.F_STAGED_ROWS)             # kernel C': rows staged in shared memory by cp.async
+        flag_sets.append(L.F_ONE_WARP | L.F_PLAIN_STORES)            # atomic-free build: one item at a time loses no update
     for flags in flag_sets:
-        monkeypatch.setenv("DGE_SGNS_DEBUG", flags)
-        e0, e1 = rel_err()
+        e0, e1 = rel_err(flags=flags)
         assert e0 < 0.02 and e1 < 0.02, (flags, e0, e1)
-    monkeypatch.delenv("DGE_SGNS_DEBUG")
     e0, e1 = rel_err(concurrency=2)                 # two sentences in flight
     assert e0 < 0.35 and e1 < 0.35, (e0, e1)
     e0, e1 = rel_err()                              # automatic full-GPU schedule

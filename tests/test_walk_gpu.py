@@ -103,7 +103,6 @@ def test_every_step_is_an_edge_and_layers_advance(dge_lib, ctx):
     assert np.isin(pair.ravel(), key).all()
 
 
-@pytest.mark.skipif(not os.environ.get("DGE_TEST_EXPERIMENTAL"), reason="16-bit token download: written after the round's GPU budget ended, first run next round")
 def test_tokens_u16_equal_tokens(dge_lib, ctx):
     g = small_graph(seed=12)
     G = dge_lib.Graph(ctx, g["n_vertices"], g["src"], g["dst"], g["w"], g["sources"])
