@@ -80,5 +80,27 @@ def build(force=False, verbose=False):
     return LIB
 
 
+# Stand-alone CUDA micro-benchmarks (the measured ceilings bench.py and DESIGN.md quote): scripts/*.cu -> scripts/bin/
+MICROBENCH = ["red_microbench", "walk_microbench"]
+
+
+def build_microbenchmarks(force=False):
+    root = os.path.dirname(HERE)
+    out_dir = os.path.join(root, "scripts", "bin")
+    os.makedirs(out_dir, exist_ok=True)
+    outs = []
+    for name in MICROBENCH:
+        src, out = os.path.join(root, "scripts", name + ".cu"), os.path.join(out_dir, name)
+        if not os.path.exists(src):
+            continue
+        if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+            r = subprocess.run([_nvcc()] + ARCH + ["-O3", "-lineinfo", "-std=c++17", "-o", out, src], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+        outs.append(out)
+    return outs
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_microbenchmarks(force="--force" in sys.argv))

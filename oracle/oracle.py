@@ -95,6 +95,8 @@ def lib():
     L.ora_sgns_train.argtypes = [pi32, i64, i32, i32, pp, pi64]
     L.ora_sgns_train_dp.restype = vp
     L.ora_sgns_train_dp.argtypes = [pi32, i64, i32, i32, pp, i32, i32, i32, pi64]
+    L.ora_sgns_train_dp_tiered.restype = vp
+    L.ora_sgns_train_dp_tiered.argtypes = [pi32, i64, i32, i32, pp, i32, i32, i32, i32, i32, pi64]
     L.ora_model_free.argtypes = [vp]
     L.ora_model_vocab_size.argtypes = [vp]
     L.ora_model_get.argtypes = [vp, pf32, pf32, pi32]
@@ -281,16 +283,17 @@ def sgns_train(tokens, n_ids, params):
     return dict(syn0=syn0, syn1neg=syn1, id_of_word=ids, pairs=pairs.value)
 
 
-COMBINE_SUM, COMBINE_MEAN, COMBINE_CONTRIBUTORS = 0, 1, 2
+COMBINE_SUM, COMBINE_MEAN, COMBINE_CONTRIBUTORS, COMBINE_SQRT, COMBINE_ALIGNED, COMBINE_DELAYED = 0, 1, 2, 3, 4, 16
 
 
-def sgns_train_dp(tokens, n_ids, params, world, rounds, combine):
-    """Data-parallel emulation of stage 2 (ora_sgns_train_dp): contiguous sentence shards, per-round delta exchange."""
+def sgns_train_dp(tokens, n_ids, params, world, rounds, combine, full_every=1, hot_rows=0):
+    """Data-parallel emulation of stage 2 (ora_sgns_train_dp[_tiered]): contiguous sentence shards, per-round delta
+    exchange; with full_every > 1 only the hot prefix rows [0, hot_rows) take part in most exchanges."""
     tokens = np.ascontiguousarray(tokens, np.int32)
     n_sent, L = tokens.shape
     pairs = C.c_int64()
-    h = lib().ora_sgns_train_dp(_p(tokens, C.c_int32), n_sent, L, n_ids, C.byref(params), world, rounds, combine,
-                                C.byref(pairs))
+    h = lib().ora_sgns_train_dp_tiered(_p(tokens, C.c_int32), n_sent, L, n_ids, C.byref(params), world, rounds, combine,
+                                       full_every, hot_rows, C.byref(pairs))
     V = lib().ora_model_vocab_size(h)
     syn0 = np.empty((V, params.dim), np.float32)
     syn1 = np.empty((V, params.dim), np.float32)

@@ -368,6 +368,16 @@ static float combine_div(int combine, int world, int touched, double sq_of_sum, 
 ora_model *ora_sgns_train_dp(const int32_t *tokens, int64_t n_sent, int32_t L, int32_t n_ids,
                              const ora_sgns_params *p, int32_t world, int32_t rounds, int32_t combine,
                              int64_t *pairs_out) {
+    return ora_sgns_train_dp_tiered(tokens, n_sent, L, n_ids, p, world, rounds, combine, 1, 0, pairs_out);
+}
+
+/* Tiered exchange: the vocabulary is sorted by descending count, so the rows that several ranks touch within a slice
+ * (the ones whose deltas interfere) are a contiguous PREFIX of both tables.  `rounds` exchanges per epoch; every
+ * exchange covers rows [0, hot_rows); every `full_every`-th one (and the last) covers all rows.  full_every = 1 is
+ * the plain scheme. */
+ora_model *ora_sgns_train_dp_tiered(const int32_t *tokens, int64_t n_sent, int32_t L, int32_t n_ids,
+                                    const ora_sgns_params *p, int32_t world, int32_t rounds, int32_t combine,
+                                    int32_t full_every, int32_t hot_rows, int64_t *pairs_out) {
     const int delayed = (combine & 16) != 0;
     combine &= 15;
     ora_vocab *vocab = ora_vocab_build(tokens, n_sent * L, n_ids, p->min_count);
@@ -433,6 +443,8 @@ ora_model *ora_sgns_train_dp(const int32_t *tokens, int64_t n_sent, int32_t L, i
                 if (w.s_hi > w.s_lo) { worker_run(&w); pairs += w.pairs; }
             }
             const int last = ep == p->epochs - 1 && rd == rounds - 1;
+            const int full = full_every <= 1 || last || (rd + 1) % full_every == 0;
+            const int32_t Vx = full ? V : (hot_rows < V ? hot_rows : V);   /* rows [0, Vx) take part in this exchange */
             for (int t = 0; t < 2; t++) {
                 /* a delayed exchange lands now, one slice late: replica and base += combined - own */
                 if (have_pending) {
@@ -447,7 +459,7 @@ ora_model *ora_sgns_train_dp(const int32_t *tokens, int64_t n_sent, int32_t L, i
                 memset(sumsq, 0, sizeof(double) * (size_t)(V ? V : 1));
                 for (int r = 0; r < world; r++) {
                     const float *cur = t == 0 ? rep[r].syn0 : rep[r].syn1neg;
-                    for (int32_t v = 0; v < V; v++) {
+                    for (int32_t v = 0; v < Vx; v++) {
                         int nz = 0;
                         double sq = 0.0;
                         for (int32_t d = 0; d < D; d++) {
@@ -463,19 +475,21 @@ ora_model *ora_sgns_train_dp(const int32_t *tokens, int64_t n_sent, int32_t L, i
                         sumsq[v] += sq;
                     }
                 }
-                for (int32_t v = 0; v < V; v++) {
+                for (int32_t v = 0; v < Vx; v++) {
                     double sq_of_sum = 0.0;
                     for (int32_t d = 0; d < D; d++) sq_of_sum += (double)acc[(size_t)v * D + d] * (double)acc[(size_t)v * D + d];
                     const float div = combine_div(combine, world, touched[v], sq_of_sum, sumsq[v]);
                     for (int32_t d = 0; d < D; d++) acc[(size_t)v * D + d] /= div;
                 }
+                const size_t nx = (size_t)Vx * (size_t)D;
                 if (delayed && !last) { /* in flight during the next slice */
-                    memcpy(pend[t], acc, sizeof(float) * n);
-                    for (int r = 0; r < world; r++) memcpy(pown[t][r], own[t][r], sizeof(float) * n);
+                    memset(pend[t], 0, sizeof(float) * n);
+                    memcpy(pend[t], acc, sizeof(float) * nx);
+                    for (int r = 0; r < world; r++) { memset(pown[t][r], 0, sizeof(float) * n); memcpy(pown[t][r], own[t][r], sizeof(float) * nx); }
                 } else {
                     for (int r = 0; r < world; r++) {
                         float *cur = t == 0 ? rep[r].syn0 : rep[r].syn1neg;
-                        for (size_t i = 0; i < n; i++) { const float c = acc[i] - own[t][r][i]; cur[i] += c; bas[t][r][i] += c; }
+                        for (size_t i = 0; i < nx; i++) { const float c = acc[i] - own[t][r][i]; cur[i] += c; bas[t][r][i] += c; }
                     }
                 }
             }

@@ -66,6 +66,12 @@ ora_model *ora_sgns_train_dp(const int32_t *tokens, int64_t n_sent, int32_t L, i
                              const ora_sgns_params *p, int32_t world, int32_t rounds, int32_t combine,
                              int64_t *pairs_out);
 
+/* Tiered exchange: every exchange covers the hot prefix rows [0, hot_rows) of the frequency-sorted tables, every
+ * full_every-th one (and the last) all rows. */
+ora_model *ora_sgns_train_dp_tiered(const int32_t *tokens, int64_t n_sent, int32_t L, int32_t n_ids,
+                                    const ora_sgns_params *p, int32_t world, int32_t rounds, int32_t combine,
+                                    int32_t full_every, int32_t hot_rows, int64_t *pairs_out);
+
 /* Count pairs only (same enumeration, no arithmetic). */
 int64_t ora_sgns_count_pairs(const int32_t *tokens, int64_t n_sent, int32_t L, int32_t n_ids,
                              const ora_sgns_params *p);

@@ -16,14 +16,14 @@ timeout 600 python scripts/sgns_ab.py synth 100000 2000000 --dim 128 --variants 
 echo "== CA staleness sweep, 1M walks"
 timeout 900 python scripts/sgns_ab.py ca 1000000 --quality --conc 0,206,412,824,1648,3296 --variants tp:0 --tag r2s1_ca 2>&1 | tail -10
 echo "== bench: clock sampler on / off"
-timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/r2s1_bench_sampler_on.json 2> gpurun_out/r2s1_bench_on.err; python - <<'PY'
+timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-synth > gpurun_out/r2s1_bench_sampler_on.json 2> gpurun_out/r2s1_bench_on.err; python - <<'PY'
 import json
 for f in ("on",):
     d = json.load(open("gpurun_out/r2s1_bench_sampler_%s.json" % f))
     s = d["stages"]["sgns"]
     print(f, "device", s["value"], "kernel_ms", s["kernel_ms"], "e2e", s["e2e"]["value"])
 PY
-timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-clock-sampler > gpurun_out/r2s1_bench_sampler_off.json 2> gpurun_out/r2s1_bench_off.err; python - <<'PY'
+timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-synth --no-clock-sampler > gpurun_out/r2s1_bench_sampler_off.json 2> gpurun_out/r2s1_bench_off.err; python - <<'PY'
 import json
 d = json.load(open("gpurun_out/r2s1_bench_sampler_off.json"))
 s = d["stages"]["sgns"]

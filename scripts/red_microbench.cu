@@ -9,6 +9,7 @@
 // (cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32: no per-lane LSU reduction at all), 4 = load + 3.
 #include <cstdio>
 #include <cstdint>
+#include <string>
 #include <cuda_runtime.h>
 
 __device__ __forceinline__ void red4(float4 *p, float v) {
@@ -64,6 +65,9 @@ __global__ void __launch_bounds__(128) k(float *table, uint32_t V, uint32_t pitc
     if (acc == 123.456f) *sink = acc;
 }
 
+static bool g_json = false;
+static double g_last_rows_per_s = 0;
+
 template <int G, int MODE>
 static void run(const char *name, float *table, uint32_t V, uint32_t pitch, int live, int sms) {
     float *sink;
@@ -80,15 +84,34 @@ static void run(const char *name, float *table, uint32_t V, uint32_t pitch, int 
     cudaEventElapsedTime(&ms, e0, e1);
     double rows = (double)blocks * 128 / G * iters * 6;
     double lane_ops = rows * live * (MODE == 2 || MODE == 4 ? 2 : 1);
-    printf("%-34s G=%2d live=%2d pitch=%4u V=%8u mode=%d : %8.1f M rows/s  %8.1f G lane-ops/s  %7.1f GB/s  (%.2f ms)\n", name, G, live, pitch,
+    g_last_rows_per_s = rows / ms * 1e3;
+    if (!g_json) printf("%-34s G=%2d live=%2d pitch=%4u V=%8u mode=%d : %8.1f M rows/s  %8.1f G lane-ops/s  %7.1f GB/s  (%.2f ms)\n", name, G, live, pitch,
            V, MODE, rows / ms / 1e3, lane_ops / ms / 1e6, lane_ops * 16 / ms / 1e6, ms);
     cudaFree(sink);
 }
 
-int main() {
+int main(int argc, char **argv) {
     cudaDeviceProp p;
     cudaGetDeviceProperties(&p, 0);
     const int sms = p.multiProcessorCount;
+    if (argc > 1 && std::string(argv[1]) == "--json") {
+        // bench.py's live ceiling: the tract x 24 access shape (80-byte rows on a 96-byte pitch, 5 of 8 lanes, 19 224 rows,
+        // L2-resident) and the community-area shape (32-byte rows, 2 of 8 lanes, 1 848 rows); one JSON line
+        g_json = true;
+        float *t;
+        cudaMalloc(&t, (size_t)19224 * 128);
+        cudaMemset(t, 0, (size_t)19224 * 128);
+        double r[6];
+        run<8, 0>("", t, 19224, 96, 5, sms); r[0] = g_last_rows_per_s;
+        run<8, 1>("", t, 19224, 96, 5, sms); r[1] = g_last_rows_per_s;
+        run<8, 2>("", t, 19224, 96, 5, sms); r[2] = g_last_rows_per_s;
+        run<8, 0>("", t, 1848, 32, 2, sms); r[3] = g_last_rows_per_s;
+        run<8, 1>("", t, 1848, 32, 2, sms); r[4] = g_last_rows_per_s;
+        run<8, 2>("", t, 1848, 32, 2, sms); r[5] = g_last_rows_per_s;
+        printf("{\"device\": \"%s\", \"tract24_rows_per_s\": {\"red\": %.4g, \"load\": %.4g, \"load_red\": %.4g}, "
+               "\"ca_rows_per_s\": {\"red\": %.4g, \"load\": %.4g, \"load_red\": %.4g}}\n", p.name, r[0], r[1], r[2], r[3], r[4], r[5]);
+        return cudaGetLastError() == cudaSuccess ? 0 : 1;
+    }
     printf("%s, %d SMs\n", p.name, sms);
     float *small, *big;
     const uint32_t Vs = 19224, Vb = 2400000;

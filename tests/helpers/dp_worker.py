@@ -14,6 +14,7 @@ from embedding_b200 import abi, parallel, synth  # noqa: E402
 def main():
     rank, world, d = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
     rounds = int(sys.argv[4]) if len(sys.argv) > 4 else 6
+    transport = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     ctx = abi.Context(rank)
     idf = os.path.join(d, "nccl_id.bin")
     if rank == 0:
@@ -35,10 +36,11 @@ def main():
     n_walks = 40_000
     first, count = parallel.walk_shard(n_walks, rank, world)
     corpus = G.walk(count, 8, seed=11, first_walk_id=first)          # this rank's shard of the walk ids
-    m = abi.Model.train(ctx, [corpus], abi.sgns_params(dim=32, window=5, negative=5, min_count=2, seed=3, sync_rounds=rounds))
+    m = abi.Model.train(ctx, [corpus], abi.sgns_params(dim=32, window=5, negative=5, min_count=2, seed=3, sync_rounds=rounds, transport=transport))
     syn0, syn1, ids = m.vectors(want_syn1neg=True)
     np.savez(os.path.join(d, "rank%d.npz" % rank), syn0=syn0, syn1=syn1, ids=ids, pairs=m.pairs,
-             rounds=ctx.phase_ms("sgns_rounds"), sync_ms=ctx.phase_ms("sgns_sync"), tok=corpus.tokens())
+             rounds=ctx.phase_ms("sgns_rounds"), sync_ms=ctx.phase_ms("sgns_sync"), transport=ctx.phase_ms("sgns_transport"),
+             tok=corpus.tokens())
     ctx.close()
 
 

@@ -1,5 +1,5 @@
 """GPU tests of the multi-GPU row: the NCCL communicator of a ctx and the data-parallel skip-gram
-(delta all-reduce, per row divided by the contributing ranks).  The 1-GPU cases run the same code path with a world of one; the 2-rank case needs two
+(embedding deltas combined per row by the peer-memory kernel over NVLink, or by NCCL all-reduces).  The 1-GPU cases run the same code path with a world of one; the 2-rank case needs two
 GPUs on the box (gpurun --gpus 2) and is skipped otherwise."""
 import os
 import subprocess
@@ -74,16 +74,20 @@ def _device_count():
 
 
 @pytest.mark.skipif(_device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
-def test_two_rank_data_parallel_skipgram(dge_lib, tmp_path):
+@pytest.mark.parametrize("transport", [1, 2])          # 1: peer-memory kernel over NVLink (cudaIpc), 2: NCCL all-reduce
+def test_two_rank_data_parallel_skipgram(dge_lib, tmp_path, transport):
     """Two processes, one GPU each: walk ids sharded, vocabulary from the all-reduced counts, embedding deltas combined
-    over NCCL (per row: sum / contributing ranks).  Both ranks must end with bit-identical tables, the vocabulary must be the one of the whole corpus, and
-    the embeddings must carry the same neighbourhood structure as a single-GPU run on the whole corpus."""
+    per row (alignment-weighted rule) by the peer-memory kernel / by NCCL.  Both ranks must end with bit-identical
+    tables, the vocabulary must be the one of the whole corpus, the two ranks together must train EXACTLY the pairs of a
+    single-GPU run over the whole corpus (global sentence indices key the RNG), and the embeddings must carry the same
+    neighbourhood structure as that run."""
     from embedding_b200 import evaluation as ev
     worker = os.path.join(ROOT, "tests", "helpers", "dp_worker.py")
-    procs = [subprocess.Popen([sys.executable, worker, str(r), "2", str(tmp_path), "24"]) for r in range(2)]
+    procs = [subprocess.Popen([sys.executable, worker, str(r), "2", str(tmp_path), "24", str(transport)]) for r in range(2)]
     for p in procs:
         assert p.wait(timeout=600) == 0
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    assert r0["transport"] == transport and r1["transport"] == transport
     assert np.array_equal(r0["ids"], r1["ids"])
     assert np.array_equal(r0["syn0"], r1["syn0"]) and np.array_equal(r0["syn1"], r1["syn1"])
     assert r0["rounds"] == 24 and np.isfinite(r0["syn0"]).all()
@@ -96,17 +100,22 @@ def test_two_rank_data_parallel_skipgram(dge_lib, tmp_path):
     # single-GPU run over the whole corpus, same hyper-parameters
     ctx = dge_lib.Context(0)
     c = dge_lib.Corpus.from_tokens(ctx, whole, nv)
-    m = dge_lib.Model.train(ctx, [c], dge_lib.sgns_params(dim=32, window=5, negative=5, min_count=2, seed=3))
+    kw = dict(dim=32, window=5, negative=5, min_count=2)
+    m = dge_lib.Model.train(ctx, [c], dge_lib.sgns_params(seed=3, **kw))
     s0, ids = m.vectors()
     assert np.array_equal(ids, r0["ids"])
-    assert abs(int(r0["pairs"]) + int(r1["pairs"]) - m.pairs) < 0.02 * m.pairs
-    zeros = np.zeros(nv, np.int32)
-    la = ev.layers_from_model(s0, ids, zeros, np.arange(nv, dtype=np.int32))
-    lb = ev.layers_from_model(r0["syn0"], r0["ids"], zeros, np.arange(nv, dtype=np.int32))
+    assert int(r0["pairs"]) + int(r1["pairs"]) == m.pairs       # same pairs, same negatives: only the interleaving differs
+    m2 = dge_lib.Model.train(ctx, [c], dge_lib.sgns_params(seed=4, **kw))
+    zeros, ar = np.zeros(nv, np.int32), np.arange(nv, dtype=np.int32)
+    la = ev.layers_from_model(s0, ids, zeros, ar)
+    lb = ev.layers_from_model(r0["syn0"], r0["ids"], zeros, ar)
+    ls = ev.layers_from_model(m2.vectors()[0], ids, zeros, ar)
     lc = {0: (np.random.default_rng(0).standard_normal(s0.shape), la[0][1])}
-    ov, ov_rand = ev.knn_overlap(la, lb, 10), ev.knn_overlap(la, lc, 10)
-    # Calibration (profiles/r1s20_dp_diagnose.json, tests/test_sgns_oracle.py::test_data_parallel_combine_rules): two
-    # single-GPU runs with different seeds agree to 0.50, the oracle's emulation of this exchange (24 rounds, average
-    # over contributors) to 0.41 with the sequential run; the plain sum of deltas fell to 0.10 here.
-    assert ov > 20 * ov_rand and ov > 0.25, (ov, ov_rand)
+    ov, ov_seed, ov_rand = ev.knn_overlap(la, lb, 10), ev.knn_overlap(la, ls, 10), ev.knn_overlap(la, lc, 10)
+    print("kNN agreement with the single-GPU run: data-parallel %.3f, another seed %.3f, random %.3f" % (ov, ov_seed, ov_rand))
+    # Calibration: the oracle's emulation of this exchange (24 rounds, two ranks, alignment-weighted rule) agrees with the
+    # sequential run to 0.65, two sequential runs with different seeds to 0.50 (scripts/dp_emulation_sweep.py, DESIGN.md
+    # 3.4); the plain sum of the deltas of round 1 fell to 0.10 on the GPUs.  Bar: at least 0.35, and not worse than
+    # 0.8 x what two single-GPU seeds agree to.
+    assert ov > 20 * ov_rand and ov >= 0.35 and ov >= 0.8 * ov_seed, (ov, ov_seed, ov_rand)
     ctx.close()

@@ -129,7 +129,9 @@ def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negati
         flag_sets.append(L.F_ONE_WARP | L.F_PLAIN_STORES)            # atomic-free build: one item at a time loses no update
     for flags in flag_sets:
         e0, e1 = rel_err(flags=flags)
-        assert e0 < 0.02 and e1 < 0.02, (flags, e0, e1)
+        # plain stores lose an update whenever one row is drawn twice within a unit (both copies start from the same load)
+        tol = 0.06 if flags & L.F_PLAIN_STORES else 0.02
+        assert e0 < tol and e1 < tol, (flags, e0, e1)
     e0, e1 = rel_err(concurrency=2)                 # two sentences in flight
     assert e0 < 0.35 and e1 < 0.35, (e0, e1)
     e0, e1 = rel_err()                              # automatic full-GPU schedule
