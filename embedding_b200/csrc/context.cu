@@ -1,5 +1,6 @@
 // context.cu -- ctx lifecycle, error text, pinned host memory, phase timings.
 #include "dge_internal.cuh"
+#include <cstring>
 
 static thread_local std::string g_tls_error;
 
@@ -10,6 +11,22 @@ void dge_set_error(dge_ctx *ctx, const std::string &msg) {
 int dge_fail(dge_ctx *ctx, int code, const std::string &msg) {
     dge_set_error(ctx, msg);
     return code;
+}
+
+static void ctx_teardown(dge_ctx *ctx) {
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->tev0) cudaEventDestroy(ctx->tev0);
+    if (ctx->tev1) cudaEventDestroy(ctx->tev1);
+    delete ctx;
+}
+void dge_ctx_retain(dge_ctx *ctx) { if (ctx) ctx->refs++; }
+void dge_ctx_release(dge_ctx *ctx) {
+    if (ctx && --ctx->refs == 0) ctx_teardown(ctx);
 }
 
 extern "C" {
@@ -43,27 +60,31 @@ int dge_create(int device, dge_ctx **out) {
         delete ctx;
         return dge_fail(nullptr, DGE_E_CUDA, "dge_create: stream/event creation failed");
     }
-    // stream-ordered allocator: keep freed blocks in the pool (no trim at synchronisation points)
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    // stream-ordered allocator: a pool of this ctx's own that keeps freed blocks (no trim at synchronisation points);
+    // the device's default pool -- shared with torch / NCCL living in the same process -- is not touched
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if (cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess) {
         uint64_t keep = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+        ctx->pool = nullptr;   // fall back to the default pool with its default (trimming) threshold
+        cudaGetLastError();
     }
     *out = ctx;
     return DGE_OK;
 }
 
 void dge_destroy(dge_ctx *ctx) {
-    if (!ctx) return;
+    if (!ctx || ctx->closed) return;
+    ctx->closed = true;
     dge_comm_destroy(ctx);
-    cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->tev0) cudaEventDestroy(ctx->tev0);
-    if (ctx->tev1) cudaEventDestroy(ctx->tev1);
-    delete ctx;
+    // handles that are still alive keep the stream and the pool alive; their *_free releases the last reference
+    dge_ctx_release(ctx);
 }
 
 const char *dge_last_error(const dge_ctx *ctx) { return ctx ? ctx->err.c_str() : g_tls_error.c_str(); }

@@ -20,7 +20,13 @@ struct dge_ctx {
     std::string err;
     std::map<std::string, float> phase_ms;
     int64_t launches = 0;
+    cudaMemPool_t pool = nullptr;               // PRIVATE stream-ordered pool of this ctx (not the device's default pool)
+    int refs = 1;                               // the ctx itself + every live graph / corpus / model / flows handle
+    bool closed = false;                        // dge_destroy was called; torn down when the last handle is freed
 };
+// Handles keep their ctx alive: a *_free after dge_destroy is safe (the ctx is torn down by the last release).
+void dge_ctx_retain(dge_ctx *ctx);
+void dge_ctx_release(dge_ctx *ctx);
 
 // One 32-byte sector per edge: a walk step is ONE dependent random load.  The record carries the
 // chosen column's and the alias column's destination together with their CSR row (start, degree),
@@ -89,6 +95,10 @@ struct dge_model {
     int32_t *id_of_word = nullptr;             // device [V]
 };
 
+// every handle is created and deleted through these: the handle holds a reference on its ctx
+template <typename H> static inline H *dge_new_handle(dge_ctx *ctx) { H *h = new H(); h->ctx = ctx; dge_ctx_retain(ctx); return h; }
+template <typename H> static inline void dge_delete_handle(H *h) { if (!h) return; dge_ctx *c = h->ctx; delete h; dge_ctx_release(c); }
+
 // ---- multi-GPU (comm.cu); no-ops without a communicator
 int dge_comm_allreduce_sum_f32(dge_ctx *ctx, float *buf, size_t n);
 int dge_comm_allreduce_sum_u64(dge_ctx *ctx, unsigned long long *buf, size_t n);
@@ -136,11 +146,13 @@ struct dge_phase_timer {
     }
 };
 
-// Device memory comes from the device's stream-ordered pool on the ctx stream (context.cu sets the release
-// threshold to "never"): the multi-GB token / scratch buffers of one step are reused by the next step without a
-// round trip to the driver.  Frees are stream-ordered too, so they never synchronise the device.
+// Device memory comes from the ctx's OWN stream-ordered pool on the ctx stream (context.cu creates it with the release
+// threshold "never" and destroys it with the ctx, so the process-wide default pool that torch / NCCL may share is left
+// alone): the multi-GB token / scratch buffers of one step are reused by the next step without a round trip to the
+// driver.  Frees are stream-ordered too, so they never synchronise the device.
 template <typename T>
 static inline cudaError_t dge_malloc(dge_ctx *ctx, T **p, size_t n) {
+    if (ctx->pool) return cudaMallocFromPoolAsync((void **)p, (n ? n : 1) * sizeof(T), ctx->pool, ctx->stream);
     return cudaMallocAsync((void **)p, (n ? n : 1) * sizeof(T), ctx->stream);
 }
 static inline void dge_free(dge_ctx *ctx, void *p) {

@@ -131,7 +131,7 @@ int dge_flows_create(dge_ctx *ctx, int32_t n_regions, const int32_t *F, dge_flow
     if (n_regions > FLOWS_MAX_REGIONS)
         return dge_fail(ctx, DGE_E_LIMIT, "dge_flows_create: the dense flow tensor supports at most 8192 regions");
     DGE_CUDA(ctx, cudaSetDevice(ctx->device));
-    dge_flows *f = new dge_flows();
+    dge_flows *f = dge_new_handle<dge_flows>(ctx);
     f->ctx = ctx; f->n = n_regions;
     size_t total = (size_t)n_regions * 24 * (size_t)n_regions;
     cudaError_t e = dge_malloc(ctx, &f->F, total);
@@ -142,7 +142,7 @@ int dge_flows_create(dge_ctx *ctx, int32_t n_regions, const int32_t *F, dge_flow
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         dge_free(ctx, f->F);
-        delete f;
+        dge_delete_handle(f);
         return dge_fail(ctx, DGE_E_CUDA, std::string("dge_flows_create: ") + cudaGetErrorString(e));
     }
     *out = f;
@@ -214,7 +214,7 @@ void dge_flows_free(dge_flows *f) {
     if (!f) return;
     cudaSetDevice(f->ctx->device);
     dge_free(f->ctx, f->F);
-    delete f;
+    dge_delete_handle(f);
 }
 
 int dge_crosstime_graph_build(const dge_flows *f, const int32_t *order, int32_t num_layer, int mode,
@@ -265,6 +265,8 @@ int dge_crosstime_graph_build(const dge_flows *f, const int32_t *order, int32_t 
         DGE_CUDA(ctx, cudaMemcpyAsync(&ne, (int64_t *)t_pos.p + cells, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         DGE_CUDA(ctx, cudaStreamSynchronize(st));
     }
+    // the mention scan below runs over 2 * ne int32 flags: keep it inside int32 (a dense tensor of ~8192 regions could exceed it)
+    if (2 * ne >= ((int64_t)1 << 31)) return dge_fail(ctx, DGE_E_LIMIT, "dge_crosstime_graph_build: more than 2^30 edges");
     flows_tmp t_sk(ctx), t_dk(ctx), t_w(ctx), t_mflag(ctx), t_mpos(ctx), t_vid(ctx);
     DGE_CUDA(ctx, dge_malloc(ctx, (int32_t **)&t_sk.p, (size_t)ne));
     DGE_CUDA(ctx, dge_malloc(ctx, (int32_t **)&t_dk.p, (size_t)ne));

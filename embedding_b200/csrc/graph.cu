@@ -636,7 +636,7 @@ static void graph_release(dge_graph *g) {
     dge_free(g->ctx, g->out_degree); dge_free(g->ctx, g->sources); dge_free(g->ctx, g->src_w); dge_free(g->ctx, g->src_prob);
     dge_free(g->ctx, g->src_alias); dge_free(g->ctx, g->sws); dge_free(g->ctx, g->rec); dge_free(g->ctx, g->srec);
     dge_free(g->ctx, g->v_layer); dge_free(g->ctx, g->v_region);
-    delete g;
+    dge_delete_handle(g);
 }
 
 struct graph_guard { // frees a half-built graph on an early error return
@@ -654,7 +654,7 @@ int dge_graph_build_device(dge_ctx *ctx, int32_t nv, int64_t ne, const int32_t *
     if (ns > ALIAS_BIG_MAX) return dge_fail(ctx, DGE_E_LIMIT, "dge_graph_build: more than 2^25 source vertices");
     DGE_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    dge_graph *g = new dge_graph();
+    dge_graph *g = dge_new_handle<dge_graph>(ctx);
     graph_guard guard{g};
     g->ctx = ctx; g->nv = nv; g->ne = ne; g->ns = ns;
 

@@ -17,21 +17,64 @@ static inline char *put_int(char *p, int32_t v) {
     return p;
 }
 
-// formats walks [lo,hi) into buf, returns bytes written
-static size_t format_walks(const int32_t *tok, int64_t lo, int64_t hi, int32_t L, const int32_t *layer,
-                           const int32_t *region, int position_prefix, char *buf) {
-    char *p = buf;
-    for (int64_t i = lo; i < hi; i++) {
-        const int32_t *s = tok + i * L;
-        for (int32_t j = 0; j < L && s[j] >= 0; j++) {
-            if (j) *p++ = ' ';
-            p = put_int(p, position_prefix ? j : layer[s[j]]);
-            *p++ = '-';
-            p = put_int(p, region[s[j]]);
-        }
-        *p++ = '\n';
+// ---- `.seq` text formatted on the device
+#define SEQ_BLOCK 128
+static inline int int_width(int32_t v) { // characters of the decimal form, sign included
+    int n = v < 0 ? 2 : 1;
+    for (int64_t x = v < 0 ? -(int64_t)v : v; x >= 10; x /= 10) n++;
+    return n;
+}
+__device__ __forceinline__ int dev_digits(uint32_t x) {
+    int n = 1;
+    n += x >= 10u; n += x >= 100u; n += x >= 1000u; n += x >= 10000u; n += x >= 100000u; n += x >= 1000000u;
+    n += x >= 10000000u; n += x >= 100000000u; n += x >= 1000000000u;
+    return n;
+}
+__device__ __forceinline__ int dev_width(int32_t v) { return (v < 0) + dev_digits(v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v); }
+__device__ __forceinline__ char *dev_put_int(char *p, int32_t v) {
+    uint32_t x = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v;
+    if (v < 0) *p++ = '-';
+    char *e = p + dev_digits(x), *q = e;
+    do { *--q = (char)('0' + x % 10u); x /= 10u; } while (x);
+    return e;
+}
+// line length of walks [lo, lo + m): tokens "<a>-<b>" joined by one space, '\n' terminated (String.join, CrossTimeGraph.java:136-137)
+__global__ void __launch_bounds__(SEQ_BLOCK)
+k_seq_lengths(const int32_t *__restrict__ tok, int64_t n, int64_t lo, int64_t m, int32_t L, const int32_t *__restrict__ layer,
+              const int32_t *__restrict__ region, int position_prefix, int32_t *__restrict__ len) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    int total = 1; // '\n'
+    for (int32_t j = 0; j < L; j++) {
+        const int32_t t = tok[(int64_t)j * n + lo + i];
+        if (t < 0) break;
+        total += (j > 0) + dev_width(position_prefix ? j : layer[t]) + 1 + dev_width(region[t]);
     }
-    return (size_t)(p - buf);
+    len[i] = total;
+}
+// every block formats its SEQ_BLOCK lines into shared memory (they are contiguous in the file) and copies them out coalesced
+__global__ void __launch_bounds__(SEQ_BLOCK)
+k_seq_format(const int32_t *__restrict__ tok, int64_t n, int64_t lo, int64_t m, int32_t L, const int32_t *__restrict__ layer,
+             const int32_t *__restrict__ region, int position_prefix, const int64_t *__restrict__ pos, char *__restrict__ out) {
+    extern __shared__ char s_text[];
+    const int64_t b0 = blockIdx.x * (int64_t)blockDim.x, i = b0 + threadIdx.x;
+    const int64_t b1 = b0 + blockDim.x < m ? b0 + blockDim.x : m;
+    const int64_t base = pos[b0];
+    if (i < m) {
+        char *p = s_text + (pos[i] - base);
+        for (int32_t j = 0; j < L; j++) {
+            const int32_t t = tok[(int64_t)j * n + lo + i];
+            if (t < 0) break;
+            if (j) *p++ = ' ';
+            p = dev_put_int(p, position_prefix ? j : layer[t]);
+            *p++ = '-';
+            p = dev_put_int(p, region[t]);
+        }
+        *p = '\n';
+    }
+    __syncthreads();
+    const int64_t bytes = pos[b1] - base;
+    for (int64_t q = threadIdx.x; q < bytes; q += blockDim.x) out[base + q] = s_text[q];
 }
 
 extern "C" {
@@ -40,44 +83,76 @@ int dge_corpus_write_seq(const dge_corpus *c, const int32_t *label_layer, const 
                          int position_prefix, const char *path, int append) {
     if (!c) return dge_fail(nullptr, DGE_E_INVALID, "dge_corpus_write_seq: corpus is NULL");
     dge_ctx *ctx = c->ctx;
-    if (!path || !label_region || (!position_prefix && !label_layer))
+    if (!path || (c->n_ids > 0 && (!label_region || (!position_prefix && !label_layer))))
         return dge_fail(ctx, DGE_E_INVALID, "dge_corpus_write_seq: NULL argument");
-    size_t total = (size_t)c->n * (size_t)c->L;
-    int32_t *tok = (int32_t *)dge_host_alloc((total ? total : 1) * sizeof(int32_t));
-    if (!tok) return dge_fail(ctx, DGE_E_CUDA, "dge_corpus_write_seq: pinned allocation failed");
-    int rc = dge_corpus_tokens(c, tok);
-    if (rc != DGE_OK) { dge_host_free(tok); return rc; }
+    DGE_CUDA(ctx, cudaSetDevice(ctx->device));
     FILE *f = fopen(path, append ? "ab" : "wb");
-    if (!f) {
-        dge_host_free(tok);
-        return dge_fail(ctx, DGE_E_IO, std::string("dge_corpus_write_seq: cannot open ") + path);
+    if (!f) return dge_fail(ctx, DGE_E_IO, std::string("dge_corpus_write_seq: cannot open ") + path);
+    if (c->n == 0) { return fclose(f) == 0 ? DGE_OK : dge_fail(ctx, DGE_E_IO, std::string("dge_corpus_write_seq: write failed: ") + path); }
+    // The text is formatted ON THE DEVICE (the token matrix never crosses PCIe; a line is ~2.5x the bytes of its int32
+    // tokens, but the host no longer spends ~20 ns per token in put_int): per chunk of walks, line lengths -> exclusive
+    // scan -> every block formats its 128 lines into shared memory and copies them out coalesced; the chunk travels to
+    // one of two pinned buffers while the previous chunk is being written to the file.
+    const int32_t L = c->L, n_ids = c->n_ids;
+    int d1 = 1, d2 = 1;                       // widest first number ("<layer>" or "<position>") and region id
+    for (int32_t i = 0; i < n_ids; i++) {
+        if (!position_prefix) d1 = std::max(d1, int_width(label_layer[i]));
+        d2 = std::max(d2, int_width(label_region[i]));
     }
-    // chunked, multi-threaded formatting; chunks are written in order
-    const int64_t chunk = 1 << 16;
-    unsigned nt = std::thread::hardware_concurrency();
-    if (nt == 0) nt = 1;
-    if (nt > 16) nt = 16;
-    const size_t per_walk = (size_t)c->L * 24 + 2; // two ints of <= 11 chars + '-' + ' ' per token
-    std::vector<std::vector<char>> bufs(nt);
-    std::vector<size_t> lens(nt);
+    if (position_prefix) d1 = int_width(L > 0 ? L - 1 : 0);
+    const size_t max_line = (size_t)L * (size_t)(d1 + d2 + 2) + 1;            // "<a>-<b>" + separator per token, + '\n'
+    if ((size_t)SEQ_BLOCK * max_line > 200 * 1024)
+        return fclose(f), dge_fail(ctx, DGE_E_LIMIT, "dge_corpus_write_seq: lines of this length exceed the formatter's shared-memory tile");
+    const int64_t chunk = std::max<int64_t>(SEQ_BLOCK, (int64_t)(((size_t)64 << 20) / max_line) / SEQ_BLOCK * SEQ_BLOCK);
+    const size_t chunk_bytes = (size_t)chunk * max_line;
+    int32_t *d_layer = nullptr, *d_region = nullptr, *d_len = nullptr;
+    int64_t *d_pos = nullptr;
+    char *d_text = nullptr, *h_text[2] = {nullptr, nullptr};
+    auto cleanup = [&]() {
+        dge_free(ctx, d_layer); dge_free(ctx, d_region); dge_free(ctx, d_len); dge_free(ctx, d_pos); dge_free(ctx, d_text);
+        if (h_text[0]) cudaFreeHost(h_text[0]);
+        if (h_text[1]) cudaFreeHost(h_text[1]);
+    };
+    if ((!position_prefix && dge_malloc(ctx, &d_layer, (size_t)n_ids) != cudaSuccess) || dge_malloc(ctx, &d_region, (size_t)n_ids) != cudaSuccess ||
+        dge_malloc(ctx, &d_len, (size_t)chunk + 1) != cudaSuccess || dge_malloc(ctx, &d_pos, (size_t)chunk + 2) != cudaSuccess ||
+        dge_malloc(ctx, &d_text, chunk_bytes) != cudaSuccess || cudaMallocHost((void **)&h_text[0], chunk_bytes) != cudaSuccess ||
+        cudaMallocHost((void **)&h_text[1], chunk_bytes) != cudaSuccess) {
+        cleanup(); fclose(f);
+        return dge_fail(ctx, DGE_E_CUDA, "dge_corpus_write_seq: allocation failed");
+    }
+    cudaStream_t st = ctx->stream;
+    if (!position_prefix) cudaMemcpyAsync(d_layer, label_layer, sizeof(int32_t) * (size_t)n_ids, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_region, label_region, sizeof(int32_t) * (size_t)n_ids, cudaMemcpyHostToDevice, st);
+    cudaFuncSetAttribute(k_seq_format, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SEQ_BLOCK * max_line));
     bool io_ok = true;
-    for (int64_t base = 0; base < c->n && io_ok; base += chunk * nt) {
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; t++) {
-            int64_t lo = base + (int64_t)t * chunk, hi = std::min<int64_t>(lo + chunk, c->n);
-            lens[t] = 0;
-            if (lo >= hi) continue;
-            bufs[t].resize((size_t)(hi - lo) * per_walk);
-            th.emplace_back([&, t, lo, hi]() {
-                lens[t] = format_walks(tok, lo, hi, c->L, label_layer, label_region, position_prefix, bufs[t].data());
-            });
-        }
-        for (auto &x : th) x.join();
-        for (unsigned t = 0; t < nt && io_ok; t++)
-            if (lens[t] && fwrite(bufs[t].data(), 1, lens[t], f) != lens[t]) io_ok = false;
+    int rc = DGE_OK;
+    size_t pending_bytes = 0;   // bytes of the previous chunk, sitting in h_text[(k - 1) & 1], not yet written
+    int64_t k = 0;
+    dge_phase_timer t(ctx, "seq_format");
+    for (int64_t lo = 0; lo < c->n && io_ok && rc == DGE_OK; lo += chunk, k++) {
+        const int64_t m = std::min<int64_t>(chunk, c->n - lo);
+        const unsigned blocks = (unsigned)((m + SEQ_BLOCK - 1) / SEQ_BLOCK);
+        k_seq_lengths<<<blocks, SEQ_BLOCK, 0, st>>>(c->tok, c->n, lo, m, L, d_layer, d_region, position_prefix, d_len);
+        rc = dge_scan_i32(ctx, d_len, (int32_t)m, d_pos);
+        if (rc != DGE_OK) break;
+        k_seq_format<<<blocks, SEQ_BLOCK, SEQ_BLOCK * max_line, st>>>(c->tok, c->n, lo, m, L, d_layer, d_region, position_prefix, d_pos, d_text);
+        ctx->launches += 2;
+        int64_t total = 0;
+        cudaMemcpyAsync(&total, d_pos + m, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_text[k & 1], d_text, (size_t)total, cudaMemcpyDeviceToHost, st);
+        // while this chunk travels, the previous one goes to the file
+        if (pending_bytes && fwrite(h_text[(k - 1) & 1], 1, pending_bytes, f) != pending_bytes) io_ok = false;
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) { rc = dge_fail(ctx, DGE_E_CUDA, std::string("dge_corpus_write_seq: ") + cudaGetErrorString(e)); break; }
+        pending_bytes = (size_t)total;
     }
+    if (rc == DGE_OK && io_ok && pending_bytes && fwrite(h_text[(k - 1) & 1], 1, pending_bytes, f) != pending_bytes) io_ok = false;
+    t.stop();
     if (fclose(f) != 0) io_ok = false;
-    dge_host_free(tok);
+    cleanup();
+    if (rc != DGE_OK) return rc;
     if (!io_ok) return dge_fail(ctx, DGE_E_IO, std::string("dge_corpus_write_seq: write failed: ") + path);
     return DGE_OK;
 }

@@ -1400,7 +1400,7 @@ static void model_release(dge_model *m) {
         cudaFree(m->syn0); cudaFree(m->syn1neg);
     } else { dge_free(m->ctx, m->syn0); dge_free(m->ctx, m->syn1neg); }
     dge_free(m->ctx, m->id_of_word);
-    delete m;
+    dge_delete_handle(m);
 }
 
 // device temporaries of one call: released (stream-ordered) on every way out
@@ -1572,7 +1572,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
     }
     t_vocab.stop();
 
-    dge_model *m = new dge_model();
+    dge_model *m = dge_new_handle<dge_model>(ctx);
     m->ctx = ctx; m->V = V; m->dim = p->dim; m->stride = stride;
     int32_t *d_word_of_id = nullptr, *d_table = nullptr, *d_wtok = nullptr;
     float *d_exp = nullptr;

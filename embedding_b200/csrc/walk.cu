@@ -221,11 +221,11 @@ int dge_walk(const dge_graph *g, int64_t n_walks, int64_t first_walk_id, int32_t
     if (sampler != DGE_SAMPLER_ALIAS && sampler != DGE_SAMPLER_CDF)
         return dge_fail(ctx, DGE_E_INVALID, "dge_walk: unknown sampler");
     DGE_CUDA(ctx, cudaSetDevice(ctx->device));
-    dge_corpus *c = new dge_corpus();
+    dge_corpus *c = dge_new_handle<dge_corpus>(ctx);
     c->ctx = ctx; c->n = n_walks; c->L = L; c->n_ids = g->nv;
     cudaError_t e = dge_malloc(ctx, &c->tok, (size_t)n_walks * (size_t)L);
     if (e != cudaSuccess) {
-        delete c;
+        dge_delete_handle(c);
         return dge_fail(ctx, DGE_E_CUDA, std::string("dge_walk: cudaMalloc tokens: ") + cudaGetErrorString(e));
     }
     if (n_walks > 0 && L > 0) {
@@ -243,7 +243,7 @@ int dge_walk(const dge_graph *g, int64_t n_walks, int64_t first_walk_id, int32_t
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {
             dge_free(ctx, c->tok);
-            delete c;
+            dge_delete_handle(c);
             return dge_fail(ctx, DGE_E_CUDA, std::string("dge_walk: ") + cudaGetErrorString(e));
         }
     }
@@ -259,7 +259,7 @@ int dge_corpus_from_tokens(dge_ctx *ctx, const int32_t *tokens, int64_t n_walks,
     if (n_walks < 0 || L < 0 || n_ids < 0 || (n_walks * L > 0 && !tokens))
         return dge_fail(ctx, DGE_E_INVALID, "dge_corpus_from_tokens: bad arguments");
     DGE_CUDA(ctx, cudaSetDevice(ctx->device));
-    dge_corpus *c = new dge_corpus();
+    dge_corpus *c = dge_new_handle<dge_corpus>(ctx);
     c->ctx = ctx; c->n = n_walks; c->L = L; c->n_ids = n_ids;
     size_t total = (size_t)n_walks * (size_t)L;
     int32_t *stage = nullptr;
@@ -267,7 +267,7 @@ int dge_corpus_from_tokens(dge_ctx *ctx, const int32_t *tokens, int64_t n_walks,
     int rc = DGE_OK;
     auto fail = [&](const std::string &m, int code) {
         dge_free(ctx, c->tok); dge_free(ctx, stage); dge_free(ctx, d_cnt);
-        delete c;
+        dge_delete_handle(c);
         return dge_fail(ctx, code, m);
     };
     if (dge_malloc(ctx, &c->tok, total) != cudaSuccess || dge_malloc(ctx, &stage, total) != cudaSuccess ||
@@ -372,7 +372,7 @@ void dge_corpus_free(dge_corpus *c) {
     if (!c) return;
     cudaSetDevice(c->ctx->device);
     dge_free(c->ctx, c->tok);
-    delete c;
+    dge_delete_handle(c);
 }
 
 } // extern "C"

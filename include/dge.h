@@ -11,8 +11,9 @@
  * Conventions
  *   - plain C types only; every buffer in a signature is HOST memory owned by the caller
  *     (device memory never crosses the ABI);
- *   - opaque handles are library-owned and released only by the matching *_free, which must happen before the
- *     dge_destroy of the ctx they were created on;
+ *   - opaque handles are library-owned and released only by the matching *_free; every handle keeps its ctx alive, so
+ *     a *_free that comes after dge_destroy is safe (the ctx is torn down when its last handle goes);
+ *   - device memory comes from a stream-ordered pool PRIVATE to the ctx (the process-wide default pool is not touched);
  *   - every call is blocking; a ctx (one per GPU / process) is used by one thread at a time;
  *   - return 0 on success, a negative dge_status otherwise; dge_last_error() has the text;
  *   - there is NO CPU fallback: without a usable sm_100 device dge_create fails with DGE_E_NO_DEVICE.

@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <stdio.h>
 
 /* ------------------------------------------------------------------ alias */
 
@@ -497,4 +498,30 @@ int64_t ora_crosstime_edges(const int32_t *F, int32_t n, const int32_t *order, i
     *n_vertices_out = nv;
     *n_sources_out = nsrc;
     return ne;
+}
+
+/* CrossTimeGraph.sampleSequenceHelper :134-141: fout.write(String.join(" ", seq) + "\n") per walk through a
+ * BufferedWriter -- one thread, tokens "<layer>-<region>".  The CPU arm of the reference's published timing experiment
+ * (CrossTimeGraph.java:152-159 includes this write).  Returns bytes written, -1 on an I/O error. */
+int64_t ora_write_seq(const int32_t *tokens, int64_t n_walks, int32_t L, const int32_t *layer, const int32_t *region,
+                      const char *path) {
+    FILE *f = fopen(path, "wb");
+    if (!f) return -1;
+    static char buf[1 << 16];
+    setvbuf(f, buf, _IOFBF, sizeof(buf));
+    int64_t bytes = 0;
+    char line[64 * 26 + 2];
+    for (int64_t i = 0; i < n_walks; i++) {
+        char *p = line;
+        for (int32_t j = 0; j < L && j < 64; j++) {
+            int32_t t = tokens[i * L + j];
+            if (t < 0) break;
+            if (j) *p++ = ' ';
+            p += sprintf(p, "%d-%d", layer[t], region[t]);
+        }
+        *p++ = '\n';
+        if (fwrite(line, 1, (size_t)(p - line), f) != (size_t)(p - line)) { fclose(f); return -1; }
+        bytes += p - line;
+    }
+    return fclose(f) == 0 ? bytes : -1;
 }

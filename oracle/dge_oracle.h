@@ -100,6 +100,10 @@ int64_t ora_crosstime_edges(const int32_t *F, int32_t n, const int32_t *order, i
                             int32_t *v_layer, int32_t *v_region, int32_t *n_vertices_out,
                             int32_t *sources, int32_t *n_sources_out);
 
+/* String.join(" ", seq) + "\n" per walk into a file, one thread (CrossTimeGraph.java:134-141); bytes written or -1. */
+int64_t ora_write_seq(const int32_t *tokens, int64_t n_walks, int32_t L, const int32_t *layer, const int32_t *region,
+                      const char *path);
+
 #ifdef __cplusplus
 }
 #endif

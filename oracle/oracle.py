@@ -80,6 +80,8 @@ def lib():
     L.ora_crosstime_edges.restype = i64
     L.ora_crosstime_edges.argtypes = [pi32, i32, pi32, i32, C.c_int, pi32, pi32, pi32, pf64, pi32, pi32, pi32,
                                       pi32, pi32]
+    L.ora_write_seq.restype = i64
+    L.ora_write_seq.argtypes = [pi32, i64, i32, pi32, pi32, C.c_char_p]
     # stage 2
     pp = C.POINTER(SgnsParams)
     L.ora_vocab_build.restype = vp
@@ -172,6 +174,17 @@ class Graph:
         out = np.empty((n_walks, L), np.int32)
         lib().ora_walk(self._h, n_walks, first_walk_id, L, seed, sampler, rng, _p(out, C.c_int32))
         return out
+
+
+def write_seq(tokens, layer, region, path):
+    """String.join(" ", seq) + "\\n" per walk, one thread (CrossTimeGraph.java:134-141); returns the bytes written."""
+    tokens = np.ascontiguousarray(tokens, np.int32)
+    layer, region = np.ascontiguousarray(layer, np.int32), np.ascontiguousarray(region, np.int32)
+    n = lib().ora_write_seq(_p(tokens, C.c_int32), tokens.shape[0], tokens.shape[1], _p(layer, C.c_int32), _p(region, C.c_int32),
+                            os.fsencode(path))
+    if n < 0:
+        raise IOError("ora_write_seq failed: %s" % path)
+    return n
 
 
 def philox4x32_10(ctr, key):

@@ -154,3 +154,33 @@ def test_corpus_roundtrip_relabel_and_seq_format(dge_lib, ctx, tmp_path):
     assert np.array_equal(got, want)
     with pytest.raises(dge_lib.DgeError):
         dge_lib.Corpus.from_tokens(ctx, np.array([[99]], np.int32), 50)
+
+
+def test_seq_text_of_a_corpus_larger_than_one_chunk(dge_lib, ctx, tmp_path):
+    """dge_corpus_write_seq formats the text on the device in chunks of ~64 MB that travel through two pinned buffers:
+    the file must be byte-identical to String.join(" ", seq) + "\\n" per walk (CrossTimeGraph.java:136-137) across chunk
+    and 128-line block boundaries, with ragged lines (dead ends), one-token lines, negative and 10-digit labels."""
+    rng = np.random.default_rng(5)
+    n, L, n_ids = 700_000, 24, 4000
+    tok = rng.integers(0, n_ids, size=(n, L)).astype(np.int32)
+    cut = rng.integers(1, L + 1, size=n)
+    tok[np.arange(L)[None, :] >= cut[:, None]] = -1
+    layer = rng.integers(0, 24, size=n_ids).astype(np.int32)
+    region = rng.integers(10100, 980100, size=n_ids).astype(np.int32)
+    region[:3] = (-7, 0, 2147483647)
+    c = dge_lib.Corpus.from_tokens(ctx, tok, n_ids)
+    p = tmp_path / "big.seq"
+    c.write_seq(str(p), region, layer)
+    lab = np.array(["%d-%d" % (a, b) for a, b in zip(layer, region)])
+    data = p.read_bytes()
+    lines = data.split(b"\n")
+    assert lines[-1] == b"" and len(lines) == n + 1
+    for i in list(range(300)) + list(range(n - 300, n)) + list(rng.integers(0, n, 2000)):
+        assert lines[i].decode() == " ".join(lab[t] for t in tok[i] if t >= 0), i
+    lab_len = np.array([len(x) for x in lab])
+    want_bytes = int(lab_len[tok[tok >= 0]].sum()) + int((tok >= 0).sum() - n) + n      # labels + separators + newlines
+    assert len(data) == want_bytes
+    back = dge_lib.Corpus.read_seq(ctx, str(p), region, layer)
+    assert np.array_equal(back.tokens(), tok)
+    c.free()
+    back.free()
