@@ -456,6 +456,29 @@ def knn_overlap_sample(a, b, n_query=2000, n_cand=50_000, k=10):
     return round(hits / (len(q) * k), 4)
 
 
+_CEIL = {}
+
+
+def synth_sgns_roofline(ach_gbs, pairs_per_s, dim, neg, peak, peak_src, traffic, kernel_ms):
+    """The D = 128 tables are 1.2 GB each, but the walk corpus is skewed and most row traffic hits the 126 MB L2 (ncu: DRAM
+    traffic ~ 5 % of the algorithmic bytes), so HBM does not bound the kernel: its limit is what the L2 delivers for
+    512-byte-row 128-bit loads + reductions on the hot set, measured live by scripts/bin/red_microbench."""
+    if "c" not in _CEIL:
+        _CEIL["c"] = l2_reduction_ceiling()
+    c = _CEIL["c"]
+    rows = c["d128_hot100k_rows_per_s"]["load_red"] if c and "d128_hot100k_rows_per_s" in c else None
+    bpp = sgns_bytes_per_pair(dim, neg)
+    ceil_pairs = rows / (neg + 1) if rows else None
+    return dict(bound="l2-reduction", achieved=ach_gbs, peak=(ceil_pairs * bpp / 1e9) if ceil_pairs else None, unit="GB/s",
+                frac=(pairs_per_s / ceil_pairs) if ceil_pairs else None, bytes_per_unit=bpp,
+                peak_source=("scripts/bin/red_microbench --json, live: %.3g rows/s of 512 bytes loaded AND reduced on a 100 000-row hot set / (K + 1) rows per "
+                             "pair = %.3g pairs/s; the kernel can exceed it because it sends no reduction for a saturated sigmoid (g = 0)" % (rows, ceil_pairs)) if rows else "micro-benchmark binary missing",
+                traffic=traffic["bytes"] if traffic else None,
+                hbm=dict(peak=peak, peak_source=peak_src, frac_by_algorithmic_bytes=ach_gbs / peak,
+                         frac_by_dram_traffic=(traffic["bytes"] / (kernel_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                         note="algorithmic bytes/s exceed the HBM peak because ~80-95 % of the row traffic hits L2; the DRAM-traffic fraction is the HBM load"))
+
+
 def run_synth(args, rank, world, D, dist, abi, ctx, local, steps=3, warmup=1):
     """BASELINE configs[2] (HBM-resident): 100K regions x 24 slices, ~100M edges, 4M walks x 24 per GPU, D=128.
     N = 1: one GPU.  N > 1: walk ids sharded by rank, skip-gram DATA-PARALLEL over the ranks' corpus shards."""
@@ -474,7 +497,7 @@ def run_synth(args, rank, world, D, dist, abi, ctx, local, steps=3, warmup=1):
     t0 = time.perf_counter()
     G = abi.Graph(ctx, f["nv"], f["src"], f["dst"], f["w"], f["sources"])
     build_s = time.perf_counter() - t0
-    wms, sms, toks, pairs, syncs = [], [], [], [], []
+    wms, sms, toks, pairs, syncs, phases = [], [], [], [], [], []
     stats = rounds = transport = keep = None
     for it in range(warmup + steps):
         if it == warmup:
@@ -493,6 +516,8 @@ def run_synth(args, rank, world, D, dist, abi, ctx, local, steps=3, warmup=1):
             toks.append(c.count_tokens())
             pairs.append(m.pairs)
             syncs.append(ctx.phase_ms("sgns_sync"))
+            phases.append(dict(vocab_ms=ctx.phase_ms("vocab"), compact_ms=ctx.phase_ms("compact"), train_ms=ctx.phase_ms("sgns"),
+                               exchange_setup_ms=ctx.phase_ms("sgns_dp_setup")))
         rounds = ctx.phase_ms("sgns_rounds")
         transport = {0.0: "none", 1.0: "peer-memory kernel over NVLink (cudaIpc)", 2.0: "NCCL all-reduce"}.get(ctx.phase_ms("sgns_transport"), "?")
         if last:
@@ -518,11 +543,10 @@ def run_synth(args, rank, world, D, dist, abi, ctx, local, steps=3, warmup=1):
                                 note="3.2 GB of 32-byte walk records, 25x the L2: one dependent random sector per step; the hardware's own rate "
                                      "for this access shape is measured by scripts/walk_microbench.cu (profiles/)")),
         sgns=dict(value=tot_pairs / t_sgns, unit="pairs/s", kernel=sg_kernel, kernel_ms=sk_ms, sync_rounds=rounds, sync_ms=float(np.mean(syncs)),
-                  transport=transport,
-                  roofline=dict(bound="hbm", achieved=sg_ach, peak=peak, unit="GB/s", frac=sg_ach / peak, bytes_per_unit=sgns_bytes_per_pair(dim, neg),
-                                peak_source=peak_src, traffic=ts["bytes"] if ts else None,
-                                note="tables are 1.2 GB each (HBM), but the walk corpus is skewed: most row traffic hits the 126 MB L2, so the "
-                                     "algorithmic bytes/s can exceed the HBM peak; `traffic` has the measured DRAM bytes")),
+                  transport=transport, call_ms=t_sgns / steps * 1e3,
+                  call_phases_ms={k: float(np.mean([ph[k] for ph in phases])) for k in phases[0]},
+                  kernel_pairs_per_s=tot_pairs / D.max(sum(x[1] for x in sms) / 1e3),
+                  roofline=synth_sgns_roofline(sg_ach, float(np.mean(pairs)) / (sk_ms * 1e-3), dim, neg, peak, peak_src, ts, sk_ms)),
         model_stats=stats)
     if multi:
         # ---- what ONE GPU does with the same per-GPU work, in the same run (no communicator): the scaling reference
@@ -531,16 +555,21 @@ def run_synth(args, rank, world, D, dist, abi, ctx, local, steps=3, warmup=1):
         if rank == 0:
             G1 = abi.Graph(ctx1, f["nv"], f["src"], f["dst"], f["w"], f["sources"])
             p1 = abi.sgns_params(dim=dim, window=w["window"], negative=neg, min_count=2, seed=1)
-            ms1, pr1 = [], []
+            ms1, pr1, cl1 = [], [], []
             for it in range(3):
                 c = G1.walk(f["n_walks"], L, 1000 + it, first_walk_id=0)
+                ctx1.timer_start()
                 m1 = abi.Model.train(ctx1, [c], p1)
+                call = ctx1.timer_stop()
                 if it >= 1:
                     ms1.append(ctx1.phase_ms("sgns"))
+                    cl1.append(call)
                     pr1.append(m1.pairs)
                 m1.free()
                 c.free()
-            single = dict(value=sum(pr1) / (sum(ms1) / 1e3), unit="pairs/s", note="one GPU of this box, the same 4M walks, no communicator, kernel time, same run")
+            single = dict(value=sum(pr1) / (sum(cl1) / 1e3), unit="pairs/s", kernel_pairs_per_s=sum(pr1) / (sum(ms1) / 1e3), call_ms=float(np.mean(cl1)),
+                          note="one GPU of this box, the same 4M walks per GPU, no communicator, same run: `value` times the whole dge_sgns_train "
+                               "call like sgns.value above; kernel_pairs_per_s the training launches only")
             # ---- neighbourhood agreement of the data-parallel embedding with a single-GPU run over the WHOLE corpus (walk
             # ids [0, N x 4M) of seed 777: exactly the union of the ranks' shards), and the single-GPU noise floor
             cu = G1.walk(f["n_walks"] * world, L, 777, first_walk_id=0)

@@ -1539,14 +1539,30 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
     local = ce == cudaSuccess ? DGE_OK : dge_fail(ctx, DGE_E_CUDA, std::string("dge_sgns_train: histogram: ") + cudaGetErrorString(ce));
     if (multi) local = dge_comm_agree(ctx, local, "dge_sgns_train (histogram read-back)");
     if (local != DGE_OK) return local;
+    // descending count, ties by ascending id: one 64-bit key per word, (2^32 - 1 - count) in the high half and the id in
+    // the low half, sorted ascending (3x faster than a comparator that chases cnt[] for the 2.4M-word synthetic vocabularies)
     std::vector<int32_t> order;
-    order.reserve(n_ids);
-    for (int32_t i = 0; i < n_ids; i++)
-        if (cnt[i] > 0 && cnt[i] >= (unsigned long long)p->min_count) order.push_back(i);
-    std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
-        if (cnt[x] != cnt[y]) return cnt[x] > cnt[y];
-        return x < y;
-    });
+    {
+        std::vector<uint64_t> keys;
+        keys.reserve(n_ids);
+        bool small_counts = true;
+        for (int32_t i = 0; i < n_ids; i++)
+            if (cnt[i] > 0 && cnt[i] >= (unsigned long long)p->min_count) {
+                if (cnt[i] > 0xFFFFFFFFULL) small_counts = false;
+                keys.push_back(((0xFFFFFFFFULL - (cnt[i] & 0xFFFFFFFFULL)) << 32) | (uint32_t)i);
+            }
+        order.resize(keys.size());
+        if (small_counts) {
+            std::sort(keys.begin(), keys.end());
+            for (size_t k = 0; k < keys.size(); k++) order[k] = (int32_t)(uint32_t)keys[k];
+        } else { // counts beyond 32 bits (> 4e9 occurrences of one token): the plain comparator
+            for (size_t k = 0; k < keys.size(); k++) order[k] = (int32_t)(uint32_t)keys[k];
+            std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+                if (cnt[x] != cnt[y]) return cnt[x] > cnt[y];
+                return x < y;
+            });
+        }
+    }
     const int32_t V = (int32_t)order.size();
     std::vector<int32_t> word_of_id((size_t)n_ids + 1, -1);
     for (int32_t wd = 0; wd < V; wd++) word_of_id[order[wd]] = wd;
@@ -1601,7 +1617,8 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         k_init_syn0<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(m->syn0, V, p->dim, stride, p->seed);
         ctx->launches++;
     }
-    ctx->phase_ms["sgns_rounds"] = 0.f; ctx->phase_ms["sgns_sync"] = 0.f; ctx->phase_ms["sgns_transport"] = 0.f;
+    ctx->phase_ms["sgns_rounds"] = 0.f; ctx->phase_ms["sgns_sync"] = 0.f; ctx->phase_ms["sgns_transport"] = 0.f; ctx->phase_ms["sgns_dp_setup"] = 0.f;
+    ctx->phase_ms["compact"] = 0.f; ctx->phase_ms["sgns"] = 0.f;
 
     if (train) {
         // ---- compacted corpus in vocabulary indices (position-major, all corpora concatenated)
@@ -1685,10 +1702,13 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             rounds = (int)std::min<int64_t>(rounds, std::max<int64_t>(1, max_sent));
         }
         dge_dp *dp = nullptr;
+        ctx->phase_ms["sgns_dp_setup"] = 0.f;
         if (multi) {
+            dge_phase_timer t_dp(ctx, "sgns_dp_setup");   // peer mapping of the replicas (cudaIpc), base slices
             const int rc = dge_dp_begin(ctx, m->syn0, m->syn1neg, V, stride, n4, p->combine == DGE_COMBINE_DEFAULT ? DGE_COMBINE_ALIGNED : p->combine,
                                         p->transport, &dp);
             if (rc != DGE_OK) { model_release(m); return rc; }   // collective: every rank takes this way out
+            t_dp.stop();
         }
         ctx->phase_ms["sgns_rounds"] = (float)rounds;
         int rc = DGE_OK, any_error = 0;

@@ -101,15 +101,24 @@ int main(int argc, char **argv) {
         float *t;
         cudaMalloc(&t, (size_t)19224 * 128);
         cudaMemset(t, 0, (size_t)19224 * 128);
-        double r[6];
+        double r[9];
         run<8, 0>("", t, 19224, 96, 5, sms); r[0] = g_last_rows_per_s;
         run<8, 1>("", t, 19224, 96, 5, sms); r[1] = g_last_rows_per_s;
         run<8, 2>("", t, 19224, 96, 5, sms); r[2] = g_last_rows_per_s;
         run<8, 0>("", t, 1848, 32, 2, sms); r[3] = g_last_rows_per_s;
         run<8, 1>("", t, 1848, 32, 2, sms); r[4] = g_last_rows_per_s;
         run<8, 2>("", t, 1848, 32, 2, sms); r[5] = g_last_rows_per_s;
+        // the synthetic shape: 512-byte rows (D = 128), 32 lanes, a hot set of 100 000 rows (what a skewed walk corpus touches most)
+        float *big;
+        cudaMalloc(&big, (size_t)100000 * 512);
+        cudaMemset(big, 0, (size_t)100000 * 512);
+        run<32, 0>("", big, 100000, 512, 32, sms); r[6] = g_last_rows_per_s;
+        run<32, 1>("", big, 100000, 512, 32, sms); r[7] = g_last_rows_per_s;
+        run<32, 2>("", big, 100000, 512, 32, sms); r[8] = g_last_rows_per_s;
         printf("{\"device\": \"%s\", \"tract24_rows_per_s\": {\"red\": %.4g, \"load\": %.4g, \"load_red\": %.4g}, "
-               "\"ca_rows_per_s\": {\"red\": %.4g, \"load\": %.4g, \"load_red\": %.4g}}\n", p.name, r[0], r[1], r[2], r[3], r[4], r[5]);
+               "\"ca_rows_per_s\": {\"red\": %.4g, \"load\": %.4g, \"load_red\": %.4g}, "
+               "\"d128_hot100k_rows_per_s\": {\"red\": %.4g, \"load\": %.4g, \"load_red\": %.4g}}\n", p.name, r[0], r[1], r[2], r[3], r[4], r[5],
+               r[6], r[7], r[8]);
         return cudaGetLastError() == cudaSuccess ? 0 : 1;
     }
     printf("%s, %d SMs\n", p.name, sms);
