@@ -17,8 +17,8 @@ SCHEDULE_ITEMS, SCHEDULE_SENTENCE = 0, 1
 COMBINE_DEFAULT, COMBINE_MEAN, COMBINE_CONTRIBUTORS, COMBINE_SQRT, COMBINE_ALIGNED, COMBINE_SUM = 0, 1, 2, 3, 4, 5
 TRANSPORT_AUTO, TRANSPORT_PEER, TRANSPORT_NCCL = 0, 1, 2
 # dge_sgns_params.flags (include/dge.h DGE_SGNS_F_*): kernel-selection / measurement hooks for tests and A/B runs
-F_NO_UPDATES, F_NO_NARROW, F_ONE_WARP, F_NARROW, F_TARGET_PARALLEL, F_NO_TARGET_PARALLEL, F_STAGED_ROWS, F_PLAIN_STORES = \
-    1, 2, 8, 32, 64, 128, 256, 512
+F_NO_UPDATES, F_NO_NARROW, F_ONE_WARP, F_NARROW, F_TARGET_PARALLEL, F_NO_TARGET_PARALLEL, F_STAGED_ROWS, F_PLAIN_STORES, F_SMEM_NEG_TABLE = \
+    1, 2, 8, 32, 64, 128, 256, 512, 1024
 COMM_ID_BYTES = 128
 
 class DgeError(RuntimeError):

@@ -471,10 +471,16 @@ __device__ __forceinline__ void stcg4_if(uint64_t p, const float4 &v, bool pred)
 }
 __device__ __forceinline__ float4 add4(const float4 &a, const float4 &b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-template <int G, bool MULTI, bool PLAIN>
-__global__ void __launch_bounds__(128, 5)
+// MODE 2 (DGE_SGNS_F_SMEM_NEG_TABLE; vocabularies below 65 536 words): ONE block of 640 threads per SM instead of five of
+// 128, and the unigram^0.75 negative table lives in its shared memory as 16-bit entries (100 000 x 2 bytes), so the five
+// table lookups of a pair are LDS instead of five scattered 4-byte global loads through the same LSU path the row loads
+// and reductions need.
+template <int G, bool MULTI, int MODE>
+__global__ void __launch_bounds__(MODE == 2 ? 640 : 128, MODE == 2 ? 1 : 5)
 k_sgns_items_v2(const sgns_args a) {
     static_assert(G == 8 || G == 16 || G == 32, "lane groups of 8, 16 or 32");
+    constexpr bool PLAIN = MODE == 1;
+    constexpr bool SMEM_NEG = MODE == 2;
     extern __shared__ int32_t smem[];
     float *s_exp = reinterpret_cast<float *>(smem);
     constexpr unsigned FULL = 0xffffffffu;
@@ -484,7 +490,10 @@ k_sgns_items_v2(const sgns_args a) {
     const int lane = threadIdx.x % G;
     const int gw = (threadIdx.x & 31) / G;
     int32_t *mytok = smem + a.exp_table_size + (threadIdx.x / G) * a.Lmax;
+    uint16_t *s_neg = reinterpret_cast<uint16_t *>(smem + a.exp_table_size + (blockDim.x / G) * a.Lmax);
     for (int i = threadIdx.x; i < a.exp_table_size; i += blockDim.x) s_exp[i] = a.exp_table[i];
+    if (SMEM_NEG)
+        for (int i = threadIdx.x; i < a.neg_table_size; i += blockDim.x) s_neg[i] = (uint16_t)a.neg_table[i]; // V <= 65535 (host)
     __syncthreads();
     const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int E = a.exp_table_size;
@@ -561,7 +570,7 @@ k_sgns_items_v2(const sgns_args a) {
                 const int kc = drawer ? kk : 0;
                 t.nsk = a.lcg_a[kc] * ns0 + a.lcg_c[kc]; // the LCG is affine: state after kk+1 steps
                 t.traw = -2;                             // "draws nothing"
-                if (drawer && t.act) t.traw = a.neg_table[mod48(t.nsk >> 16, tsize, inv_tsize)];
+                if (drawer && t.act) t.traw = SMEM_NEG ? (int32_t)s_neg[mod48(t.nsk >> 16, tsize, inv_tsize)] : a.neg_table[mod48(t.nsk >> 16, tsize, inv_tsize)];
                 if (MULTI) { if (++jT == NCH) { jT = 0; cT++; } }
                 else cT++;
                 return t;
@@ -1334,7 +1343,8 @@ struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq,
 // Kernel A (exact order): rows of up to 8 float4 slots are held by ONE thread; wider rows give each lane of a
 // 16- or 32-lane group one 128-bit slot (2 or 4 for rows wider than 32 slots).
 // Kernel B (items): groups of 8 / 16 / 32 lanes, one slot per lane (2 or 4 beyond 32 slots).
-static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_parallel, bool staged_rows, bool plain_stores, int blk, sgns_variant *out) {
+static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_parallel, bool staged_rows, bool plain_stores, int blk, bool smem_neg,
+                         sgns_variant *out) {
     if (n4 > 128) return false;
     sgns_kernel_t seq = nullptr, items = nullptr;
     int Gs = 1, Vs = 1;
@@ -1379,13 +1389,14 @@ static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_p
     }
     else if (n4 <= 32 && plain_stores) { // experiment: atomic-free row stores (lost updates allowed)
         code = 6;
-        if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true, true> : k_sgns_items_v2<8, false, true>; }
-        else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v2<16, true, true> : k_sgns_items_v2<16, false, true>; }
-        else { Gi = 32; items = multi ? k_sgns_items_v2<32, true, true> : k_sgns_items_v2<32, false, true>; }
+        if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true, 1> : k_sgns_items_v2<8, false, 1>; }
+        else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v2<16, true, 1> : k_sgns_items_v2<16, false, 1>; }
+        else { Gi = 32; items = multi ? k_sgns_items_v2<32, true, 1> : k_sgns_items_v2<32, false, 1>; }
     }
-    else if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true, false> : k_sgns_items_v2<8, false, false>; }
-    else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v2<16, true, false> : k_sgns_items_v2<16, false, false>; }
-    else if (n4 <= 32) { Gi = 32; items = multi ? k_sgns_items_v2<32, true, false> : k_sgns_items_v2<32, false, false>; }
+    else if (n4 <= 8 && smem_neg) { Gi = 8; code = 7; items = multi ? k_sgns_items_v2<8, true, 2> : k_sgns_items_v2<8, false, 2>; }
+    else if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true, 0> : k_sgns_items_v2<8, false, 0>; }
+    else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v2<16, true, 0> : k_sgns_items_v2<16, false, 0>; }
+    else if (n4 <= 32) { Gi = 32; items = multi ? k_sgns_items_v2<32, true, 0> : k_sgns_items_v2<32, false, 0>; }
     else if (n4 <= 64) { Gi = 32; Vi = 2; code = 1; items = k_sgns_items<32, 2>; }
     else { Gi = 32; Vi = 4; code = 1; items = k_sgns_items<32, 4>; }
     out->G_seq = Gs; out->VPL_seq = Vs; out->seq = seq;
@@ -1656,7 +1667,9 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             const bool narrow = (dbg & 32) || (!(dbg & 2) && allowed >= (int64_t)ctx->sm_count * 4 * 32);
             // fewer pairs in flight than the 8-lane kernel needs to fill the GPU (5 blocks x 16 groups per SM): latency-bound
             const bool tp = (dbg & 64) || (!(dbg & (128 | 32)) && allowed < (int64_t)ctx->sm_count * 5 * 16);
-            pick_variant(n4, p->negative, narrow, tp, (dbg & 256) != 0, (dbg & 512) != 0, (dbg >> 12) & 15, &var); // n4 <= 128 was checked
+            // negative table in shared memory (16-bit entries): vocabularies below 65 536 words and a table that fits beside the rest
+            const bool smem_neg = (dbg & 1024) != 0 && V <= 65535 && p->neg_table_size <= 100000;
+            pick_variant(n4, p->negative, narrow, tp, (dbg & 256) != 0, (dbg & 512) != 0, (dbg >> 12) & 15, smem_neg, &var); // n4 <= 128 was checked
         }
         sgns_kernel_t fn = sequential ? var.seq : var.items;
         const int G = sequential ? var.G_seq : var.G_items;
@@ -1665,12 +1678,14 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             la = la * LCG_MUL; lc = lc * LCG_MUL + LCG_ADD;
             a.lcg_a[k] = la; a.lcg_c[k] = lc;
         }
-        int threads = 128;
+        const bool big_block = !sequential && var.items_code == 7;   // one 640-thread block per SM, negative table in its shared memory
+        int threads = big_block ? 640 : 128;
         int gpb = threads / G;
         // dynamic shared memory: the sigmoid table, plus (pipelined item kernel) one staged sentence per group
         auto smem_for = [&](int thr) {
             return sizeof(float) * (size_t)p->exp_table_size + (sequential ? 0 : sizeof(int32_t) * (size_t)(thr / G) * (size_t)Lmax) +
-                   (!sequential && var.items_code == 5 ? (size_t)thr * 2 * (SGNS_CH + 1) * 16 : 0); // kernel C': two row stages per lane
+                   (!sequential && var.items_code == 5 ? (size_t)thr * 2 * (SGNS_CH + 1) * 16 : 0) + // kernel C': two row stages per lane
+                   (big_block ? (((size_t)p->neg_table_size * 2 + 15) / 16) * 16 : 0);
         };
         size_t smem = smem_for(threads);
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1685,7 +1700,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         else want = std::min<int64_t>(full_groups, std::max<int64_t>(gpb, (int64_t)SGNS_STALE_BOUND * V / (p->negative + 1)));
         if (!sequential && (dbg & 8)) want = 1; // one warp, one item at a time, strictly in corpus order (arithmetic check against the oracle)
         want = std::max<int64_t>(1, std::min(want, units));
-        while (threads > 32 && threads > G && want < (int64_t)ctx->sm_count * gpb) { threads >>= 1; gpb = threads / G; }
+        while (!big_block && threads > 32 && threads > G && want < (int64_t)ctx->sm_count * gpb) { threads >>= 1; gpb = threads / G; }
         if (sequential && want < gpb) { gpb = (int)want; threads = gpb * G; } // kernel B keeps whole warps
         int blocks = (int)((want + gpb - 1) / gpb);
         a.n_groups = (int64_t)blocks * gpb;

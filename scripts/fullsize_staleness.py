@@ -1,0 +1,60 @@
+"""How many (sentence, centre) items may be in flight before the skip-gram embedding drifts away from the oracle's?
+Full bench size (tract x 24: 15M flow + 600K spatial walks, D=20, window=24, K=5), judged against the committed oracle
+fixture (tests/golden/fullsize_tract24_oracle*.json/.npz): nDCG@k and the agreement of the 10 nearest neighbours with oracle
+run 0 (the other oracle runs agree with it to ~0.88).
+
+    python scripts/fullsize_staleness.py [conc,conc,...] [flags]
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from embedding_b200 import abi, evaluation as ev, synth  # noqa: E402
+
+
+def main():
+    concs = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "0,256,128,64,32,16").split(",")]
+    flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    G = os.path.join(ROOT, "tests", "golden")
+    fx = json.load(open(os.path.join(G, "fullsize_tract24_oracle.json")))
+    ref = np.load(os.path.join(G, "fullsize_tract24_oracle_knn.npz"))["knn"]
+    w = bench.make_workload("tract24")
+    f, sp, L = w["flow"], w["spatial"], w["L"]
+    ctx = abi.Context(0)
+    Gf = abi.Graph(ctx, f["nv"], f["src"], f["dst"], f["w"], f["sources"])
+    S = abi.Graph(ctx, sp["nv"], sp["src"], sp["dst"], sp["w"], sp["sources"], out_degree=sp["out_degree"], source_weight_sum=sp["sws"])
+    c1, c2 = Gf.walk(f["n_walks"], L, seed=2013), S.walk(sp["n_walks"], L, seed=2014)
+    c1.relabel(f["id_map"], w["n_ids"], 0)
+    c2.relabel(sp["id_map"], w["n_ids"], w["n_regions"])
+    gt = ev.PairwiseGroundTruth(synth.tract_ids(), synth.poi_latents())
+    n = w["n_regions"]
+    idx = np.arange(w["n_ids"])
+    vl, vr = (idx // n).astype(np.int32), np.asarray(w["region_ids"])[idx % n]
+    print("oracle: nDCG@5 %.5f (min %.5f max %.5f); kNN agreement of oracle runs with run 0: %s" % (
+        fx["summary"]["5"]["mean"], fx["summary"]["5"]["min"], fx["summary"]["5"]["max"],
+        [round(r["knn_overlap_vs_run0"], 4) for r in fx["runs"] if r["objective"] == "ns"][1:]), flush=True)
+    out = []
+    for conc in concs:
+        m = abi.Model.train(ctx, [c1, c2], abi.sgns_params(dim=w["dim"], window=w["window"], negative=5, min_count=2, seed=1, concurrency=conc, flags=flags))
+        ms = ctx.phase_ms("sgns")
+        syn0, ids = m.vectors()
+        layers = ev.layers_from_model(syn0, ids, vl, vr)
+        nd = ev.pairwise_ndcg(gt, layers, ks=(5, 20, 50))
+        ov = ev.knn_table_overlap(ref, ev.knn_table(layers, w["region_ids"], L, 10))
+        r = dict(concurrency=conc, flags=flags, groups=ctx.phase_ms("sgns_groups"), kernel=int(ctx.phase_ms("sgns_kernel")), sgns_ms=round(ms, 1),
+                 gpairs_per_s=round(m.pairs / ms / 1e6, 3), ndcg={str(k): round(v, 5) for k, v in nd.items()}, knn_agreement_with_oracle_run0=round(ov, 4),
+                 mean_row_norm=round(float(np.linalg.norm(syn0, axis=1).mean()), 3))
+        out.append(r)
+        print(json.dumps(r), flush=True)
+        m.free()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "fullsize_staleness_f%d.json" % flags), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
