@@ -44,6 +44,7 @@ struct sgns_args {
     int64_t s_off, n_global;  // data-parallel shard: global index of local sentence 0 and the global sentence count.  RNG keys
                               // and the learning-rate schedule use GLOBAL sentence indices, so the shards of all ranks
                               // enumerate exactly the pairs and negatives of a single-GPU run over the whole corpus
+    const uint32_t *neg_bits;  // kernel F: the negative table as increment bitmap [nwords] + per-word prefix [nwords], or NULL
     uint64_t lcg_a[SGNS_MAX_NEG], lcg_c[SGNS_MAX_NEG]; // (k+1)-step jump of the negative-sampling LCG
     int32_t dbg;
 };
@@ -680,6 +681,228 @@ k_sgns_items_v2(const sgns_args a) {
         }
     }
     if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Kernel F: the SENTENCE-RESIDENT item kernel -- what the reference's semantics need on a GPU.
+//
+// Kernels B-E hand the <= 24 centre positions of ONE sentence to different lane groups that run at the same time, so
+// the ~23 updates a sentence makes to each of its context rows syn0[last] (one per centre) are all computed from
+// (nearly) the same stale value and summed: the diminishing steps of word2vec's sequential loop -- the second centre sees
+// the row the first one already moved -- are lost, and the embedding drifts systematically (at the full bench size: row
+// norms 2.5 instead of the oracle's 2.3, and only 0.66 of the oracle's 10 nearest neighbours recovered even with just 8
+// sentences in flight, while oracle runs with different seeds agree to 0.88: profiles/r2s4_fullsize_staleness_v2.json).
+//
+// Here a WARP owns a sentence for all its centres.  The warp's lane groups take the centres in batches (4 at G = 8),
+// walking the context positions STAGGERED (group g works on context position c - g), so that the pairs in flight in a
+// warp never share a row: they are a legitimate sequential order of the sentence's pairs.  What the warp has added to
+// the sentence's context rows lives in a per-warp shared-memory DELTA cache: a pair reads syn0[last] fresh from L2
+// (other sentences' updates) plus the warp's own pending delta, adds its neu1e to the cache, and the cache is flushed
+// to L2 with 128-bit reductions after every batch of centres (+ a fence, so the next batch reads them back).  The
+// centre's output row syn1neg[w1] stays private in registers for the item, as before.  L2 traffic per pair is what
+// kernel C had (one context-row load, K negative-row loads, K reductions, 1/23 flush); the negative table is read from
+// shared memory (exact bitmap + prefix form of the unigram^0.75 table, 25 KB for 100 000 slots instead of 400 KB in L2).
+__device__ __forceinline__ float sgns_g_lane(float tot, float label, float alpha, float g_hi, float g_lo, const float *s_exp,
+                                             int E, float idx_scale);
+__device__ __forceinline__ int32_t neg_lookup(const uint32_t *__restrict__ s_bits, const uint32_t *__restrict__ s_pref, uint32_t idx) {
+    // table[idx] = table[32 w] + number of increments in slots 32 w + 1 .. idx (the table never grows by more than one per slot)
+    const uint32_t w = idx >> 5, j = idx & 31u;
+    return (int32_t)(s_pref[w] + __popc(s_bits[w] & ((2u << j) - 2u)));
+}
+
+template <int G, bool MULTI>
+__global__ void __launch_bounds__(640, 1)
+k_sgns_sent(const sgns_args a) {
+    static_assert(G == 8 || G == 16 || G == 32, "lane groups of 8, 16 or 32");
+    extern __shared__ __align__(16) int32_t smem_f[];
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int GPW = 32 / G;
+    const int warps_per_block = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    const int n4 = a.n4, Lmax = a.Lmax;
+    const int nwords = (a.neg_table_size + 31) >> 5;
+    // shared memory: [delta cache of every warp: Lmax x n4 float4][sigmoid table][tokens of every warp][negative table bits | prefixes]
+    float4 *my_delta = reinterpret_cast<float4 *>(smem_f) + (size_t)wib * Lmax * n4;
+    float *s_exp = reinterpret_cast<float *>(reinterpret_cast<float4 *>(smem_f) + (size_t)warps_per_block * Lmax * n4);
+    int32_t *mytok = reinterpret_cast<int32_t *>(s_exp + a.exp_table_size) + wib * Lmax;
+    uint32_t *s_bits = reinterpret_cast<uint32_t *>(s_exp + a.exp_table_size) + warps_per_block * Lmax;
+    uint32_t *s_pref = s_bits + nwords;
+    const bool smem_neg = a.neg_bits != nullptr;
+    for (int i = threadIdx.x; i < a.exp_table_size; i += blockDim.x) s_exp[i] = a.exp_table[i];
+    if (smem_neg)
+        for (int i = threadIdx.x; i < 2 * nwords; i += blockDim.x) s_bits[i] = a.neg_bits[i];
+    __syncthreads();
+    const int gpw_eff = (a.dbg & 8) ? 1 : GPW; // test mode: one group, i.e. the oracle's exact pair order
+    const int lane = threadIdx.x % G, wl = threadIdx.x & 31;
+    const int gw = wl / G;
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int E = a.exp_table_size;
+    const float idx_scale = (float)E / SGNS_MAX_EXP / 2.0f;
+    const int win = a.window;
+    const int64_t N = a.n_sent;
+    const double inv_total = 1.0 / (double)((int64_t)a.epochs * a.n_global);
+    const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
+    const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int K = a.V >= 2 ? a.negative : 0;
+    const int NCH = MULTI ? max(1, (K + SGNS_CH - 1) / SGNS_CH) : 1;
+    const bool live = lane < n4;
+    const uint32_t pitch = (uint32_t)a.stride * 4u;
+    const char *base0 = reinterpret_cast<const char *>(a.syn0) + (live ? lane : 0) * 16;
+    const char *base1 = reinterpret_cast<const char *>(a.syn1neg) + (live ? lane : 0) * 16;
+    const int L8 = lane & 7;
+    const bool up4 = (lane & 4) != 0, up2 = (lane & 2) != 0, up1 = (lane & 1) != 0;
+    const float my_label = L8 == SGNS_CH ? 1.f : 0.f;
+    const bool reds_on = !(a.dbg & 1);
+    unsigned long long pairs = 0;
+
+    struct stage_t { int32_t last; bool act; uint64_t nsk; int32_t traw; int j; int c; };
+    struct stage_r { int32_t last; bool act; int j; int c; int32_t mine; int32_t tg[SGNS_CH]; float4 row[SGNS_CH]; float4 v0; };
+
+    for (int ep = a.ep_lo; ep < a.ep_hi; ep++) {
+        for (int64_t s = a.s_lo + warp_id; s < a.s_hi; s += a.n_groups) { // n_groups = warps = sentences in flight
+            __syncwarp();
+            int n_tok = 0;
+            for (int j = wl; j < Lmax; j += 32) { const int32_t tk = a.wtok[(int64_t)j * N + s]; mytok[j] = tk; n_tok += tk >= 0; }
+            for (int q = wl; q < Lmax * n4; q += 32) my_delta[q] = zero4;
+            __syncwarp();
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) n_tok += __shfl_xor_sync(FULL, n_tok, o);
+            if (n_tok < 2) continue;
+            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * a.n_global + a.s_off + s) * inv_total);
+            if (alpha < a.min_lr) alpha = a.min_lr;
+            const float g_hi = (my_label - 1.f) * alpha, g_lo = my_label * alpha;
+            const uint64_t S = sgns_sentence_rng(a.seed, ep, s + a.s_off);
+            int npairs = 0;
+            for (int i0 = 0; i0 < n_tok; i0 += gpw_eff) { // a batch of centres: one per lane group
+                const int i = i0 + gw;
+                const bool valid = gw < gpw_eff && i < n_tok;
+                const int32_t w1 = valid ? mytok[i] : 0;
+                const int b = (int32_t)(uint32_t)sgns_position_rng(S, valid ? i : 0) % win;
+                const int lo = valid ? i - win + b : 1, hi = valid ? i + win - b : 0; // inclusive context range; empty if invalid
+                const int c_min = __reduce_min_sync(FULL, valid ? max(lo, 0) : Lmax);
+                const int c_max = __reduce_max_sync(FULL, valid ? min(hi, n_tok - 1) : -1);
+                if (c_max < c_min) continue;
+                float4 cur = zero4, d1 = zero4, neu = zero4, v0p = zero4;
+                ldcg4_into(cur, row_addr(base1, (uint32_t)w1, pitch), valid && live); // private copy of syn1neg[w1]
+                // unit u of the batch: group g works on context position c_min + u - g (staggered: no two groups on one row)
+                int uT = 0, jT = 0;
+                uint64_t hc = 0;
+                int hcb = -1;
+
+                auto stageT = [&]() {
+                    stage_t t;
+                    t.j = jT;
+                    t.c = c_min + uT - gw;
+                    const bool in_row = t.c >= 0 && t.c < Lmax;
+                    t.last = in_row ? mytok[t.c] : -1;
+                    t.act = valid && in_row && t.c >= lo && t.c <= hi && t.c != i && t.last >= 0 && t.last != w1;
+                    const int cc = in_row ? t.c : 0;
+                    if (cc / G != hcb) { hcb = cc / G; hc = sgns_pair_rng(S, i, hcb * G + lane); } // per group
+                    const uint64_t ns0 = shfl64(hc, cc & (G - 1), G);
+                    const int kk = jT * SGNS_CH + lane;
+                    const bool drawer = lane < SGNS_CH && kk < K;
+                    const int kc = drawer ? kk : 0;
+                    t.nsk = a.lcg_a[kc] * ns0 + a.lcg_c[kc];
+                    t.traw = -2;
+                    if (drawer && t.act) {
+                        const uint32_t idx = mod48(t.nsk >> 16, tsize, inv_tsize);
+                        t.traw = smem_neg ? neg_lookup(s_bits, s_pref, idx) : a.neg_table[idx];
+                    }
+                    if (MULTI) { if (++jT == NCH) { jT = 0; uT++; } }
+                    else uT++;
+                    return t;
+                };
+                auto stageR = [&](const stage_t &t, stage_r &r) {
+                    r.last = t.last; r.act = t.act; r.j = t.j; r.c = t.c;
+                    int32_t tt = t.traw;
+                    const bool redraw = tt != -2 && (tt <= 0 || tt >= a.V);
+                    if (__any_sync(FULL, redraw)) {
+                        if (redraw) tt = (int32_t)mod64(t.nsk, vm1, inv_vm1) + 1;
+                    }
+                    r.mine = (tt != -2 && tt != w1) ? tt : -1;
+#pragma unroll
+                    for (int k = 0; k < SGNS_CH; k++) r.tg[k] = __shfl_sync(FULL, r.mine, k, G);
+                    if (!MULTI || t.j == 0) ldcg4_into(r.v0, row_addr(base0, (uint32_t)t.last, pitch), t.act && live);
+#pragma unroll
+                    for (int k = 0; k < SGNS_CH; k++) ldcg4_into(r.row[k], row_addr(base1, (uint32_t)r.tg[k], pitch), r.tg[k] >= 0 && live);
+                };
+                auto compute = [&](const stage_r &r) {
+                    if (!__any_sync(FULL, r.act)) return;
+                    const bool first = !MULTI || r.j == 0;
+                    if (first) {
+                        npairs += r.act;
+                        neu = zero4;
+                        // the row as this sentence sees it: L2's value + what this warp has added since its last flush
+                        v0p = r.v0;
+                        if (r.act && live) { const float4 dl = my_delta[r.c * n4 + lane]; v0p.x += dl.x; v0p.y += dl.y; v0p.z += dl.z; v0p.w += dl.w; }
+                    }
+                    const float4 v0 = v0p;
+                    float d0 = dot4(v0, r.row[0]), d1v = dot4(v0, r.row[1]), d2 = dot4(v0, r.row[2]), d3 = dot4(v0, r.row[3]);
+                    float d4 = dot4(v0, r.row[4]), d5 = first ? dot4(v0, cur) : 0.f;
+                    float e0 = (up4 ? d4 : d0) + __shfl_xor_sync(FULL, up4 ? d0 : d4, 4);
+                    float e1 = (up4 ? d5 : d1v) + __shfl_xor_sync(FULL, up4 ? d1v : d5, 4);
+                    float e2 = (up4 ? 0.f : d2) + __shfl_xor_sync(FULL, up4 ? d2 : 0.f, 4);
+                    float e3 = (up4 ? 0.f : d3) + __shfl_xor_sync(FULL, up4 ? d3 : 0.f, 4);
+                    float f0 = (up2 ? e2 : e0) + __shfl_xor_sync(FULL, up2 ? e0 : e2, 2);
+                    float f1 = (up2 ? e3 : e1) + __shfl_xor_sync(FULL, up2 ? e1 : e3, 2);
+                    float tot = (up1 ? f1 : f0) + __shfl_xor_sync(FULL, up1 ? f0 : f1, 1);
+                    if (G >= 16) tot += __shfl_xor_sync(FULL, tot, 8);
+                    if (G >= 32) tot += __shfl_xor_sync(FULL, tot, 16);
+                    float g = sgns_g_lane(tot, my_label, alpha, g_hi, g_lo, s_exp, E, idx_scale);
+                    {
+                        const bool mine_ok = L8 < SGNS_CH ? r.mine >= 0 : (L8 == SGNS_CH && r.act && first);
+                        if (!mine_ok) g = 0.f;
+                    }
+                    float gk[SGNS_CH + 1];
+#pragma unroll
+                    for (int k = 0; k < SGNS_CH; k++) gk[k] = __shfl_sync(FULL, g, k, G);
+                    gk[SGNS_CH] = first ? __shfl_sync(FULL, g, SGNS_CH, G) : 0.f;
+#pragma unroll
+                    for (int k = 0; k < SGNS_CH; k++) {
+                        axpy4(neu, gk[k], r.row[k]);
+                        red_add4_if(row_addr(base1, (uint32_t)r.tg[k], pitch), scale4(gk[k], v0), gk[k] != 0.f && live && reds_on);
+                    }
+                    if (first) {
+                        axpy4(neu, gk[SGNS_CH], cur);
+                        axpy4(d1, gk[SGNS_CH], v0);
+                        axpy4(cur, gk[SGNS_CH], v0);
+                    }
+                    if ((!MULTI || r.j == NCH - 1) && r.act && live) { // the pair is complete: syn0[last] += neu, kept in the warp's cache
+                        float4 dl = my_delta[r.c * n4 + lane];
+                        dl.x += neu.x; dl.y += neu.y; dl.z += neu.z; dl.w += neu.w;
+                        my_delta[r.c * n4 + lane] = dl;
+                    }
+                };
+
+                const int U = (c_max - c_min + 1 + (gpw_eff - 1)) * NCH;
+                stage_r rA;
+                rA.v0 = zero4;
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) rA.row[k] = zero4;
+                stage_t t1 = stageT();
+                for (int u = 0; u < U; u++) {
+                    stageR(t1, rA);
+                    t1 = stageT();
+                    compute(rA);
+                    __syncwarp(); // the cache rows written in this unit are read by other groups in later units
+                }
+                red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, valid && live && reds_on);
+                // flush the warp's pending context-row updates: one 128-bit reduction per slot that moved
+                for (int q = wl; q < n_tok * n4; q += 32) {
+                    const float4 dl = my_delta[q];
+                    const int row = q / n4, slot = q - row * n4;
+                    if (dl.x != 0.f || dl.y != 0.f || dl.z != 0.f || dl.w != 0.f) {
+                        if (reds_on) red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)mytok[row] * a.stride) + slot, dl);
+                        my_delta[q] = zero4;
+                    }
+                }
+                __threadfence(); // the next batch re-reads these rows from L2
+                __syncwarp();
+            }
+            pairs += (unsigned)npairs;
+        }
+    }
+    if ((threadIdx.x % G) == 0 && pairs) atomicAdd(a.pairs, pairs);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1344,7 +1567,7 @@ struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq,
 // 16- or 32-lane group one 128-bit slot (2 or 4 for rows wider than 32 slots).
 // Kernel B (items): groups of 8 / 16 / 32 lanes, one slot per lane (2 or 4 beyond 32 slots).
 static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_parallel, bool staged_rows, bool plain_stores, int blk, bool smem_neg,
-                         sgns_variant *out) {
+                         bool sentence_resident, sgns_variant *out) {
     if (n4 > 128) return false;
     sgns_kernel_t seq = nullptr, items = nullptr;
     int Gs = 1, Vs = 1;
@@ -1392,6 +1615,12 @@ static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_p
         if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true, 1> : k_sgns_items_v2<8, false, 1>; }
         else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v2<16, true, 1> : k_sgns_items_v2<16, false, 1>; }
         else { Gi = 32; items = multi ? k_sgns_items_v2<32, true, 1> : k_sgns_items_v2<32, false, 1>; }
+    }
+    else if (n4 <= 32 && sentence_resident) { // kernel F: a warp owns a sentence (intra-sentence updates in sequence)
+        code = 8;
+        if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_sent<8, true> : k_sgns_sent<8, false>; }
+        else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_sent<16, true> : k_sgns_sent<16, false>; }
+        else { Gi = 32; items = multi ? k_sgns_sent<32, true> : k_sgns_sent<32, false>; }
     }
     else if (n4 <= 8 && smem_neg) { Gi = 8; code = 7; items = multi ? k_sgns_items_v2<8, true, 2> : k_sgns_items_v2<8, false, 2>; }
     else if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true, 0> : k_sgns_items_v2<8, false, 0>; }
@@ -1669,7 +1898,10 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             const bool tp = (dbg & 64) || (!(dbg & (128 | 32)) && allowed < (int64_t)ctx->sm_count * 5 * 16);
             // negative table in shared memory (16-bit entries): vocabularies below 65 536 words and a table that fits beside the rest
             const bool smem_neg = (dbg & 1024) != 0 && V <= 65535 && p->neg_table_size <= 100000;
-            pick_variant(n4, p->negative, narrow, tp, (dbg & 256) != 0, (dbg & 512) != 0, (dbg >> 12) & 15, smem_neg, &var); // n4 <= 128 was checked
+            // kernel F (sentence-resident) is the rule for rows of up to 32 slots; the item kernels B-E remain for A/B (flag) and wider rows
+            const bool forced_other = (dbg & (32 | 64 | 256 | 512 | 1024)) != 0;
+            const bool sent = (dbg & 2048) != 0;
+            pick_variant(n4, p->negative, narrow, tp, (dbg & 256) != 0, (dbg & 512) != 0, (dbg >> 12) & 15, smem_neg, sent && !forced_other, &var); // n4 <= 128 was checked
         }
         sgns_kernel_t fn = sequential ? var.seq : var.items;
         const int G = sequential ? var.G_seq : var.G_items;
@@ -1678,33 +1910,63 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             la = la * LCG_MUL; lc = lc * LCG_MUL + LCG_ADD;
             a.lcg_a[k] = la; a.lcg_c[k] = lc;
         }
-        const bool big_block = !sequential && var.items_code == 7;   // one 640-thread block per SM, negative table in its shared memory
+        const bool sent_kernel = !sequential && var.items_code == 8;     // kernel F: a.n_groups counts WARPS (sentences in flight)
+        // negative table in shared memory as increment bitmap + per-word prefix (kernel F, narrow rows): exact iff the table never
+        // grows by more than one word per slot, which its construction guarantees; checked all the same
+        uint32_t *d_negbits = nullptr;
+        const int nwords = (p->neg_table_size + 31) / 32;
+        if (sent_kernel && n4 <= 8) {
+            std::vector<uint32_t> nb((size_t)2 * nwords, 0u);
+            bool exact = true;
+            for (int32_t i = 0; i < p->neg_table_size; i++) {
+                if ((i & 31) == 0) nb[(size_t)nwords + (i >> 5)] = (uint32_t)table[i];
+                else {
+                    const int32_t inc = table[i] - table[i - 1];
+                    if (inc == 1) nb[i >> 5] |= 1u << (i & 31);
+                    else if (inc != 0) exact = false;
+                }
+            }
+            if (exact && tmp.get(&d_negbits, (size_t)2 * nwords) == cudaSuccess)
+                cudaMemcpyAsync(d_negbits, nb.data(), sizeof(uint32_t) * nb.size(), cudaMemcpyHostToDevice, st);
+            else d_negbits = nullptr;
+            cudaStreamSynchronize(st);   // nb goes out of scope
+        }
+        a.neg_bits = d_negbits;
+        const bool big_block = !sequential && (var.items_code == 7 || (sent_kernel && n4 <= 8 && !(dbg & 16))); // one 640-thread block per SM
         int threads = big_block ? 640 : 128;
         int gpb = threads / G;
         // dynamic shared memory: the sigmoid table, plus (pipelined item kernel) one staged sentence per group
         auto smem_for = [&](int thr) {
+            if (sent_kernel)
+                return (size_t)(thr / 32) * (size_t)Lmax * (size_t)n4 * 16 + sizeof(float) * (size_t)p->exp_table_size +
+                       sizeof(int32_t) * (size_t)(thr / 32) * (size_t)Lmax + (d_negbits ? sizeof(uint32_t) * (size_t)2 * nwords : 0);
             return sizeof(float) * (size_t)p->exp_table_size + (sequential ? 0 : sizeof(int32_t) * (size_t)(thr / G) * (size_t)Lmax) +
                    (!sequential && var.items_code == 5 ? (size_t)thr * 2 * (SGNS_CH + 1) * 16 : 0) + // kernel C': two row stages per lane
-                   (big_block ? (((size_t)p->neg_table_size * 2 + 15) / 16) * 16 : 0);
+                   (var.items_code == 7 ? (((size_t)p->neg_table_size * 2 + 15) / 16) * 16 : 0);
         };
         size_t smem = smem_for(threads);
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
         if (per_sm < 1) per_sm = 1;
+        const int GPW = 32 / G;
         const int64_t full_groups = (int64_t)ctx->sm_count * per_sm * gpb;
         const int64_t units = sequential ? std::max<int64_t>(1, n_sent) : std::max<int64_t>(1, n_sent * (int64_t)Lmax);
         int64_t want;
-        if (p->concurrency > 0) want = sequential ? (int64_t)p->concurrency : (int64_t)p->concurrency * Lmax;
+        if (p->concurrency > 0) want = sequential ? (int64_t)p->concurrency : (int64_t)p->concurrency * (sent_kernel ? GPW : Lmax);
         else if (sequential) want = full_groups;
         else want = std::min<int64_t>(full_groups, std::max<int64_t>(gpb, (int64_t)SGNS_STALE_BOUND * V / (p->negative + 1)));
         if (!sequential && (dbg & 8)) want = 1; // one warp, one item at a time, strictly in corpus order (arithmetic check against the oracle)
-        want = std::max<int64_t>(1, std::min(want, units));
+        want = std::max<int64_t>(1, std::min(want, sent_kernel ? std::max<int64_t>(1, n_sent) * GPW : units));
         while (!big_block && threads > 32 && threads > G && want < (int64_t)ctx->sm_count * gpb) { threads >>= 1; gpb = threads / G; }
         if (sequential && want < gpb) { gpb = (int)want; threads = gpb * G; } // kernel B keeps whole warps
         int blocks = (int)((want + gpb - 1) / gpb);
         a.n_groups = (int64_t)blocks * gpb;
         if (!sequential && (dbg & 8)) a.n_groups = 1; // the single warp advances one item at a time
+        if (sent_kernel) { // groups in flight -> warps (= sentences) in flight
+            a.n_groups = std::max<int64_t>(1, ((int64_t)blocks * gpb) / GPW);
+            if (dbg & 8) { a.n_groups = 1; blocks = 1; threads = 32; }
+        }
         ctx->phase_ms["sgns_groups"] = (float)a.n_groups;
         ctx->phase_ms["sgns_kernel"] = (float)(sequential ? 0 : var.items_code);
         // ---- launches.  Single GPU: one launch over all epochs and sentences.  Data-parallel (the ctx has a

@@ -125,6 +125,8 @@ def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negati
         if negative <= 7:
             flag_sets.append(L.F_ONE_WARP | L.F_TARGET_PARALLEL)     # the target-parallel kernel (D <= 16, K <= 7)
     if dim <= 128:
+        flag_sets.append(L.F_ONE_WARP | L.F_SENTENCE_RESIDENT)       # kernel F on one lane group: the oracle's exact pair order
+        flag_sets.append(L.F_ONE_WARP | L.F_SENTENCE_RESIDENT | L.F_SMALL_BLOCKS)
         flag_sets.append(L.F_ONE_WARP | L.F_STAGED_ROWS)             # kernel C': rows staged in shared memory by cp.async
         flag_sets.append(L.F_ONE_WARP | L.F_PLAIN_STORES)            # atomic-free build: one item at a time loses no update
     for flags in flag_sets:
