@@ -906,6 +906,203 @@ k_sgns_sent(const sgns_args a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Kernel G: kernel F's semantics with the parallelism INSIDE the sentence.  Parity bounds the number of sentences in
+// flight (a few hundred on a 19 K-word vocabulary: profiles/r2s5_fullsize_staleness_kernelF.json), and one warp per
+// sentence then leaves the GPU nearly empty.  But a sentence of n tokens is n centres x n contexts, and a round-robin
+// schedule makes n of its pairs independent at a time: in round r, the lane group of centre i takes context
+// (i + r) mod n -- all centres distinct (each group keeps its centre's output row in registers, as before), all
+// contexts distinct (each context row's pending delta has one writer per round).  So a BLOCK owns a sentence, one lane
+// group per centre position (6 warps for 24 positions at G = 8), n - 1 rounds with a block barrier in between; every
+// pair still reads syn0[last] fresh from L2 plus the block's own pending delta from shared memory, and the sentence's
+// deltas are flushed with 128-bit reductions once, at its end.  The pairs of a sentence are applied in a different
+// order than the oracle's centre-major loop, but in AN order: no two pairs in flight share a row of the sentence.
+template <int G, bool MULTI>
+__global__ void __launch_bounds__(256, 3)
+k_sgns_block(const sgns_args a) {
+    static_assert(G == 8 || G == 16 || G == 32, "lane groups of 8, 16 or 32");
+    extern __shared__ __align__(16) int32_t smem_g[];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int n4 = a.n4, Lmax = a.Lmax;
+    const int nwords = (a.neg_table_size + 31) >> 5;
+    float4 *delta = reinterpret_cast<float4 *>(smem_g);                       // [Lmax][n4]
+    float *s_exp = reinterpret_cast<float *>(delta + (size_t)Lmax * n4);
+    int32_t *tok = reinterpret_cast<int32_t *>(s_exp + a.exp_table_size);
+    uint32_t *s_bits = reinterpret_cast<uint32_t *>(tok + Lmax);
+    uint32_t *s_pref = s_bits + nwords;
+    const bool smem_neg = a.neg_bits != nullptr;
+    for (int q = threadIdx.x; q < a.exp_table_size; q += blockDim.x) s_exp[q] = a.exp_table[q];
+    if (smem_neg)
+        for (int q = threadIdx.x; q < 2 * nwords; q += blockDim.x) s_bits[q] = a.neg_bits[q];
+    const int lane = threadIdx.x % G;
+    const int i = threadIdx.x / G;          // this lane group's centre position, for every sentence of the block
+    const int E = a.exp_table_size;
+    const float idx_scale = (float)E / SGNS_MAX_EXP / 2.0f;
+    const int win = a.window;
+    const int64_t N = a.n_sent;
+    const double inv_total = 1.0 / (double)((int64_t)a.epochs * a.n_global);
+    const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
+    const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int K = a.V >= 2 ? a.negative : 0;
+    const int NCH = MULTI ? max(1, (K + SGNS_CH - 1) / SGNS_CH) : 1;
+    const bool live = lane < n4;
+    const uint32_t pitch = (uint32_t)a.stride * 4u;
+    const char *base0 = reinterpret_cast<const char *>(a.syn0) + (live ? lane : 0) * 16;
+    const char *base1 = reinterpret_cast<const char *>(a.syn1neg) + (live ? lane : 0) * 16;
+    const int L8 = lane & 7;
+    const bool up4 = (lane & 4) != 0, up2 = (lane & 2) != 0, up1 = (lane & 1) != 0;
+    const float my_label = L8 == SGNS_CH ? 1.f : 0.f;
+    const bool reds_on = !(a.dbg & 1);
+    unsigned long long pairs = 0;
+
+    struct stage_t { int32_t last; bool act; uint64_t nsk; int32_t traw; int j; int c; };
+    struct stage_r { int32_t last; bool act; int j; int c; int32_t mine; int32_t tg[SGNS_CH]; float4 row[SGNS_CH]; float4 v0; };
+
+    for (int ep = a.ep_lo; ep < a.ep_hi; ep++) {
+        for (int64_t s = a.s_lo + blockIdx.x; s < a.s_hi; s += a.n_groups) { // n_groups = blocks = sentences in flight
+            __syncthreads(); // the previous sentence's flush has read the delta cache
+            int32_t tk = -1;
+            if ((int)threadIdx.x < Lmax) { tk = a.wtok[(int64_t)threadIdx.x * N + s]; tok[threadIdx.x] = tk; }
+            for (int q = threadIdx.x; q < Lmax * n4; q += blockDim.x) delta[q] = zero4;
+            const int n_tok = __syncthreads_count(tk >= 0); // the compacted sentence: tokens first, then padding
+            if (n_tok < 2) continue;
+            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * a.n_global + a.s_off + s) * inv_total);
+            if (alpha < a.min_lr) alpha = a.min_lr;
+            const float g_hi = (my_label - 1.f) * alpha, g_lo = my_label * alpha;
+            const uint64_t S = sgns_sentence_rng(a.seed, ep, s + a.s_off);
+            const bool valid = i < n_tok;
+            const int32_t w1 = valid ? tok[i] : 0;
+            const int b = (int32_t)(uint32_t)sgns_position_rng(S, valid ? i : 0) % win;
+            const int lo = valid ? i - win + b : 1, hi = valid ? i + win - b : 0; // inclusive context range; empty if invalid
+            float4 cur = zero4, d1 = zero4, neu = zero4, v0p = zero4;
+            ldcg4_into(cur, row_addr(base1, (uint32_t)w1, pitch), valid && live); // private copy of syn1neg[w1]
+            int npairs = 0;
+            int rT = 1, jT = 0; // (round, chunk) of the next unit the T stage hands out
+            uint64_t hc = 0;
+            int hcb = -1;
+            // rounds in which nobody can be active (both cyclic distances beyond the window) are skipped by every thread alike
+            auto skip_dead_rounds = [&]() { while (rT < n_tok && min(rT, n_tok - rT) > win) rT++; };
+            skip_dead_rounds();
+
+            auto stageT = [&]() {
+                stage_t t;
+                t.j = jT;
+                int c = i + rT;
+                if (c >= n_tok) c -= n_tok;
+                const bool in_round = valid && rT < n_tok;
+                t.c = in_round ? c : 0;
+                t.last = in_round ? tok[t.c] : -1;
+                t.act = in_round && t.c >= lo && t.c <= hi && t.last >= 0 && t.last != w1;
+                if (t.c / G != hcb) { hcb = t.c / G; hc = sgns_pair_rng(S, i, hcb * G + lane); }
+                const uint64_t ns0 = shfl64(hc, t.c & (G - 1), G);
+                const int kk = jT * SGNS_CH + lane;
+                const bool drawer = lane < SGNS_CH && kk < K;
+                const int kc = drawer ? kk : 0;
+                t.nsk = a.lcg_a[kc] * ns0 + a.lcg_c[kc];
+                t.traw = -2;
+                if (drawer && t.act) {
+                    const uint32_t idx = mod48(t.nsk >> 16, tsize, inv_tsize);
+                    t.traw = smem_neg ? neg_lookup(s_bits, s_pref, idx) : a.neg_table[idx];
+                }
+                if (MULTI) { if (++jT == NCH) { jT = 0; rT++; skip_dead_rounds(); } }
+                else { rT++; skip_dead_rounds(); }
+                return t;
+            };
+            auto stageR = [&](const stage_t &t, stage_r &r) {
+                r.last = t.last; r.act = t.act; r.j = t.j; r.c = t.c;
+                int32_t tt = t.traw;
+                const bool redraw = tt != -2 && (tt <= 0 || tt >= a.V);
+                if (__any_sync(FULL, redraw)) {
+                    if (redraw) tt = (int32_t)mod64(t.nsk, vm1, inv_vm1) + 1;
+                }
+                r.mine = (tt != -2 && tt != w1) ? tt : -1;
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) r.tg[k] = __shfl_sync(FULL, r.mine, k, G);
+                if (!MULTI || t.j == 0) ldcg4_into(r.v0, row_addr(base0, (uint32_t)t.last, pitch), t.act && live);
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) ldcg4_into(r.row[k], row_addr(base1, (uint32_t)r.tg[k], pitch), r.tg[k] >= 0 && live);
+            };
+            auto compute = [&](const stage_r &r) {
+                if (!__any_sync(FULL, r.act)) return;
+                const bool first = !MULTI || r.j == 0;
+                if (first) {
+                    npairs += r.act;
+                    neu = zero4;
+                    v0p = r.v0; // L2's value + what this sentence has added to the row so far
+                    if (r.act && live) { const float4 dl = delta[r.c * n4 + lane]; v0p.x += dl.x; v0p.y += dl.y; v0p.z += dl.z; v0p.w += dl.w; }
+                }
+                const float4 v0 = v0p;
+                float d0 = dot4(v0, r.row[0]), d1v = dot4(v0, r.row[1]), d2 = dot4(v0, r.row[2]), d3 = dot4(v0, r.row[3]);
+                float d4 = dot4(v0, r.row[4]), d5 = first ? dot4(v0, cur) : 0.f;
+                float e0 = (up4 ? d4 : d0) + __shfl_xor_sync(FULL, up4 ? d0 : d4, 4);
+                float e1 = (up4 ? d5 : d1v) + __shfl_xor_sync(FULL, up4 ? d1v : d5, 4);
+                float e2 = (up4 ? 0.f : d2) + __shfl_xor_sync(FULL, up4 ? d2 : 0.f, 4);
+                float e3 = (up4 ? 0.f : d3) + __shfl_xor_sync(FULL, up4 ? d3 : 0.f, 4);
+                float f0 = (up2 ? e2 : e0) + __shfl_xor_sync(FULL, up2 ? e0 : e2, 2);
+                float f1 = (up2 ? e3 : e1) + __shfl_xor_sync(FULL, up2 ? e1 : e3, 2);
+                float tot = (up1 ? f1 : f0) + __shfl_xor_sync(FULL, up1 ? f0 : f1, 1);
+                if (G >= 16) tot += __shfl_xor_sync(FULL, tot, 8);
+                if (G >= 32) tot += __shfl_xor_sync(FULL, tot, 16);
+                float g = sgns_g_lane(tot, my_label, alpha, g_hi, g_lo, s_exp, E, idx_scale);
+                {
+                    const bool mine_ok = L8 < SGNS_CH ? r.mine >= 0 : (L8 == SGNS_CH && r.act && first);
+                    if (!mine_ok) g = 0.f;
+                }
+                float gk[SGNS_CH + 1];
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) gk[k] = __shfl_sync(FULL, g, k, G);
+                gk[SGNS_CH] = first ? __shfl_sync(FULL, g, SGNS_CH, G) : 0.f;
+#pragma unroll
+                for (int k = 0; k < SGNS_CH; k++) {
+                    axpy4(neu, gk[k], r.row[k]);
+                    red_add4_if(row_addr(base1, (uint32_t)r.tg[k], pitch), scale4(gk[k], v0), gk[k] != 0.f && live && reds_on);
+                }
+                if (first) {
+                    axpy4(neu, gk[SGNS_CH], cur);
+                    axpy4(d1, gk[SGNS_CH], v0);
+                    axpy4(cur, gk[SGNS_CH], v0);
+                }
+                if ((!MULTI || r.j == NCH - 1) && r.act && live) { // the pair is complete: syn0[last] += neu, pending in the block's cache
+                    float4 dl = delta[r.c * n4 + lane];
+                    dl.x += neu.x; dl.y += neu.y; dl.z += neu.z; dl.w += neu.w;
+                    delta[r.c * n4 + lane] = dl;
+                }
+            };
+
+            stage_r rA;
+            rA.v0 = zero4;
+#pragma unroll
+            for (int k = 0; k < SGNS_CH; k++) rA.row[k] = zero4;
+            stage_t t1 = stageT();
+            // every thread of the block walks the same (round, chunk) sequence: rT / jT advance identically everywhere
+            int r_now = 1;
+            while (r_now < n_tok && min(r_now, n_tok - r_now) > win) r_now++;
+            while (r_now < n_tok) {
+                for (int j = 0; j < NCH; j++) {
+                    stageR(t1, rA);
+                    t1 = stageT();
+                    __syncthreads(); // the delta rows written in the previous unit are read now (one writer per row per round)
+                    compute(rA);
+                }
+                r_now++;
+                while (r_now < n_tok && min(r_now, n_tok - r_now) > win) r_now++;
+            }
+            red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, valid && live && reds_on);
+            pairs += (unsigned)npairs;
+            __syncthreads();
+            // flush the sentence's pending context-row updates: one 128-bit reduction per slot that moved
+            for (int q = threadIdx.x; q < n_tok * n4; q += blockDim.x) {
+                const float4 dl = delta[q];
+                const int row = q / n4, slot = q - row * n4;
+                if (reds_on && (dl.x != 0.f || dl.y != 0.f || dl.z != 0.f || dl.w != 0.f))
+                    red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)tok[row] * a.stride) + slot, dl);
+            }
+        }
+    }
+    if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Kernel C': kernel C with the rows of a unit staged in SHARED MEMORY by cp.async instead of registers.
 // EXPERIMENTAL (DGE_SGNS_DEBUG bit 256; never chosen by default; not yet measured on the GPU).  Motivation, from
 // the ncu source page of kernel C on tract x 24 (profiles/r1_stalls_sgns15_tract24.txt): 40.6 % of all stall samples
@@ -1567,7 +1764,7 @@ struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq,
 // 16- or 32-lane group one 128-bit slot (2 or 4 for rows wider than 32 slots).
 // Kernel B (items): groups of 8 / 16 / 32 lanes, one slot per lane (2 or 4 beyond 32 slots).
 static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_parallel, bool staged_rows, bool plain_stores, int blk, bool smem_neg,
-                         bool sentence_resident, sgns_variant *out) {
+                         bool sentence_resident, bool block_sentence, sgns_variant *out) {
     if (n4 > 128) return false;
     sgns_kernel_t seq = nullptr, items = nullptr;
     int Gs = 1, Vs = 1;
@@ -1615,6 +1812,12 @@ static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_p
         if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true, 1> : k_sgns_items_v2<8, false, 1>; }
         else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v2<16, true, 1> : k_sgns_items_v2<16, false, 1>; }
         else { Gi = 32; items = multi ? k_sgns_items_v2<32, true, 1> : k_sgns_items_v2<32, false, 1>; }
+    }
+    else if (n4 <= 32 && sentence_resident && block_sentence) { // kernel G: a block owns a sentence, one lane group per centre position
+        code = 9;
+        if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_block<8, true> : k_sgns_block<8, false>; }
+        else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_block<16, true> : k_sgns_block<16, false>; }
+        else { Gi = 32; items = multi ? k_sgns_block<32, true> : k_sgns_block<32, false>; }
     }
     else if (n4 <= 32 && sentence_resident) { // kernel F: a warp owns a sentence (intra-sentence updates in sequence)
         code = 8;
@@ -1890,7 +2093,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         //  schedule ITEMS (default) : kernel B, (sentence, centre) items with L2 reductions; in flight:
         //                             concurrency * Lmax items, or (auto) min(full GPU, 8 * V / (negative + 1)) so
         //                             that a row sees at most ~8 concurrent stale updates
-        const bool sequential = p->concurrency == 1 || p->schedule == DGE_SCHEDULE_SENTENCE;
+        const bool sequential = (p->concurrency == 1 && !(dbg & 2048)) || p->schedule == DGE_SCHEDULE_SENTENCE;
         {   // kernel variant; 4-lane groups need (sentences in flight allowed) >= what fills the GPU with them
             const int64_t allowed = p->concurrency > 0 ? (int64_t)p->concurrency * Lmax : (int64_t)SGNS_STALE_BOUND * V / (p->negative + 1);
             const bool narrow = (dbg & 32) || (!(dbg & 2) && allowed >= (int64_t)ctx->sm_count * 4 * 32);
@@ -1901,7 +2104,11 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             // kernel F (sentence-resident) is the rule for rows of up to 32 slots; the item kernels B-E remain for A/B (flag) and wider rows
             const bool forced_other = (dbg & (32 | 64 | 256 | 512 | 1024)) != 0;
             const bool sent = (dbg & 2048) != 0;
-            pick_variant(n4, p->negative, narrow, tp, (dbg & 256) != 0, (dbg & 512) != 0, (dbg >> 12) & 15, smem_neg, sent && !forced_other, &var); // n4 <= 128 was checked
+            // kernel G needs one lane group per position of the longest sentence in a block of at most 256 threads
+            const int G_of = n4 <= 8 ? 8 : (n4 <= 16 ? 16 : 32);
+            const bool blk_fits = ((Lmax + 32 / G_of - 1) / (32 / G_of)) * 32 <= 256;
+            const bool blk = (dbg & 4) != 0 && blk_fits && !(dbg & 8);
+            pick_variant(n4, p->negative, narrow, tp, (dbg & 256) != 0, (dbg & 512) != 0, (dbg >> 12) & 15, smem_neg, sent && !forced_other, blk, &var); // n4 <= 128 was checked
         }
         sgns_kernel_t fn = sequential ? var.seq : var.items;
         const int G = sequential ? var.G_seq : var.G_items;
@@ -1910,12 +2117,13 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             la = la * LCG_MUL; lc = lc * LCG_MUL + LCG_ADD;
             a.lcg_a[k] = la; a.lcg_c[k] = lc;
         }
-        const bool sent_kernel = !sequential && var.items_code == 8;     // kernel F: a.n_groups counts WARPS (sentences in flight)
+        const bool block_kernel = !sequential && var.items_code == 9;    // kernel G: a.n_groups counts BLOCKS (sentences in flight)
+        const bool sent_kernel = !sequential && (var.items_code == 8 || block_kernel);   // kernel F: a.n_groups counts WARPS (sentences in flight)
         // negative table in shared memory as increment bitmap + per-word prefix (kernel F, narrow rows): exact iff the table never
         // grows by more than one word per slot, which its construction guarantees; checked all the same
         uint32_t *d_negbits = nullptr;
         const int nwords = (p->neg_table_size + 31) / 32;
-        if (sent_kernel && n4 <= 8) {
+        if ((sent_kernel && n4 <= 8) || block_kernel) {
             std::vector<uint32_t> nb((size_t)2 * nwords, 0u);
             bool exact = true;
             for (int32_t i = 0; i < p->neg_table_size; i++) {
@@ -1932,11 +2140,15 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             cudaStreamSynchronize(st);   // nb goes out of scope
         }
         a.neg_bits = d_negbits;
-        const bool big_block = !sequential && (var.items_code == 7 || (sent_kernel && n4 <= 8 && !(dbg & 16))); // one 640-thread block per SM
+        const bool big_block = !sequential && (var.items_code == 7 || (sent_kernel && !block_kernel && n4 <= 8 && !(dbg & 16))); // one 640-thread block per SM
         int threads = big_block ? 640 : 128;
+        if (block_kernel) threads = ((Lmax + 32 / G - 1) / (32 / G)) * 32;   // one lane group per position of the longest sentence
         int gpb = threads / G;
         // dynamic shared memory: the sigmoid table, plus (pipelined item kernel) one staged sentence per group
         auto smem_for = [&](int thr) {
+            if (block_kernel)
+                return (size_t)Lmax * (size_t)n4 * 16 + sizeof(float) * (size_t)p->exp_table_size + sizeof(int32_t) * (size_t)Lmax +
+                       (d_negbits ? sizeof(uint32_t) * (size_t)2 * nwords : 0);
             if (sent_kernel)
                 return (size_t)(thr / 32) * (size_t)Lmax * (size_t)n4 * 16 + sizeof(float) * (size_t)p->exp_table_size +
                        sizeof(int32_t) * (size_t)(thr / 32) * (size_t)Lmax + (d_negbits ? sizeof(uint32_t) * (size_t)2 * nwords : 0);
@@ -1958,14 +2170,21 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         else want = std::min<int64_t>(full_groups, std::max<int64_t>(gpb, (int64_t)SGNS_STALE_BOUND * V / (p->negative + 1)));
         if (!sequential && (dbg & 8)) want = 1; // one warp, one item at a time, strictly in corpus order (arithmetic check against the oracle)
         want = std::max<int64_t>(1, std::min(want, sent_kernel ? std::max<int64_t>(1, n_sent) * GPW : units));
-        while (!big_block && threads > 32 && threads > G && want < (int64_t)ctx->sm_count * gpb) { threads >>= 1; gpb = threads / G; }
+        while (!big_block && !block_kernel && threads > 32 && threads > G && want < (int64_t)ctx->sm_count * gpb) { threads >>= 1; gpb = threads / G; }
         if (sequential && want < gpb) { gpb = (int)want; threads = gpb * G; } // kernel B keeps whole warps
         int blocks = (int)((want + gpb - 1) / gpb);
         a.n_groups = (int64_t)blocks * gpb;
         if (!sequential && (dbg & 8)) a.n_groups = 1; // the single warp advances one item at a time
-        if (sent_kernel) { // groups in flight -> warps (= sentences) in flight
+        if (sent_kernel && !block_kernel) { // groups in flight -> warps (= sentences) in flight
             a.n_groups = std::max<int64_t>(1, ((int64_t)blocks * gpb) / GPW);
             if (dbg & 8) { a.n_groups = 1; blocks = 1; threads = 32; }
+        }
+        if (block_kernel) { // sentences in flight = blocks: `concurrency`, or what fills the GPU, or the staleness bound (pairs in flight / Lmax)
+            const int64_t full_blocks = (int64_t)ctx->sm_count * per_sm;
+            int64_t wb = p->concurrency > 0 ? p->concurrency : std::min<int64_t>(full_blocks, std::max<int64_t>(1, (int64_t)SGNS_STALE_BOUND * V / (p->negative + 1) / Lmax));
+            wb = std::max<int64_t>(1, std::min<int64_t>(wb, std::max<int64_t>(1, n_sent)));
+            blocks = (int)wb;
+            a.n_groups = blocks;
         }
         ctx->phase_ms["sgns_groups"] = (float)a.n_groups;
         ctx->phase_ms["sgns_kernel"] = (float)(sequential ? 0 : var.items_code);

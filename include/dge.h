@@ -224,6 +224,7 @@ enum { DGE_SGNS_F_NO_UPDATES = 1,     /* timing experiment: compute everything, 
        DGE_SGNS_F_NO_TARGET_PARALLEL = 128,
        DGE_SGNS_F_STAGED_ROWS = 256,  /* item kernel with the rows of the next unit staged in shared memory (cp.async) */
        DGE_SGNS_F_PLAIN_STORES = 512, /* atomic-free item kernel: plain 128-bit row stores instead of L2 reductions */
+       DGE_SGNS_F_BLOCK_PER_SENTENCE = 4, /* with SENTENCE_RESIDENT: kernel G, a block owns a sentence (one lane group per centre position) */
        DGE_SGNS_F_SMALL_BLOCKS = 16,  /* sentence-resident kernel: 128-thread blocks instead of one 640-thread block per SM */
        DGE_SGNS_F_SENTENCE_RESIDENT = 2048, /* kernel F: a warp owns a sentence for all its centres */
        DGE_SGNS_F_SMEM_NEG_TABLE = 1024, /* rows of up to 8 slots, V < 65536: one 640-thread block per SM, negative table in shared memory */
