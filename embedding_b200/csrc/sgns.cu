@@ -908,14 +908,18 @@ k_sgns_sent(const sgns_args a) {
 // ---------------------------------------------------------------------------------------------------------
 // Kernel G: kernel F's semantics with the parallelism INSIDE the sentence.  Parity bounds the number of sentences in
 // flight (a few hundred on a 19 K-word vocabulary: profiles/r2s5_fullsize_staleness_kernelF.json), and one warp per
-// sentence then leaves the GPU nearly empty.  But a sentence of n tokens is n centres x n contexts, and a round-robin
-// schedule makes n of its pairs independent at a time: in round r, the lane group of centre i takes context
-// (i + r) mod n -- all centres distinct (each group keeps its centre's output row in registers, as before), all
-// contexts distinct (each context row's pending delta has one writer per round).  So a BLOCK owns a sentence, one lane
-// group per centre position (6 warps for 24 positions at G = 8), n - 1 rounds with a block barrier in between; every
-// pair still reads syn0[last] fresh from L2 plus the block's own pending delta from shared memory, and the sentence's
-// deltas are flushed with 128-bit reductions once, at its end.  The pairs of a sentence are applied in a different
-// order than the oracle's centre-major loop, but in AN order: no two pairs in flight share a row of the sentence.
+// sentence then leaves the GPU nearly empty.  A BLOCK owns a sentence, one lane group per centre position (6 warps for
+// 24 positions at G = 8), and the pairs run as a WAVEFRONT: in round u the group of centre i takes context u - i.
+// Two pairs of a sentence conflict only if they share the centre (its output row syn1neg[w1], private to the group) or
+// the context (its row syn0[last]); the wavefront keeps both relative orders of word2vec's centre-major loop -- every
+// centre sees its contexts in ascending order, every context its centres in ascending order -- so the schedule is
+// conflict-equivalent to the sequential loop (2 n - 3 rounds is the shortest such schedule: the chain (0,1) ... (0,n-1),
+// (1,n-1) ... (n-1,n-2) must stay in order).  A first version walked the contexts round-robin ((i + r) mod n: n - 1
+// rounds, every group busy); it is a valid order too but not the reference's, and its embedding agreed with the
+// oracle's only to 0.81 where kernel F reaches 0.92 (profiles/r2s6_fullsize_staleness_kernelG_roundrobin.json).
+// Every pair reads syn0[last] fresh from L2 plus the block's own pending delta from shared memory; a context row is
+// flushed (one 128-bit reduction per slot) in the round after its last centre, a centre's output-row delta after its
+// last context, so nothing stays pending longer than ~n rounds.
 template <int G, bool MULTI>
 __global__ void __launch_bounds__(256, 3)
 k_sgns_block(const sgns_args a) {
@@ -977,19 +981,17 @@ k_sgns_block(const sgns_args a) {
             float4 cur = zero4, d1 = zero4, neu = zero4, v0p = zero4;
             ldcg4_into(cur, row_addr(base1, (uint32_t)w1, pitch), valid && live); // private copy of syn1neg[w1]
             int npairs = 0;
-            int rT = 1, jT = 0; // (round, chunk) of the next unit the T stage hands out
+            int rT = 1, jT = 0; // (round, chunk) of the next unit the T stage hands out; rounds 1 .. 2 n_tok - 3
+            const int n_rounds = 2 * n_tok - 3;
             uint64_t hc = 0;
             int hcb = -1;
-            // rounds in which nobody can be active (both cyclic distances beyond the window) are skipped by every thread alike
-            auto skip_dead_rounds = [&]() { while (rT < n_tok && min(rT, n_tok - rT) > win) rT++; };
-            skip_dead_rounds();
+            bool d1_flushed = false;
 
             auto stageT = [&]() {
                 stage_t t;
                 t.j = jT;
-                int c = i + rT;
-                if (c >= n_tok) c -= n_tok;
-                const bool in_round = valid && rT < n_tok;
+                const int c = rT - i;   // wavefront: centre i meets context u - i in round u
+                const bool in_round = valid && rT <= n_rounds && c >= 0 && c < n_tok && c != i;
                 t.c = in_round ? c : 0;
                 t.last = in_round ? tok[t.c] : -1;
                 t.act = in_round && t.c >= lo && t.c <= hi && t.last >= 0 && t.last != w1;
@@ -1004,8 +1006,8 @@ k_sgns_block(const sgns_args a) {
                     const uint32_t idx = mod48(t.nsk >> 16, tsize, inv_tsize);
                     t.traw = smem_neg ? neg_lookup(s_bits, s_pref, idx) : a.neg_table[idx];
                 }
-                if (MULTI) { if (++jT == NCH) { jT = 0; rT++; skip_dead_rounds(); } }
-                else { rT++; skip_dead_rounds(); }
+                if (MULTI) { if (++jT == NCH) { jT = 0; rT++; } }
+                else rT++;
                 return t;
             };
             auto stageR = [&](const stage_t &t, stage_r &r) {
@@ -1075,27 +1077,37 @@ k_sgns_block(const sgns_args a) {
             for (int k = 0; k < SGNS_CH; k++) rA.row[k] = zero4;
             stage_t t1 = stageT();
             // every thread of the block walks the same (round, chunk) sequence: rT / jT advance identically everywhere
-            int r_now = 1;
-            while (r_now < n_tok && min(r_now, n_tok - r_now) > win) r_now++;
-            while (r_now < n_tok) {
+            const int last_ctx = min(hi, n_tok - 1);   // beyond it this centre has no context left
+            for (int u = 1; u <= n_rounds; u++) {
                 for (int j = 0; j < NCH; j++) {
                     stageR(t1, rA);
                     t1 = stageT();
                     __syncthreads(); // the delta rows written in the previous unit are read now (one writer per row per round)
+                    if (j == 0) {
+                        // context row i saw its last centre (n_tok - 1, or n_tok - 2 for the last row) in round i + n_tok - 1 at the latest:
+                        // its group sends the row's pending delta now, nobody reads or writes it again in this sentence
+                        if (valid && live && u == i + n_tok) {
+                            const float4 dl = delta[i * n4 + lane];
+                            if (reds_on && (dl.x != 0.f || dl.y != 0.f || dl.z != 0.f || dl.w != 0.f))
+                                red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)w1 * a.stride) + lane, dl);
+                        }
+                        // and the centre's own output row once its contexts are exhausted
+                        if (!d1_flushed && u - i > last_ctx) {
+                            red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, valid && live && reds_on);
+                            d1_flushed = true;
+                        }
+                    }
                     compute(rA);
                 }
-                r_now++;
-                while (r_now < n_tok && min(r_now, n_tok - r_now) > win) r_now++;
             }
-            red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, valid && live && reds_on);
+            if (!d1_flushed) red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, valid && live && reds_on);
             pairs += (unsigned)npairs;
             __syncthreads();
-            // flush the sentence's pending context-row updates: one 128-bit reduction per slot that moved
-            for (int q = threadIdx.x; q < n_tok * n4; q += blockDim.x) {
-                const float4 dl = delta[q];
-                const int row = q / n4, slot = q - row * n4;
+            // the context rows whose last centre came in the final rounds (u == i + n_tok was never reached)
+            if (valid && live && i + n_tok > n_rounds) {
+                const float4 dl = delta[i * n4 + lane];
                 if (reds_on && (dl.x != 0.f || dl.y != 0.f || dl.z != 0.f || dl.w != 0.f))
-                    red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)tok[row] * a.stride) + slot, dl);
+                    red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)w1 * a.stride) + lane, dl);
             }
         }
     }
