@@ -920,8 +920,8 @@ k_sgns_sent(const sgns_args a) {
 // Every pair reads syn0[last] fresh from L2 plus the block's own pending delta from shared memory; a context row is
 // flushed (one 128-bit reduction per slot) in the round after its last centre, a centre's output-row delta after its
 // last context, so nothing stays pending longer than ~n rounds.
-template <int G, bool MULTI>
-__global__ void __launch_bounds__(256, 3)
+template <int G, bool MULTI, int MAXT>
+__global__ void __launch_bounds__(MAXT, 2)
 k_sgns_block(const sgns_args a) {
     static_assert(G == 8 || G == 16 || G == 32, "lane groups of 8, 16 or 32");
     extern __shared__ __align__(16) int32_t smem_g[];
@@ -1071,33 +1071,47 @@ k_sgns_block(const sgns_args a) {
                 }
             };
 
-            stage_r rA;
-            rA.v0 = zero4;
+            // Parity keeps the sentences in flight few (two blocks per SM), so latency is hidden INSIDE the block: the rows of
+            // unit k + 1 are requested before unit k is computed (two row buffers in registers; the negative-table entries run
+            // two units ahead).  What a pair reads early is only L2's copy; the sentence's own pending delta is added from
+            // shared memory when the pair is computed, after the barrier.
+            stage_r rA, rB;
+            rA.v0 = rB.v0 = zero4;
 #pragma unroll
-            for (int k = 0; k < SGNS_CH; k++) rA.row[k] = zero4;
-            stage_t t1 = stageT();
-            // every thread of the block walks the same (round, chunk) sequence: rT / jT advance identically everywhere
+            for (int k = 0; k < SGNS_CH; k++) rA.row[k] = rB.row[k] = zero4;
             const int last_ctx = min(hi, n_tok - 1);   // beyond it this centre has no context left
-            for (int u = 1; u <= n_rounds; u++) {
-                for (int j = 0; j < NCH; j++) {
+            // every thread of the block walks the same unit sequence (round u = 1 + k / NCH, chunk k % NCH): rT / jT advance identically everywhere
+            auto before_compute = [&](int k) {
+                __syncthreads(); // the delta rows written in the previous unit are read now (one writer per row per round)
+                if (MULTI && k % NCH != 0) return;
+                const int u = 1 + k / NCH;
+                // context row i saw its last centre in round i + n_tok - 1 at the latest: its group sends the row's pending delta
+                // now, nobody reads or writes it again in this sentence
+                if (valid && live && u == i + n_tok) {
+                    const float4 dl = delta[i * n4 + lane];
+                    if (reds_on && (dl.x != 0.f || dl.y != 0.f || dl.z != 0.f || dl.w != 0.f))
+                        red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)w1 * a.stride) + lane, dl);
+                }
+                // and the centre's own output row once its contexts are exhausted
+                if (!d1_flushed && u - i > last_ctx) {
+                    red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, valid && live && reds_on);
+                    d1_flushed = true;
+                }
+            };
+            const int U = n_rounds * NCH;
+            stage_t t1 = stageT();  // unit 0
+            stageR(t1, rA);
+            t1 = stageT();          // unit 1
+            for (int k = 0; k < U; k += 2) {
+                stageR(t1, rB);     // rows of unit k + 1 (nothing is requested past the end: act is false there)
+                t1 = stageT();
+                before_compute(k);
+                compute(rA);
+                if (k + 1 < U) {
                     stageR(t1, rA);
                     t1 = stageT();
-                    __syncthreads(); // the delta rows written in the previous unit are read now (one writer per row per round)
-                    if (j == 0) {
-                        // context row i saw its last centre (n_tok - 1, or n_tok - 2 for the last row) in round i + n_tok - 1 at the latest:
-                        // its group sends the row's pending delta now, nobody reads or writes it again in this sentence
-                        if (valid && live && u == i + n_tok) {
-                            const float4 dl = delta[i * n4 + lane];
-                            if (reds_on && (dl.x != 0.f || dl.y != 0.f || dl.z != 0.f || dl.w != 0.f))
-                                red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)w1 * a.stride) + lane, dl);
-                        }
-                        // and the centre's own output row once its contexts are exhausted
-                        if (!d1_flushed && u - i > last_ctx) {
-                            red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, valid && live && reds_on);
-                            d1_flushed = true;
-                        }
-                    }
-                    compute(rA);
+                    before_compute(k + 1);
+                    compute(rB);
                 }
             }
             if (!d1_flushed) red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, valid && live && reds_on);
@@ -1776,7 +1790,7 @@ struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq,
 // 16- or 32-lane group one 128-bit slot (2 or 4 for rows wider than 32 slots).
 // Kernel B (items): groups of 8 / 16 / 32 lanes, one slot per lane (2 or 4 beyond 32 slots).
 static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_parallel, bool staged_rows, bool plain_stores, int blk, bool smem_neg,
-                         bool sentence_resident, bool block_sentence, sgns_variant *out) {
+                         bool sentence_resident, bool block_sentence, int block_threads, sgns_variant *out) {
     if (n4 > 128) return false;
     sgns_kernel_t seq = nullptr, items = nullptr;
     int Gs = 1, Vs = 1;
@@ -1827,9 +1841,10 @@ static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_p
     }
     else if (n4 <= 32 && sentence_resident && block_sentence) { // kernel G: a block owns a sentence, one lane group per centre position
         code = 9;
-        if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_block<8, true> : k_sgns_block<8, false>; }
-        else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_block<16, true> : k_sgns_block<16, false>; }
-        else { Gi = 32; items = multi ? k_sgns_block<32, true> : k_sgns_block<32, false>; }
+        if (n4 <= 8 && block_threads <= 192) { Gi = 8; items = multi ? k_sgns_block<8, true, 192> : k_sgns_block<8, false, 192>; } // 170 registers
+        else if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_block<8, true, 256> : k_sgns_block<8, false, 256>; }
+        else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_block<16, true, 256> : k_sgns_block<16, false, 256>; }
+        else { Gi = 32; items = multi ? k_sgns_block<32, true, 256> : k_sgns_block<32, false, 256>; }
     }
     else if (n4 <= 32 && sentence_resident) { // kernel F: a warp owns a sentence (intra-sentence updates in sequence)
         code = 8;
@@ -2105,22 +2120,27 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         //  schedule ITEMS (default) : kernel B, (sentence, centre) items with L2 reductions; in flight:
         //                             concurrency * Lmax items, or (auto) min(full GPU, 8 * V / (negative + 1)) so
         //                             that a row sees at most ~8 concurrent stale updates
-        const bool sequential = (p->concurrency == 1 && !(dbg & 2048)) || p->schedule == DGE_SCHEDULE_SENTENCE;
+        const bool sequential = (p->concurrency == 1 && !(dbg & (2048 | 4))) || p->schedule == DGE_SCHEDULE_SENTENCE;
         {   // kernel variant; 4-lane groups need (sentences in flight allowed) >= what fills the GPU with them
             const int64_t allowed = p->concurrency > 0 ? (int64_t)p->concurrency * Lmax : (int64_t)SGNS_STALE_BOUND * V / (p->negative + 1);
-            const bool narrow = (dbg & 32) || (!(dbg & 2) && allowed >= (int64_t)ctx->sm_count * 4 * 32);
+            const bool narrow = (dbg & 32) || ((dbg & 65536) && !(dbg & 2) && allowed >= (int64_t)ctx->sm_count * 4 * 32);
             // fewer pairs in flight than the 8-lane kernel needs to fill the GPU (5 blocks x 16 groups per SM): latency-bound
-            const bool tp = (dbg & 64) || (!(dbg & (128 | 32)) && allowed < (int64_t)ctx->sm_count * 5 * 16);
+            const bool tp = (dbg & 64) || ((dbg & 65536) && !(dbg & (128 | 32)) && allowed < (int64_t)ctx->sm_count * 5 * 16);
             // negative table in shared memory (16-bit entries): vocabularies below 65 536 words and a table that fits beside the rest
             const bool smem_neg = (dbg & 1024) != 0 && V <= 65535 && p->neg_table_size <= 100000;
-            // kernel F (sentence-resident) is the rule for rows of up to 32 slots; the item kernels B-E remain for A/B (flag) and wider rows
-            const bool forced_other = (dbg & (32 | 64 | 256 | 512 | 1024)) != 0;
-            const bool sent = (dbg & 2048) != 0;
+            // Kernels F / G (sentence-resident: intra-sentence updates in the reference's order) are the rule for rows of up to
+            // 32 slots: G (a block per sentence) for narrow rows when one lane group per position fits a block, F (a warp per
+            // sentence) otherwise.  The item kernels B-E, which put the centres of one sentence in flight at once and drift
+            // from the oracle, remain behind flags for A/B measurements, and kernel B for rows beyond 32 slots.
+            const bool forced_other = (dbg & (32 | 64 | 256 | 512 | 1024 | 65536)) != 0;
+            const bool sent = !forced_other;
             // kernel G needs one lane group per position of the longest sentence in a block of at most 256 threads
             const int G_of = n4 <= 8 ? 8 : (n4 <= 16 ? 16 : 32);
             const bool blk_fits = ((Lmax + 32 / G_of - 1) / (32 / G_of)) * 32 <= 256;
-            const bool blk = (dbg & 4) != 0 && blk_fits && !(dbg & 8);
-            pick_variant(n4, p->negative, narrow, tp, (dbg & 256) != 0, (dbg & 512) != 0, (dbg >> 12) & 15, smem_neg, sent && !forced_other, blk, &var); // n4 <= 128 was checked
+            const bool force_warp_per_sentence = (dbg & 2048) != 0 && !(dbg & 4);
+            const bool blk = blk_fits && n4 <= 8 && !(dbg & 8) && !force_warp_per_sentence;
+            pick_variant(n4, p->negative, narrow, tp, (dbg & 256) != 0, (dbg & 512) != 0, (dbg >> 12) & 15, smem_neg, sent && !forced_other, blk,
+                         ((Lmax + 32 / G_of - 1) / (32 / G_of)) * 32, &var); // n4 <= 128 was checked
         }
         sgns_kernel_t fn = sequential ? var.seq : var.items;
         const int G = sequential ? var.G_seq : var.G_items;
@@ -2194,7 +2214,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         if (block_kernel) { // sentences in flight = blocks: `concurrency`, or what fills the GPU, or the staleness bound (pairs in flight / Lmax)
             const int64_t full_blocks = (int64_t)ctx->sm_count * per_sm;
             int64_t wb = p->concurrency > 0 ? p->concurrency : std::min<int64_t>(full_blocks, std::max<int64_t>(1, (int64_t)SGNS_STALE_BOUND * V / (p->negative + 1) / Lmax));
-            wb = std::max<int64_t>(1, std::min<int64_t>(wb, std::max<int64_t>(1, n_sent)));
+            wb = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(wb, full_blocks), std::max<int64_t>(1, n_sent)));
             blocks = (int)wb;
             a.n_groups = blocks;
         }

@@ -119,7 +119,7 @@ def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negati
         return np.linalg.norm(syn0 - ref["syn0"]) / learned0, np.linalg.norm(syn1 - ref["syn1neg"]) / learned1
 
     L = dge_lib
-    flag_sets = [L.F_ONE_WARP]
+    flag_sets = [L.F_ONE_WARP, L.F_ONE_WARP | L.F_ITEM_KERNELS]           # kernel F / kernel C on one lane group
     if dim <= 16:
         flag_sets.append(L.F_ONE_WARP | L.F_NARROW)                  # the 4-lane-group kernel for D <= 16
         if negative <= 7:
