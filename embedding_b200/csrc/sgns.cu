@@ -934,6 +934,9 @@ k_sgns_block(const sgns_args a) {
     uint32_t *s_bits = reinterpret_cast<uint32_t *>(tok + Lmax);
     uint32_t *s_pref = s_bits + nwords;
     const bool smem_neg = a.neg_bits != nullptr;
+    // the negatives of every (centre, context) pair of the sentence, drawn by all threads before the rounds start:
+    // [Lmax][Lmax][K] vocabulary indices, -1 = none (a draw that hit the centre itself is skipped, as in the oracle)
+    int32_t *s_tg = reinterpret_cast<int32_t *>(s_bits + (smem_neg ? 2 * nwords : 0));
     for (int q = threadIdx.x; q < a.exp_table_size; q += blockDim.x) s_exp[q] = a.exp_table[q];
     if (smem_neg)
         for (int q = threadIdx.x; q < 2 * nwords; q += blockDim.x) s_bits[q] = a.neg_bits[q];
@@ -959,7 +962,7 @@ k_sgns_block(const sgns_args a) {
     const bool reds_on = !(a.dbg & 1);
     unsigned long long pairs = 0;
 
-    struct stage_t { int32_t last; bool act; uint64_t nsk; int32_t traw; int j; int c; };
+    struct stage_t { int32_t last; bool act; int j; int c; };
     struct stage_r { int32_t last; bool act; int j; int c; int32_t mine; int32_t tg[SGNS_CH]; float4 row[SGNS_CH]; float4 v0; };
 
     for (int ep = a.ep_lo; ep < a.ep_hi; ep++) {
@@ -974,6 +977,18 @@ k_sgns_block(const sgns_args a) {
             if (alpha < a.min_lr) alpha = a.min_lr;
             const float g_hi = (my_label - 1.f) * alpha, g_lo = my_label * alpha;
             const uint64_t S = sgns_sentence_rng(a.seed, ep, s + a.s_off);
+            // ---- draw phase: K negatives for each of the n (n - 1) ordered pairs, off the rounds' critical path and on every lane
+            for (int e = threadIdx.x; e < n_tok * n_tok * K; e += blockDim.x) {
+                const int kq = e % K, ic = e / K;
+                const int cc = ic % n_tok, ii = ic / n_tok;
+                if (cc == ii) continue;
+                const uint64_t nsk = a.lcg_a[kq] * sgns_pair_rng(S, ii, cc) + a.lcg_c[kq]; // the LCG is affine: state after kq + 1 steps
+                const uint32_t idx = mod48(nsk >> 16, tsize, inv_tsize);
+                int32_t t = smem_neg ? neg_lookup(s_bits, s_pref, idx) : a.neg_table[idx];
+                if (t <= 0 || t >= a.V) t = (int32_t)mod64(nsk, vm1, inv_vm1) + 1;   // DL4J: target = r % (V - 1) + 1
+                s_tg[(ii * Lmax + cc) * K + kq] = t == tok[ii] ? -1 : t;
+            }
+            __syncthreads();
             const bool valid = i < n_tok;
             const int32_t w1 = valid ? tok[i] : 0;
             const int b = (int32_t)(uint32_t)sgns_position_rng(S, valid ? i : 0) % win;
@@ -983,8 +998,6 @@ k_sgns_block(const sgns_args a) {
             int npairs = 0;
             int rT = 1, jT = 0; // (round, chunk) of the next unit the T stage hands out; rounds 1 .. 2 n_tok - 3
             const int n_rounds = 2 * n_tok - 3;
-            uint64_t hc = 0;
-            int hcb = -1;
             bool d1_flushed = false;
 
             auto stageT = [&]() {
@@ -995,31 +1008,16 @@ k_sgns_block(const sgns_args a) {
                 t.c = in_round ? c : 0;
                 t.last = in_round ? tok[t.c] : -1;
                 t.act = in_round && t.c >= lo && t.c <= hi && t.last >= 0 && t.last != w1;
-                if (t.c / G != hcb) { hcb = t.c / G; hc = sgns_pair_rng(S, i, hcb * G + lane); }
-                const uint64_t ns0 = shfl64(hc, t.c & (G - 1), G);
-                const int kk = jT * SGNS_CH + lane;
-                const bool drawer = lane < SGNS_CH && kk < K;
-                const int kc = drawer ? kk : 0;
-                t.nsk = a.lcg_a[kc] * ns0 + a.lcg_c[kc];
-                t.traw = -2;
-                if (drawer && t.act) {
-                    const uint32_t idx = mod48(t.nsk >> 16, tsize, inv_tsize);
-                    t.traw = smem_neg ? neg_lookup(s_bits, s_pref, idx) : a.neg_table[idx];
-                }
                 if (MULTI) { if (++jT == NCH) { jT = 0; rT++; } }
                 else rT++;
                 return t;
             };
             auto stageR = [&](const stage_t &t, stage_r &r) {
                 r.last = t.last; r.act = t.act; r.j = t.j; r.c = t.c;
-                int32_t tt = t.traw;
-                const bool redraw = tt != -2 && (tt <= 0 || tt >= a.V);
-                if (__any_sync(FULL, redraw)) {
-                    if (redraw) tt = (int32_t)mod64(t.nsk, vm1, inv_vm1) + 1;
-                }
-                r.mine = (tt != -2 && tt != w1) ? tt : -1;
+                const int32_t *tgp = s_tg + ((i < Lmax ? i : 0) * Lmax + t.c) * K + t.j * SGNS_CH; // the pair's negatives of this chunk (broadcast reads)
 #pragma unroll
-                for (int k = 0; k < SGNS_CH; k++) r.tg[k] = __shfl_sync(FULL, r.mine, k, G);
+                for (int k = 0; k < SGNS_CH; k++) r.tg[k] = (t.act && t.j * SGNS_CH + k < K) ? tgp[k] : -1;
+                r.mine = (t.act && L8 < SGNS_CH && t.j * SGNS_CH + L8 < K) ? tgp[L8] : -1;
                 if (!MULTI || t.j == 0) ldcg4_into(r.v0, row_addr(base0, (uint32_t)t.last, pitch), t.act && live);
 #pragma unroll
                 for (int k = 0; k < SGNS_CH; k++) ldcg4_into(r.row[k], row_addr(base1, (uint32_t)r.tg[k], pitch), r.tg[k] >= 0 && live);
@@ -2180,7 +2178,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         auto smem_for = [&](int thr) {
             if (block_kernel)
                 return (size_t)Lmax * (size_t)n4 * 16 + sizeof(float) * (size_t)p->exp_table_size + sizeof(int32_t) * (size_t)Lmax +
-                       (d_negbits ? sizeof(uint32_t) * (size_t)2 * nwords : 0);
+                       (d_negbits ? sizeof(uint32_t) * (size_t)2 * nwords : 0) + sizeof(int32_t) * (size_t)Lmax * (size_t)Lmax * (size_t)std::max(1, p->negative);
             if (sent_kernel)
                 return (size_t)(thr / 32) * (size_t)Lmax * (size_t)n4 * 16 + sizeof(float) * (size_t)p->exp_table_size +
                        sizeof(int32_t) * (size_t)(thr / 32) * (size_t)Lmax + (d_negbits ? sizeof(uint32_t) * (size_t)2 * nwords : 0);
