@@ -42,7 +42,7 @@ if ROOT not in sys.path:
 WALK_BYTES_PER_STEP = 28.0      # row_ptr pair 8 + prob 8 + alias 4 + col 4 + token 4
 METRIC = "walk_steps_per_sec_through_walks_and_skipgram"
 SG_KERNELS = {0: "k_sgns_seq", 1: "k_sgns_items", 2: "k_sgns_items_v2", 3: "k_sgns_items_g4", 4: "k_sgns_items_tp",
-              5: "k_sgns_items_v3", 6: "k_sgns_items_v2 (plain stores)", 7: "k_sgns_items_v2 (negative table in shared memory)", 8: "k_sgns_sent", 9: "k_sgns_block"}
+              5: "k_sgns_items_v3", 6: "k_sgns_items_v2 (plain stores)", 7: "k_sgns_items_v2 (negative table in shared memory)", 8: "k_sgns_sent", 9: "k_sgns_block", 10: "k_sgns_pipe"}
 
 
 def sgns_bytes_per_pair(dim, negative):

@@ -1127,6 +1127,257 @@ k_sgns_block(const sgns_args a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Kernel H: kernel G with the sentences of a block PIPELINED through the wavefront.  In kernel G half of the lane groups
+// idle on average: the wavefront of a sentence fills for n rounds and drains for n rounds.  Here the groups that have
+// finished their centre of sentence k start sentence k + 1 at once (sentence k + 1 enters the block n_k rounds after
+// sentence k, not 2 n_k - 3), so the drain of one sentence overlaps the fill of the next and every group has a pair in
+// (almost) every round.  The number of PAIRS in flight in a block is unchanged (one per lane group), every sentence
+// still runs the conflict-equivalent wavefront order; what a block holds pending at any time is the second half of one
+// sentence and the first half of the next.  Three sentence slots in shared memory (tokens, pending context-row deltas,
+// pre-drawn negatives): sentence k + 2 is set up while k + 1 starts and k drains; a slot is reused only after every row
+// of its old sentence has been flushed (start_{k+2} >= start_k + 2 n_k).
+// Rows of up to 8 slots, K <= 5 negatives, sentences of up to 24 tokens (192 threads); otherwise kernel G runs.
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 2)
+k_sgns_pipe(const sgns_args a) {
+    constexpr int G = 8;
+    extern __shared__ __align__(16) int32_t smem_h[];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int n4 = a.n4, Lmax = a.Lmax;
+    const int nwords = (a.neg_table_size + 31) >> 5;
+    const int K = a.V >= 2 ? a.negative : 0; // <= 5 (host)
+    float4 *delta = reinterpret_cast<float4 *>(smem_h);                         // [3][Lmax][n4]
+    float *s_exp = reinterpret_cast<float *>(delta + (size_t)3 * Lmax * n4);
+    int32_t *tok = reinterpret_cast<int32_t *>(s_exp + a.exp_table_size);       // [3][Lmax]
+    int32_t *meta = tok + 3 * Lmax;                                              // [3][8]: n, start, alpha bits, S lo, S hi
+    uint32_t *s_bits = reinterpret_cast<uint32_t *>(meta + 24);
+    uint32_t *s_pref = s_bits + nwords;
+    const bool smem_neg = a.neg_bits != nullptr;
+    int32_t *s_tg = reinterpret_cast<int32_t *>(s_bits + (smem_neg ? 2 * nwords : 0)); // [3][Lmax][Lmax][K]
+    const int tg_slot = Lmax * Lmax * (K > 0 ? K : 1);
+    for (int q = threadIdx.x; q < a.exp_table_size; q += blockDim.x) s_exp[q] = a.exp_table[q];
+    if (smem_neg)
+        for (int q = threadIdx.x; q < 2 * nwords; q += blockDim.x) s_bits[q] = a.neg_bits[q];
+    if (threadIdx.x < 24) meta[threadIdx.x] = 0;
+    const int lane = threadIdx.x % G;
+    const int i = threadIdx.x / G;          // this lane group's centre position in every sentence
+    const int E = a.exp_table_size;
+    const float idx_scale = (float)E / SGNS_MAX_EXP / 2.0f;
+    const int win = a.window;
+    const int64_t N = a.n_sent;
+    const double inv_total = 1.0 / (double)((int64_t)a.epochs * a.n_global);
+    const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
+    const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool live = lane < n4;
+    const uint32_t pitch = (uint32_t)a.stride * 4u;
+    const char *base0 = reinterpret_cast<const char *>(a.syn0) + (live ? lane : 0) * 16;
+    const char *base1 = reinterpret_cast<const char *>(a.syn1neg) + (live ? lane : 0) * 16;
+    const int L8 = lane & 7;
+    const bool up4 = (lane & 4) != 0, up2 = (lane & 2) != 0, up1 = (lane & 1) != 0;
+    const float my_label = L8 == SGNS_CH ? 1.f : 0.f;
+    const bool reds_on = !(a.dbg & 1);
+    unsigned long long pairs = 0;
+    __syncthreads();
+
+    struct stage_t { int32_t last; bool act; int c; int slot; };
+    struct stage_r { int32_t last; bool act; int c; int slot; int32_t mine; int32_t tg[SGNS_CH]; float4 row[SGNS_CH]; float4 v0; };
+
+    for (int ep = a.ep_lo; ep < a.ep_hi; ep++) {
+        // the block's sentences: s_lo + blockIdx.x + k * n_groups.  `ns` of them have been set up; start_m1 / start_m2 and
+        // n_m1 / n_m2 are the start rounds and lengths of the last two that were (uniform across the block).
+        int64_t s_next = a.s_lo + blockIdx.x;
+        int ns = 0, start_m1 = 0, start_m2 = 0, n_m1 = 0, n_m2 = 0, end_round = 0;
+        // ---- sets up the next non-empty sentence of the block in slot ns % 3; false when the block has no sentence left
+        auto setup_next = [&]() -> bool {
+            while (s_next < a.s_hi) {
+                const int64_t s = s_next;
+                s_next += a.n_groups;
+                const int slot = ns % 3;
+                __syncthreads();
+                int32_t tk = -1;
+                if ((int)threadIdx.x < Lmax) { tk = a.wtok[(int64_t)threadIdx.x * N + s]; tok[slot * Lmax + threadIdx.x] = tk; }
+                const int n = __syncthreads_count(tk >= 0);
+                if (n < 2) continue; // no pair in it
+                for (int q = threadIdx.x; q < Lmax * n4; q += blockDim.x) delta[slot * Lmax * n4 + q] = zero4;
+                const uint64_t S = sgns_sentence_rng(a.seed, ep, s + a.s_off);
+                // sentence k enters n_{k-1} rounds after sentence k - 1, and not before sentence k - 2 has flushed its last row
+                // (+ 4 rounds of margin: a sentence is set up 4 rounds before its predecessor starts, so that the stages that run
+                // 2-3 rounds ahead of the computation always find it)
+                const int start = ns == 0 ? 0 : max(start_m1 + n_m1, ns >= 2 ? start_m2 + 2 * n_m2 + 4 : 0);
+                if (threadIdx.x == 0) {
+                    float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * a.n_global + a.s_off + s) * inv_total);
+                    if (alpha < a.min_lr) alpha = a.min_lr;
+                    meta[slot * 8 + 0] = n; meta[slot * 8 + 1] = start; meta[slot * 8 + 2] = __float_as_int(alpha);
+                    meta[slot * 8 + 3] = (int32_t)(uint32_t)S; meta[slot * 8 + 4] = (int32_t)(uint32_t)(S >> 32);
+                }
+                const int32_t *tk_s = tok + slot * Lmax;
+                for (int e = threadIdx.x; e < n * n * K; e += blockDim.x) { // the K negatives of all n (n - 1) ordered pairs
+                    const int kq = e % K, ic = e / K;
+                    const int cc = ic % n, ii = ic / n;
+                    if (cc == ii) continue;
+                    const uint64_t nsk = a.lcg_a[kq] * sgns_pair_rng(S, ii, cc) + a.lcg_c[kq];
+                    const uint32_t idx = mod48(nsk >> 16, tsize, inv_tsize);
+                    int32_t t = smem_neg ? neg_lookup(s_bits, s_pref, idx) : a.neg_table[idx];
+                    if (t <= 0 || t >= a.V) t = (int32_t)mod64(nsk, vm1, inv_vm1) + 1;
+                    s_tg[slot * tg_slot + (ii * Lmax + cc) * K + kq] = t == tk_s[ii] ? -1 : t;
+                }
+                __syncthreads();
+                start_m2 = start_m1; n_m2 = n_m1; start_m1 = start; n_m1 = n;
+                end_round = start + 2 * n; // every row of this sentence has been flushed by then
+                ns++;
+                return true;
+            }
+            return false;
+        };
+        // ---- where is this lane group in round U?  (slot, context position) or slot = -1
+        auto locate = [&](int U, int &slot, int &c) {
+            slot = -1; c = 0;
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const int n = meta[q * 8 + 0], cc = U - meta[q * 8 + 1] - i;
+                if (i < n && cc >= 0 && cc < n) { slot = q; c = cc; }
+            }
+        };
+        if (!setup_next()) continue;
+        bool more = setup_next();
+        // per-group state of the sentence it is on
+        int cur_slot = -1, lo = 1, hi = 0;
+        int32_t w1 = 0;
+        float alpha = 0.f;
+        float4 cur = zero4, d1 = zero4, cur_next = zero4;
+        int npairs = 0;
+        int UT = 0; // round of the next unit the T stage hands out
+
+        auto stageT = [&]() {
+            stage_t t;
+            int slot, c;
+            locate(UT, slot, c);
+            const bool on = slot >= 0 && c != i;
+            t.slot = on ? slot : 0;
+            t.c = on ? c : 0;
+            t.last = on ? tok[t.slot * Lmax + t.c] : -1;
+            // the window of the centre: b from the sentence key of that slot (the group may be about to change sentences)
+            bool act = false;
+            if (on) {
+                const uint64_t S = ((uint64_t)(uint32_t)meta[t.slot * 8 + 4] << 32) | (uint32_t)meta[t.slot * 8 + 3];
+                const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
+                act = t.c >= i - win + b && t.c <= i + win - b && t.last >= 0 && t.last != tok[t.slot * Lmax + i];
+            }
+            t.act = act;
+            UT++;
+            return t;
+        };
+        auto stageR = [&](const stage_t &t, stage_r &r, int U) {
+            r.last = t.last; r.act = t.act; r.c = t.c; r.slot = t.slot;
+            const int32_t *tgp = s_tg + t.slot * tg_slot + ((i < Lmax ? i : 0) * Lmax + t.c) * K;
+#pragma unroll
+            for (int k = 0; k < SGNS_CH; k++) r.tg[k] = (t.act && k < K) ? tgp[k] : -1;
+            r.mine = (t.act && L8 < SGNS_CH && L8 < K) ? tgp[L8] : -1;
+            ldcg4_into(r.v0, row_addr(base0, (uint32_t)t.last, pitch), t.act && live);
+#pragma unroll
+            for (int k = 0; k < SGNS_CH; k++) ldcg4_into(r.row[k], row_addr(base1, (uint32_t)r.tg[k], pitch), r.tg[k] >= 0 && live);
+            // the group starts a new sentence in round U: its centre's output row is requested one round ahead
+            int slot, c;
+            locate(U, slot, c);
+            if (slot >= 0 && c == 0 && slot != cur_slot)
+                ldcg4_into(cur_next, row_addr(base1, (uint32_t)tok[slot * Lmax + i], pitch), live);
+        };
+        auto compute = [&](const stage_r &r, int U) {
+            // ---- time-triggered flushes: row i of a sentence saw its last centre in round start + i + n - 1
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const int n = meta[q * 8 + 0];
+                if (i < n && U == meta[q * 8 + 1] + i + n) {
+                    if (live) {
+                        const float4 dl = delta[(q * Lmax + i) * n4 + lane];
+                        if (reds_on && (dl.x != 0.f || dl.y != 0.f || dl.z != 0.f || dl.w != 0.f))
+                            red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)tok[q * Lmax + i] * a.stride) + lane, dl);
+                    }
+                    if (q == cur_slot) { // and the centre's output row: the group has left the sentence
+                        red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, live && reds_on);
+                        cur_slot = -1;
+                    }
+                }
+            }
+            // ---- entering a sentence: the group's centre, its window and its private copy of syn1neg[w1]
+            int slot, c;
+            locate(U, slot, c);
+            if (slot >= 0 && slot != cur_slot) {
+                cur_slot = slot;
+                w1 = tok[slot * Lmax + i];
+                alpha = __int_as_float(meta[slot * 8 + 2]);
+                const uint64_t S = ((uint64_t)(uint32_t)meta[slot * 8 + 4] << 32) | (uint32_t)meta[slot * 8 + 3];
+                const int b = (int32_t)(uint32_t)sgns_position_rng(S, i) % win;
+                lo = i - win + b; hi = i + win - b;
+                cur = cur_next;
+                d1 = zero4;
+            }
+            if (!__any_sync(FULL, r.act)) return;
+            const float g_hi = (my_label - 1.f) * alpha, g_lo = my_label * alpha;
+            npairs += r.act;
+            float4 neu = zero4;
+            float4 v0 = r.v0; // L2's value + what the sentence has added to the row so far
+            if (r.act && live) { const float4 dl = delta[(r.slot * Lmax + r.c) * n4 + lane]; v0.x += dl.x; v0.y += dl.y; v0.z += dl.z; v0.w += dl.w; }
+            float d0 = dot4(v0, r.row[0]), d1v = dot4(v0, r.row[1]), d2 = dot4(v0, r.row[2]), d3 = dot4(v0, r.row[3]);
+            float d4 = dot4(v0, r.row[4]), d5 = dot4(v0, cur);
+            float e0 = (up4 ? d4 : d0) + __shfl_xor_sync(FULL, up4 ? d0 : d4, 4);
+            float e1 = (up4 ? d5 : d1v) + __shfl_xor_sync(FULL, up4 ? d1v : d5, 4);
+            float e2 = (up4 ? 0.f : d2) + __shfl_xor_sync(FULL, up4 ? d2 : 0.f, 4);
+            float e3 = (up4 ? 0.f : d3) + __shfl_xor_sync(FULL, up4 ? d3 : 0.f, 4);
+            float f0 = (up2 ? e2 : e0) + __shfl_xor_sync(FULL, up2 ? e0 : e2, 2);
+            float f1 = (up2 ? e3 : e1) + __shfl_xor_sync(FULL, up2 ? e1 : e3, 2);
+            float tot = (up1 ? f1 : f0) + __shfl_xor_sync(FULL, up1 ? f0 : f1, 1);
+            float g = sgns_g_lane(tot, my_label, alpha, g_hi, g_lo, s_exp, E, idx_scale);
+            {
+                const bool mine_ok = L8 < SGNS_CH ? r.mine >= 0 : (L8 == SGNS_CH && r.act);
+                if (!mine_ok) g = 0.f;
+            }
+            float gk[SGNS_CH + 1];
+#pragma unroll
+            for (int k = 0; k <= SGNS_CH; k++) gk[k] = __shfl_sync(FULL, g, k, G);
+#pragma unroll
+            for (int k = 0; k < SGNS_CH; k++) {
+                axpy4(neu, gk[k], r.row[k]);
+                red_add4_if(row_addr(base1, (uint32_t)r.tg[k], pitch), scale4(gk[k], v0), gk[k] != 0.f && live && reds_on);
+            }
+            axpy4(neu, gk[SGNS_CH], cur);
+            axpy4(d1, gk[SGNS_CH], v0);
+            axpy4(cur, gk[SGNS_CH], v0);
+            if (r.act && live) { // syn0[last] += neu, pending in the block's cache
+                float4 dl = delta[(r.slot * Lmax + r.c) * n4 + lane];
+                dl.x += neu.x; dl.y += neu.y; dl.z += neu.z; dl.w += neu.w;
+                delta[(r.slot * Lmax + r.c) * n4 + lane] = dl;
+            }
+        };
+
+        stage_r rA, rB;
+        rA.v0 = rB.v0 = zero4;
+#pragma unroll
+        for (int k = 0; k < SGNS_CH; k++) rA.row[k] = rB.row[k] = zero4;
+        stage_t t1 = stageT();   // round 0
+        stageR(t1, rA, 0);
+        t1 = stageT();           // round 1
+        for (int U = 0; U <= end_round; U += 2) {
+            // the sentence after the newest one is set up as soon as the newest has started (uniform decision)
+            if (more && U + 4 >= start_m1) more = setup_next();
+            stageR(t1, rB, U + 1);
+            t1 = stageT();
+            __syncthreads();
+            compute(rA, U);
+            if (more && U + 5 >= start_m1) more = setup_next();
+            stageR(t1, rA, U + 2);
+            t1 = stageT();
+            __syncthreads();
+            compute(rB, U + 1);
+        }
+        pairs += (unsigned)npairs;
+        __syncthreads();
+    }
+    if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Kernel C': kernel C with the rows of a unit staged in SHARED MEMORY by cp.async instead of registers.
 // EXPERIMENTAL (DGE_SGNS_DEBUG bit 256; never chosen by default; not yet measured on the GPU).  Motivation, from
 // the ncu source page of kernel C on tract x 24 (profiles/r1_stalls_sgns15_tract24.txt): 40.6 % of all stall samples
@@ -1788,7 +2039,7 @@ struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq,
 // 16- or 32-lane group one 128-bit slot (2 or 4 for rows wider than 32 slots).
 // Kernel B (items): groups of 8 / 16 / 32 lanes, one slot per lane (2 or 4 beyond 32 slots).
 static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_parallel, bool staged_rows, bool plain_stores, int blk, bool smem_neg,
-                         bool sentence_resident, bool block_sentence, int block_threads, sgns_variant *out) {
+                         bool sentence_resident, bool block_sentence, int block_threads, bool pipelined, sgns_variant *out) {
     if (n4 > 128) return false;
     sgns_kernel_t seq = nullptr, items = nullptr;
     int Gs = 1, Vs = 1;
@@ -1836,6 +2087,9 @@ static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_p
         if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true, 1> : k_sgns_items_v2<8, false, 1>; }
         else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v2<16, true, 1> : k_sgns_items_v2<16, false, 1>; }
         else { Gi = 32; items = multi ? k_sgns_items_v2<32, true, 1> : k_sgns_items_v2<32, false, 1>; }
+    }
+    else if (n4 <= 8 && sentence_resident && block_sentence && pipelined && negative <= SGNS_CH && block_threads <= 192) { // kernel H
+        code = 10; Gi = 8; items = k_sgns_pipe<192>;
     }
     else if (n4 <= 32 && sentence_resident && block_sentence) { // kernel G: a block owns a sentence, one lane group per centre position
         code = 9;
@@ -2138,7 +2392,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             const bool force_warp_per_sentence = (dbg & 2048) != 0 && !(dbg & 4);
             const bool blk = blk_fits && n4 <= 8 && !(dbg & 8) && !force_warp_per_sentence;
             pick_variant(n4, p->negative, narrow, tp, (dbg & 256) != 0, (dbg & 512) != 0, (dbg >> 12) & 15, smem_neg, sent && !forced_other, blk,
-                         ((Lmax + 32 / G_of - 1) / (32 / G_of)) * 32, &var); // n4 <= 128 was checked
+                         ((Lmax + 32 / G_of - 1) / (32 / G_of)) * 32, (dbg & 131072) != 0, &var); // n4 <= 128 was checked
         }
         sgns_kernel_t fn = sequential ? var.seq : var.items;
         const int G = sequential ? var.G_seq : var.G_items;
@@ -2147,7 +2401,8 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             la = la * LCG_MUL; lc = lc * LCG_MUL + LCG_ADD;
             a.lcg_a[k] = la; a.lcg_c[k] = lc;
         }
-        const bool block_kernel = !sequential && var.items_code == 9;    // kernel G: a.n_groups counts BLOCKS (sentences in flight)
+        const bool pipe_kernel = !sequential && var.items_code == 10;    // kernel H: kernel G with the block's sentences pipelined
+        const bool block_kernel = !sequential && (var.items_code == 9 || pipe_kernel);    // kernel G: a.n_groups counts BLOCKS (sentences in flight)
         const bool sent_kernel = !sequential && (var.items_code == 8 || block_kernel);   // kernel F: a.n_groups counts WARPS (sentences in flight)
         // negative table in shared memory as increment bitmap + per-word prefix (kernel F, narrow rows): exact iff the table never
         // grows by more than one word per slot, which its construction guarantees; checked all the same
@@ -2176,6 +2431,9 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         int gpb = threads / G;
         // dynamic shared memory: the sigmoid table, plus (pipelined item kernel) one staged sentence per group
         auto smem_for = [&](int thr) {
+            if (pipe_kernel)
+                return 3 * ((size_t)Lmax * (size_t)n4 * 16 + sizeof(int32_t) * (size_t)Lmax + sizeof(int32_t) * (size_t)Lmax * (size_t)Lmax * (size_t)std::max(1, p->negative)) +
+                       sizeof(float) * (size_t)p->exp_table_size + 24 * sizeof(int32_t) + (d_negbits ? sizeof(uint32_t) * (size_t)2 * nwords : 0);
             if (block_kernel)
                 return (size_t)Lmax * (size_t)n4 * 16 + sizeof(float) * (size_t)p->exp_table_size + sizeof(int32_t) * (size_t)Lmax +
                        (d_negbits ? sizeof(uint32_t) * (size_t)2 * nwords : 0) + sizeof(int32_t) * (size_t)Lmax * (size_t)Lmax * (size_t)std::max(1, p->negative);

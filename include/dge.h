@@ -225,6 +225,7 @@ enum { DGE_SGNS_F_NO_UPDATES = 1,     /* timing experiment: compute everything, 
        DGE_SGNS_F_STAGED_ROWS = 256,  /* item kernel with the rows of the next unit staged in shared memory (cp.async) */
        DGE_SGNS_F_PLAIN_STORES = 512, /* atomic-free item kernel: plain 128-bit row stores instead of L2 reductions */
        DGE_SGNS_F_BLOCK_PER_SENTENCE = 4, /* kernel G (a block owns a sentence) even with concurrency = 1 (else the default for narrow rows) */
+       DGE_SGNS_F_PIPELINED = 131072,     /* kernel H: kernel G with the sentences of a block pipelined through the wavefront */
        DGE_SGNS_F_ITEM_KERNELS = 65536,   /* the round-1 item kernels B-E with their automatic choice (centres of a sentence in flight at once) */
        DGE_SGNS_F_SMALL_BLOCKS = 16,  /* sentence-resident kernel: 128-thread blocks instead of one 640-thread block per SM */
        DGE_SGNS_F_SENTENCE_RESIDENT = 2048, /* kernel F (a warp owns a sentence for all its centres) where kernel G would be chosen */

@@ -140,6 +140,10 @@ def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negati
         # word of the same sentence)
         e0, e1 = rel_err(concurrency=1, schedule=dge_lib.SCHEDULE_ITEMS, flags=L.F_SENTENCE_RESIDENT | L.F_BLOCK_PER_SENTENCE | L.F_NO_TARGET_PARALLEL)
         assert e0 < 0.05 and e1 < 0.05, ("kernel G", e0, e1)
+        if dim <= 32 and negative <= 5:
+            # kernel H: the same wavefront with the block's sentences pipelined -- one block: two sentences overlap at most
+            e0, e1 = rel_err(concurrency=1, schedule=dge_lib.SCHEDULE_ITEMS, flags=L.F_SENTENCE_RESIDENT | L.F_BLOCK_PER_SENTENCE | L.F_NO_TARGET_PARALLEL | L.F_PIPELINED)
+            assert e0 < 0.1 and e1 < 0.1, ("kernel H", e0, e1)
     e0, e1 = rel_err(concurrency=2)                 # two sentences in flight
     assert e0 < 0.35 and e1 < 0.35, (e0, e1)
     e0, e1 = rel_err()                              # automatic full-GPU schedule
