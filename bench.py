@@ -533,7 +533,7 @@ def run_synth(args, rank, world, D, dist, abi, ctx, local, steps=3, warmup=1):
     wk_ms, sk_ms = float(np.mean([x[1] for x in wms])), float(np.mean([x[1] for x in sms]))
     walk_ach = float(np.mean(toks)) * WALK_BYTES_PER_STEP / (wk_ms * 1e-3) / 1e9
     sg_ach = float(np.mean(pairs)) * sgns_bytes_per_pair(dim, neg) / (sk_ms * 1e-3) / 1e9
-    tw, ts = ncu_traffic("synth100k", "k_walk_alias"), ncu_traffic("synth100k", "k_sgns_items")
+    tw, ts = ncu_traffic("synth100k", "k_walk_alias"), ncu_traffic("synth100k", "sgns")
     out = dict(
         workload=w["desc"], host_generation_s=round(gen_s, 1), graph_build_from_host_coo_s=round(build_s, 2), steps=steps, warmup=warmup,
         value=tot_tok / (t_walk + t_sgns), unit="steps/s", ms_per_step=(t_walk + t_sgns) / steps * 1e3,
@@ -631,7 +631,7 @@ def run_gpu_arm(args, w, rank, world, dist):
     walk_ach = R["per_step_tokens"] * WALK_BYTES_PER_STEP / (R["wk_ms"] * 1e-3) / 1e9
     bpp = sgns_bytes_per_pair(dim, neg)
     sgns_ach = R["pairs_per_launch"] * bpp / (R["sk_ms"] * 1e-3) / 1e9
-    sg_traffic = ncu_traffic(w["name"], "k_sgns_items")
+    sg_traffic = ncu_traffic(w["name"], "sgns")
     if w["name"] == "synth100k":
         sg_roof = dict(bound="hbm", achieved=sgns_ach, peak=peak, unit="GB/s", frac=sgns_ach / peak, peak_source=peak_src)
     else:

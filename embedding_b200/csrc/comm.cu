@@ -143,7 +143,6 @@ struct dge_dp {
     float *aux = nullptr;                 // NCCL: per row and table {contributors, sum_r |d_r|^2}
     unsigned long long *flag = nullptr;   // device word for the barrier all-reduce (carries the error status)
     float *peer[2][DGE_DP_MAX_WORLD];     // PEER: replica of every rank, mapped here
-    bool mapped[DGE_DP_MAX_WORLD];
     int32_t V = 0, stride = 0, n4 = 0;
     int64_t row_lo = 0, row_hi = 0;
     int combine = DGE_COMBINE_ALIGNED;
@@ -309,12 +308,47 @@ static int dp_barrier(dge_dp *dp, int local_error, bool check, int *any_error) {
     return DGE_OK;
 }
 
+void dge_dp_release_cache(dge_ctx *ctx) {
+    for (int r = 0; r < DGE_DP_MAX_WORLD; r++)
+        if (ctx->dp_peer_mapped[r]) { cudaIpcCloseMemHandle(ctx->dp_peer_ptr[r]); ctx->dp_peer_mapped[r] = false; ctx->dp_peer_ptr[r] = nullptr; }
+    if (ctx->dp_arena) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->dp_arena); ctx->dp_arena = nullptr; ctx->dp_arena_bytes = 0; }
+}
+
+// Collective.  The arena only grows; when ANY rank has to reallocate, every rank first drops its mappings of the peers'
+// arenas (nobody frees memory another process still has mapped), then the owners reallocate.
+int dge_dp_arena(dge_ctx *ctx, size_t bytes, float **out) {
+    *out = nullptr;
+    unsigned long long grow = bytes > ctx->dp_arena_bytes ? 1ULL : 0ULL;
+    std::vector<unsigned long long> all((size_t)ctx->world);
+    int rc = dge_comm_allgather_u64(ctx, &grow, 1, all.data());
+    if (rc != DGE_OK) return rc;
+    bool any = false;
+    for (int r = 0; r < ctx->world; r++) any = any || all[r] != 0;
+    int local = DGE_OK;
+    if (any) {
+        cudaStreamSynchronize(ctx->stream);
+        for (int r = 0; r < DGE_DP_MAX_WORLD; r++)
+            if (ctx->dp_peer_mapped[r]) { cudaIpcCloseMemHandle(ctx->dp_peer_ptr[r]); ctx->dp_peer_mapped[r] = false; ctx->dp_peer_ptr[r] = nullptr; }
+        rc = dge_comm_agree(ctx, DGE_OK, "dge_dp_arena (mappings closed)"); // barrier: every mapping of every arena is gone
+        if (rc != DGE_OK) return rc;
+        if (grow) {
+            if (ctx->dp_arena) { cudaFree(ctx->dp_arena); ctx->dp_arena = nullptr; ctx->dp_arena_bytes = 0; }
+            void *q = nullptr;
+            if (cudaMalloc(&q, bytes) != cudaSuccess)
+                local = dge_fail(ctx, DGE_E_CUDA, std::string("dge_dp_arena: cudaMalloc of the replica arena failed (") + cudaGetErrorString(cudaGetLastError()) + ")");
+            else { ctx->dp_arena = (float *)q; ctx->dp_arena_bytes = bytes; }
+        }
+        local = dge_comm_agree(ctx, local, "dge_dp_arena");
+        if (local != DGE_OK) return local;
+    }
+    *out = ctx->dp_arena;
+    return DGE_OK;
+}
+
 void dge_dp_end(dge_dp *dp) {
     if (!dp) return;
     dge_ctx *ctx = dp->ctx;
     cudaStreamSynchronize(ctx->stream);
-    for (int r = 0; r < DGE_DP_MAX_WORLD; r++)
-        if (dp->mapped[r]) { cudaIpcCloseMemHandle(dp->peer[0][r]); cudaIpcCloseMemHandle(dp->peer[1][r]); }
     dge_free(ctx, dp->base[0]); dge_free(ctx, dp->base[1]); dge_free(ctx, dp->aux); dge_free(ctx, dp->flag);
     if (dp->e0) cudaEventDestroy(dp->e0);
     if (dp->e1) cudaEventDestroy(dp->e1);
@@ -329,34 +363,42 @@ int dge_dp_begin(dge_ctx *ctx, float *syn0, float *syn1neg, int32_t V, int32_t s
     const int world = ctx->world, rank = ctx->rank;
     dge_dp *dp = new dge_dp();
     dp->ctx = ctx; dp->cur[0] = syn0; dp->cur[1] = syn1neg; dp->V = V; dp->stride = stride; dp->n4 = n4; dp->combine = combine;
-    for (int r = 0; r < DGE_DP_MAX_WORLD; r++) { dp->mapped[r] = false; dp->peer[0][r] = dp->peer[1][r] = nullptr; }
+    for (int r = 0; r < DGE_DP_MAX_WORLD; r++) dp->peer[0][r] = dp->peer[1][r] = nullptr;
     int local = DGE_OK;
     if (cudaEventCreate(&dp->e0) != cudaSuccess || cudaEventCreate(&dp->e1) != cudaSuccess || dge_malloc(ctx, &dp->flag, 1) != cudaSuccess)
         local = dge_fail(ctx, DGE_E_CUDA, "dge_dp_begin: event / flag allocation failed");
-    // ---- try the peer mapping (every rank must succeed, or all fall back to NCCL together)
-    bool peer_ok = transport != DGE_TRANSPORT_NCCL && world <= DGE_DP_MAX_WORLD && n4 <= 128 && V > 0;
-    unsigned long long mine[17];
+    // ---- peer mapping of the replica arenas (every rank must succeed, or all fall back to NCCL together).  syn0 / syn1neg
+    // live in the rank's arena (dge_dp_arena); a peer's mapping is kept in the ctx and reused while its handle is unchanged.
+    bool peer_ok = transport != DGE_TRANSPORT_NCCL && world <= DGE_DP_MAX_WORLD && n4 <= 128 && V > 0 && syn0 == ctx->dp_arena;
+    const size_t off1 = (size_t)(syn1neg - syn0);   // the same on every rank: V and the pitch are global
+    unsigned long long mine[9];
     memset(mine, 0, sizeof(mine));
     if (peer_ok) {
-        cudaIpcMemHandle_t h0, h1;
+        cudaIpcMemHandle_t h0;
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-        if (cudaIpcGetMemHandle(&h0, syn0) != cudaSuccess || cudaIpcGetMemHandle(&h1, syn1neg) != cudaSuccess) { peer_ok = false; cudaGetLastError(); }
-        else { memcpy(mine, &h0, 64); memcpy(mine + 8, &h1, 64); }
+        if (cudaIpcGetMemHandle(&h0, ctx->dp_arena) != cudaSuccess) { peer_ok = false; cudaGetLastError(); }
+        else memcpy(mine, &h0, 64);
     }
-    mine[16] = peer_ok ? 1 : 0;
-    std::vector<unsigned long long> all((size_t)world * 17);
-    int rc = dge_comm_allgather_u64(ctx, mine, 17, all.data());
+    mine[8] = peer_ok ? 1 : 0;
+    std::vector<unsigned long long> all((size_t)world * 9);
+    int rc = dge_comm_allgather_u64(ctx, mine, 9, all.data());
     if (rc != DGE_OK) { dge_dp_end(dp); return rc; }
-    for (int r = 0; r < world; r++) peer_ok = peer_ok && all[(size_t)r * 17 + 16] == 1;
+    for (int r = 0; r < world; r++) peer_ok = peer_ok && all[(size_t)r * 9 + 8] == 1;
     if (peer_ok) {
         for (int r = 0; r < world && peer_ok; r++) {
             if (r == rank) { dp->peer[0][r] = syn0; dp->peer[1][r] = syn1neg; continue; }
-            cudaIpcMemHandle_t h0, h1;
-            memcpy(&h0, &all[(size_t)r * 17], 64); memcpy(&h1, &all[(size_t)r * 17 + 8], 64);
-            void *p0 = nullptr, *p1 = nullptr;
-            if (cudaIpcOpenMemHandle(&p0, h0, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { peer_ok = false; cudaGetLastError(); break; }
-            if (cudaIpcOpenMemHandle(&p1, h1, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaIpcCloseMemHandle(p0); peer_ok = false; cudaGetLastError(); break; }
-            dp->peer[0][r] = (float *)p0; dp->peer[1][r] = (float *)p1; dp->mapped[r] = true;
+            const void *hbytes = &all[(size_t)r * 9];
+            if (!(ctx->dp_peer_mapped[r] && memcmp(ctx->dp_peer_handle[r], hbytes, 64) == 0)) {
+                if (ctx->dp_peer_mapped[r]) { cudaIpcCloseMemHandle(ctx->dp_peer_ptr[r]); ctx->dp_peer_mapped[r] = false; }
+                cudaIpcMemHandle_t h;
+                memcpy(&h, hbytes, 64);
+                void *q = nullptr;
+                if (cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { peer_ok = false; cudaGetLastError(); break; }
+                ctx->dp_peer_ptr[r] = q; ctx->dp_peer_mapped[r] = true;
+                memcpy(ctx->dp_peer_handle[r], hbytes, 64);
+            }
+            dp->peer[0][r] = (float *)ctx->dp_peer_ptr[r];
+            dp->peer[1][r] = (float *)ctx->dp_peer_ptr[r] + off1;
         }
     }
     // all ranks must have mapped all peers
@@ -367,11 +409,8 @@ int dge_dp_begin(dge_ctx *ctx, float *syn0, float *syn1neg, int32_t V, int32_t s
         if (rc != DGE_OK) { dge_dp_end(dp); return rc; }
         for (int r = 0; r < world; r++) peer_ok = peer_ok && oks[r] == 1;
     }
-    if (!peer_ok) {
-        for (int r = 0; r < DGE_DP_MAX_WORLD; r++)
-            if (dp->mapped[r]) { cudaIpcCloseMemHandle(dp->peer[0][r]); cudaIpcCloseMemHandle(dp->peer[1][r]); dp->mapped[r] = false; }
-        if (transport == DGE_TRANSPORT_PEER) local = dge_fail(ctx, DGE_E_COMM, "dge_dp_begin: peer mapping of the replicas (cudaIpc over NVLink) is unavailable and transport = PEER was demanded");
-    }
+    if (!peer_ok && transport == DGE_TRANSPORT_PEER)
+        local = dge_fail(ctx, DGE_E_COMM, "dge_dp_begin: peer mapping of the replicas (cudaIpc over NVLink) is unavailable and transport = PEER was demanded");
     dp->use_peer = peer_ok;
     // ---- base: the row slice of this rank (PEER) or everything (NCCL)
     if (local == DGE_OK) {
@@ -479,6 +518,7 @@ void dge_comm_destroy(dge_ctx *ctx) {
     if (!ctx || !ctx->comm) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    dge_dp_release_cache(ctx);
     if (g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->comm);
     ctx->comm = nullptr;
     ctx->rank = 0;

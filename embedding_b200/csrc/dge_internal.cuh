@@ -21,6 +21,14 @@ struct dge_ctx {
     std::map<std::string, float> phase_ms;
     int64_t launches = 0;
     cudaMemPool_t pool = nullptr;               // PRIVATE stream-ordered pool of this ctx (not the device's default pool)
+    // data-parallel skip-gram (comm.cu): the replica arena the ranks train in (cudaMalloc: mappable by the other ranks),
+    // kept across dge_sgns_train calls together with the peers' mappings of THEIR arenas -- cudaIpcOpenMemHandle costs
+    // ~20 ms per peer, so it is paid once per communicator, not once per epoch
+    float *dp_arena = nullptr;
+    size_t dp_arena_bytes = 0;
+    void *dp_peer_ptr[16] = {nullptr};
+    unsigned char dp_peer_handle[16][64] = {{0}};
+    bool dp_peer_mapped[16] = {false};
     int refs = 1;                               // the ctx itself + every live graph / corpus / model / flows handle
     bool closed = false;                        // dge_destroy was called; torn down when the last handle is freed
 };
@@ -91,7 +99,6 @@ struct dge_model {
     int64_t pairs = 0;   // (centre, context) updates executed
     int64_t words = 0;   // in-vocabulary tokens of the corpus
     float *syn0 = nullptr, *syn1neg = nullptr; // device [V*stride]
-    bool plain_alloc = false;                  // tables from cudaMalloc (mappable by peer ranks) instead of the ctx pool
     int32_t *id_of_word = nullptr;             // device [V]
 };
 
@@ -108,6 +115,8 @@ int dge_comm_agree(dge_ctx *ctx, int local_status, const char *what);
 // data-parallel exchange of the skip-gram replicas (comm.cu)
 #define DGE_DP_MAX_WORLD 16
 struct dge_dp;
+int dge_dp_arena(dge_ctx *ctx, size_t bytes, float **out);   // collective: the rank's replica arena of at least `bytes`
+void dge_dp_release_cache(dge_ctx *ctx);                      // closes the peer mappings, frees the arena
 int dge_dp_begin(dge_ctx *ctx, float *syn0, float *syn1neg, int32_t V, int32_t stride, int32_t n4, int combine, int transport,
                  dge_dp **out);
 int dge_dp_exchange(dge_dp *dp, int local_error, bool check, int *any_error);

@@ -2117,10 +2117,7 @@ static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_p
 
 static void model_release(dge_model *m) {
     if (!m) return;
-    if (m->plain_alloc) { // data-parallel run: cudaMalloc'ed so that the other ranks could map them (cudaIpc)
-        cudaStreamSynchronize(m->ctx->stream);
-        cudaFree(m->syn0); cudaFree(m->syn1neg);
-    } else { dge_free(m->ctx, m->syn0); dge_free(m->ctx, m->syn1neg); }
+    dge_free(m->ctx, m->syn0); dge_free(m->ctx, m->syn1neg);
     dge_free(m->ctx, m->id_of_word);
     dge_delete_handle(m);
 }
@@ -2317,18 +2314,25 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
     unsigned long long *d_pairs = nullptr;
     const size_t nel = (size_t)(V ? V : 1) * (size_t)stride;
     const bool train = V > 0 && (n_sent > 0 || multi);
-    // the replicas of a data-parallel run come from cudaMalloc so that the other ranks can map them (cudaIpc over NVLink)
-    m->plain_alloc = multi;
-    bool ok = (multi ? (cudaMalloc((void **)&m->syn0, nel * sizeof(float)) == cudaSuccess && cudaMalloc((void **)&m->syn1neg, nel * sizeof(float)) == cudaSuccess)
-                     : (dge_malloc(ctx, &m->syn0, nel) == cudaSuccess && dge_malloc(ctx, &m->syn1neg, nel) == cudaSuccess));
+    // A data-parallel run trains in the rank's replica ARENA (cudaMalloc, mapped by the other ranks over NVLink, kept in the
+    // ctx across calls); the model gets its own copy of the result at the end.  A single-GPU run trains in the model's tables.
+    float *t0 = nullptr, *t1 = nullptr;
+    if (multi) {
+        float *arena = nullptr;
+        const int rc = dge_dp_arena(ctx, 2 * nel * sizeof(float), &arena);   // collective
+        if (rc != DGE_OK) { model_release(m); return rc; }
+        t0 = arena; t1 = arena + nel;
+    }
+    bool ok = dge_malloc(ctx, &m->syn0, nel) == cudaSuccess && dge_malloc(ctx, &m->syn1neg, nel) == cudaSuccess;
+    if (!multi) { t0 = m->syn0; t1 = m->syn1neg; }
     ok = ok && dge_malloc(ctx, &m->id_of_word, (size_t)V) == cudaSuccess && tmp.get(&d_word_of_id, (size_t)n_ids) == cudaSuccess &&
          tmp.get(&d_table, (size_t)p->neg_table_size) == cudaSuccess && tmp.get(&d_exp, (size_t)p->exp_table_size) == cudaSuccess &&
          tmp.get(&d_pairs, 2) == cudaSuccess && (!train || tmp.get(&d_wtok, (size_t)n_sent * (size_t)Lmax) == cudaSuccess);
     local = ok ? DGE_OK : dge_fail(ctx, DGE_E_CUDA, std::string("dge_sgns_train: cudaMalloc failed (") + cudaGetErrorString(cudaGetLastError()) + ")");
     if (multi) local = dge_comm_agree(ctx, local, "dge_sgns_train (tables)");
     if (local != DGE_OK) { model_release(m); return local; }
-    cudaMemsetAsync(m->syn0, 0, nel * sizeof(float), st);
-    cudaMemsetAsync(m->syn1neg, 0, nel * sizeof(float), st);
+    cudaMemsetAsync(t0, 0, nel * sizeof(float), st);
+    cudaMemsetAsync(t1, 0, nel * sizeof(float), st);
     cudaMemsetAsync(d_pairs, 0, 2 * sizeof(unsigned long long), st);
     if (V) cudaMemcpyAsync(m->id_of_word, order.data(), sizeof(int32_t) * (size_t)V, cudaMemcpyHostToDevice, st);
     if (n_ids) cudaMemcpyAsync(d_word_of_id, word_of_id.data(), sizeof(int32_t) * (size_t)n_ids, cudaMemcpyHostToDevice, st);
@@ -2336,7 +2340,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
     cudaMemcpyAsync(d_exp, exp_table.data(), sizeof(float) * exp_table.size(), cudaMemcpyHostToDevice, st);
     if (V) {
         int64_t total = (int64_t)V * p->dim;
-        k_init_syn0<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(m->syn0, V, p->dim, stride, p->seed);
+        k_init_syn0<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t0, V, p->dim, stride, p->seed);
         ctx->launches++;
     }
     ctx->phase_ms["sgns_rounds"] = 0.f; ctx->phase_ms["sgns_sync"] = 0.f; ctx->phase_ms["sgns_transport"] = 0.f; ctx->phase_ms["sgns_dp_setup"] = 0.f;
@@ -2360,7 +2364,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         memset(&a, 0, sizeof(a));
         a.wtok = d_wtok; a.n_sent = n_sent; a.s_off = s_off; a.n_global = std::max<int64_t>(1, n_global);
         a.neg_table = d_table; a.exp_table = d_exp;
-        a.syn0 = m->syn0; a.syn1neg = m->syn1neg;
+        a.syn0 = t0; a.syn1neg = t1;
         a.V = V; a.dim = p->dim; a.stride = stride; a.n4 = n4; a.window = p->window; a.negative = p->negative; a.epochs = p->epochs;
         a.neg_table_size = p->neg_table_size; a.exp_table_size = p->exp_table_size; a.Lmax = Lmax;
         a.lr = p->lr; a.min_lr = p->min_lr; a.seed = p->seed; a.pairs = d_pairs;
@@ -2482,14 +2486,14 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         // (comm.cu dge_dp_exchange: one peer-memory kernel over NVLink, or NCCL all-reduces; rule p->combine).
         int rounds = 1;
         if (multi || p->sync_rounds > 0) {
-            rounds = p->sync_rounds > 0 ? p->sync_rounds : (int)std::max<int64_t>(8, (max_sent + (1 << 18) - 1) >> 18);
+            rounds = p->sync_rounds > 0 ? p->sync_rounds : (int)std::max<int64_t>(8, (max_sent + (1 << 19) - 1) >> 19);
             rounds = (int)std::min<int64_t>(rounds, std::max<int64_t>(1, max_sent));
         }
         dge_dp *dp = nullptr;
         ctx->phase_ms["sgns_dp_setup"] = 0.f;
         if (multi) {
             dge_phase_timer t_dp(ctx, "sgns_dp_setup");   // peer mapping of the replicas (cudaIpc), base slices
-            const int rc = dge_dp_begin(ctx, m->syn0, m->syn1neg, V, stride, n4, p->combine == DGE_COMBINE_DEFAULT ? DGE_COMBINE_ALIGNED : p->combine,
+            const int rc = dge_dp_begin(ctx, t0, t1, V, stride, n4, p->combine == DGE_COMBINE_DEFAULT ? DGE_COMBINE_ALIGNED : p->combine,
                                         p->transport, &dp);
             if (rc != DGE_OK) { model_release(m); return rc; }   // collective: every rank takes this way out
             t_dp.stop();
@@ -2534,6 +2538,10 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         cudaMemcpy(h_pairs, d_pairs, sizeof(h_pairs), cudaMemcpyDeviceToHost);
         m->pairs = (int64_t)h_pairs[0];
         m->words = (int64_t)h_pairs[1];
+    }
+    if (multi) { // the model's own copy of the trained replica (the arena is reused by the next call)
+        cudaMemcpyAsync(m->syn0, t0, nel * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(m->syn1neg, t1, nel * sizeof(float), cudaMemcpyDeviceToDevice, st);
     }
     ce = cudaStreamSynchronize(st);
     if (ce != cudaSuccess) { model_release(m); return dge_fail(ctx, DGE_E_CUDA, std::string("dge_sgns_train: ") + cudaGetErrorString(ce)); }

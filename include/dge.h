@@ -245,7 +245,7 @@ typedef struct {
                                exact order (parity tests); N = N sentences in flight */
     int32_t schedule;       /* DGE_SCHEDULE_ITEMS (default) or DGE_SCHEDULE_SENTENCE */
     int32_t sync_rounds;    /* multi-GPU only: exchanges of the embedding deltas per epoch; 0 = automatic (one per
-                               ~2^18 local sentences, at least 8).  Without a communicator of world > 1 a value > 0
+                               ~2^19 local sentences, at least 8).  Without a communicator of world > 1 a value > 0
                                still cuts the epoch into that many launches (same arithmetic, exchange = identity). */
     int32_t combine;        /* multi-GPU only: DGE_COMBINE_* rule for the per-rank deltas of a row; 0 = default
                                (DGE_COMBINE_ALIGNED).  Must agree on all ranks (checked). */
