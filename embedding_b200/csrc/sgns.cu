@@ -23,6 +23,11 @@
 // automatic schedule: at most this many concurrent (stale) updates per embedding row (measured in
 // profiles/quality_tract_r1.json: nDCG stays inside the oracle's seed-to-seed band up to ~8)
 #define SGNS_STALE_BOUND 8
+// sentence-resident kernels F / G: a sentence holds its context-row updates pending until its rows are flushed, so what
+// must stay bounded is how many sentences IN FLIGHT contain the same (hottest) word: in_flight x P(sentence contains the
+// most frequent word) <= SGNS_HUB_BOUND.  Calibrated on the full-size tract x 24 fixture (296 sentences in flight, the top
+// word in 5.8 % of the sentences: 17 concurrent holders, kNN agreement with the oracle 0.886; 370 in flight: 0.72).
+#define SGNS_HUB_BOUND 18.0
 #define LCG_MUL 25214903917ULL
 #define LCG_ADD 11ULL
 
@@ -2407,6 +2412,10 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         }
         const bool pipe_kernel = !sequential && var.items_code == 10;    // kernel H: kernel G with the block's sentences pipelined
         const bool block_kernel = !sequential && (var.items_code == 9 || pipe_kernel);    // kernel G: a.n_groups counts BLOCKS (sentences in flight)
+        // sentences in flight the hottest word allows (global counts and sentences in a data-parallel run)
+        const double hub_p = std::min(1.0, (double)cnt[order[0]] / (double)std::max<int64_t>(1, n_global));
+        const int64_t hub_sentences = std::max<int64_t>(1, (int64_t)(SGNS_HUB_BOUND / std::max(hub_p, 1e-9)));
+        ctx->phase_ms["sgns_hub_bound"] = (float)hub_sentences;
         const bool sent_kernel = !sequential && (var.items_code == 8 || block_kernel);   // kernel F: a.n_groups counts WARPS (sentences in flight)
         // negative table in shared memory as increment bitmap + per-word prefix (kernel F, narrow rows): exact iff the table never
         // grows by more than one word per slot, which its construction guarantees; checked all the same
@@ -2460,6 +2469,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         if (p->concurrency > 0) want = sequential ? (int64_t)p->concurrency : (int64_t)p->concurrency * (sent_kernel ? GPW : Lmax);
         else if (sequential) want = full_groups;
         else want = std::min<int64_t>(full_groups, std::max<int64_t>(gpb, (int64_t)SGNS_STALE_BOUND * V / (p->negative + 1)));
+        if (sent_kernel && p->concurrency == 0) want = std::min<int64_t>(want, hub_sentences * GPW);   // kernel F: a warp (GPW groups) per sentence
         if (!sequential && (dbg & 8)) want = 1; // one warp, one item at a time, strictly in corpus order (arithmetic check against the oracle)
         want = std::max<int64_t>(1, std::min(want, sent_kernel ? std::max<int64_t>(1, n_sent) * GPW : units));
         while (!big_block && !block_kernel && threads > 32 && threads > G && want < (int64_t)ctx->sm_count * gpb) { threads >>= 1; gpb = threads / G; }
@@ -2473,7 +2483,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         }
         if (block_kernel) { // sentences in flight = blocks: `concurrency`, or what fills the GPU, or the staleness bound (pairs in flight / Lmax)
             const int64_t full_blocks = (int64_t)ctx->sm_count * per_sm;
-            int64_t wb = p->concurrency > 0 ? p->concurrency : std::min<int64_t>(full_blocks, std::max<int64_t>(1, (int64_t)SGNS_STALE_BOUND * V / (p->negative + 1) / Lmax));
+            int64_t wb = p->concurrency > 0 ? p->concurrency : std::min<int64_t>(full_blocks, hub_sentences);
             wb = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(wb, full_blocks), std::max<int64_t>(1, n_sent)));
             blocks = (int)wb;
             a.n_groups = blocks;
