@@ -196,3 +196,25 @@ def test_sgns_error_behaviour(dge_lib, ctx):
     # everything below min_count: empty vocabulary, not an error
     m = dge_lib.Model.train(ctx, [c], dge_lib.sgns_params(min_count=100))
     assert m.V == 0 and m.pairs == 0
+
+
+def test_large_vocabulary_is_ranked_on_the_device(dge_lib, oracle, ctx):
+    """Id spaces of 65 536 and more are ranked by a 64-bit radix sort on the device (descending count, ties by ascending
+    id) and the unigram^0.75 table takes pow() once per run of equal counts: vocabulary order, negative table (through
+    the pair count and the sequential schedule's result) and minWordFrequency filtering must still be the oracle's."""
+    rng = np.random.default_rng(9)
+    n_ids = 200_000
+    tok = np.minimum((rng.pareto(0.9, size=(60_000, 6)) * 40).astype(np.int64), n_ids - 1).astype(np.int32)   # heavy ties in the tail
+    tok[rng.random(tok.shape) < 0.05] = -1
+    tok[:, 0] = np.maximum(tok[:, 0], 0)
+    kw = dict(dim=8, window=3, negative=5, min_count=2, seed=4)
+    _, want = oracle.vocab(tok, n_ids, 2)
+    c = dge_lib.Corpus.from_tokens(ctx, tok, n_ids)
+    m = dge_lib.Model.train(ctx, [c], dge_lib.sgns_params(concurrency=1, **kw))
+    syn0, ids = m.vectors()
+    assert np.array_equal(ids, want["id_of_word"]) and m.V == want["V"]
+    ref = oracle.sgns_train(tok, n_ids, oracle.sgns_params(threads=1, **kw))
+    assert m.pairs == ref["pairs"]
+    assert np.allclose(syn0, ref["syn0"], atol=2e-4)       # same negatives => the sequential schedule reproduces the oracle
+    m.free()
+    c.free()
