@@ -53,6 +53,7 @@ struct sgns_args {
     const uint32_t *neg_bits;  // kernel F: the negative table as increment bitmap [nwords] + per-word prefix [nwords], or NULL
     uint64_t lcg_a[SGNS_MAX_NEG], lcg_c[SGNS_MAX_NEG]; // (k+1)-step jump of the negative-sampling LCG
     int32_t dbg;
+    int32_t stages;            // kernel J: stages of the row ring in shared memory (2 .. 4)
 };
 
 __host__ __device__ static inline uint64_t mix64(uint64_t z) {
@@ -1401,6 +1402,232 @@ k_sgns_pipe(const sgns_args a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Kernel I: kernel G's wavefront with a WARP per pair and the round's pairs handed to the block's warps dynamically.
+// What the ncu capture of kernel G shows (profiles/r2s13_sgns_block_tract24.json): a sentence of 24 tokens with word2vec's
+// random window has ~283 pairs in 45 rounds, 6.3 active centres per round on average -- 60 % of kernel G's warp-rounds
+// carry no pair and still run the staging code (163 warp instructions per pair), the active warps run a 330-instruction
+// chain per round with the K + 1 targets of a pair sequential in each lane, and 35 % of all stall samples wait at the
+// round barrier for that chain.  Parity caps the sentences in flight (two blocks per SM), so the round latency is what
+// sets the throughput.  Here
+//   * the pairs of round u (centre i, context u - i, inside i's window) are listed per round while the negatives are
+//     drawn, and warp w takes entries w, w + W, ... of the list: no warp stages or computes an empty slot;
+//   * a pair is spread over the whole warp: lane = (target t = lane / 4, quarter q = lane % 4), t = 0 the centre's own
+//     output row, t = 1 .. K the negatives; a lane holds float4 slots q and 4 + q of ITS target's row and of the context
+//     row.  The K + 1 dot products are two shuffles deep, every lane computes its target's sigmoid itself, the negative
+//     rows go out as two 128-bit reductions per lane, and neu1e = sum_t g_t row_t is a 7-shuffle transposed reduction
+//     that leaves one float of the sum in every lane;
+//   * the centres' output rows (their private copies and deltas) live in shared memory beside the context-row deltas,
+//     because a centre is no longer tied to a lane group;
+//   * the rows of a warp's next pair are requested before the current one is computed (two register sets), as in kernel G.
+// Same pair / negative enumeration, same wavefront order (conflict-equivalent to the centre-major loop), same flush
+// points as kernel G.  Rows of up to 8 slots, K <= 7, sentences of up to 32 tokens.
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 2)
+k_sgns_wave(const sgns_args a) {
+    extern __shared__ __align__(16) int32_t smem_i[];
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int RP = 32; // floats per cached row: 8 slots
+    const int n4 = a.n4, Lmax = a.Lmax;
+    const int nwords = (a.neg_table_size + 31) >> 5;
+    const int K = a.V >= 2 ? a.negative : 0;
+    const bool smem_neg = a.neg_bits != nullptr;
+    float *delta = reinterpret_cast<float *>(smem_i);       // [Lmax][32] pending syn0 updates of the sentence's context rows
+    float *cur = delta + Lmax * RP;                         // [Lmax][32] the centres' output rows syn1neg[w_i] as this sentence sees them
+    float *d1 = cur + Lmax * RP;                            // [Lmax][32] what this sentence has added to them
+    float *s_exp = d1 + Lmax * RP;
+    int32_t *tok = reinterpret_cast<int32_t *>(s_exp + a.exp_table_size);
+    int32_t *s_lo = tok + Lmax, *s_hi = s_lo + Lmax, *s_fr = s_hi + Lmax;
+    int32_t *s_cnt = s_fr + Lmax;                           // [2 Lmax] pairs of round u
+    uint32_t *s_bits = reinterpret_cast<uint32_t *>(s_cnt + 2 * Lmax);
+    uint32_t *s_pref = s_bits + nwords;
+    int32_t *s_tg = reinterpret_cast<int32_t *>(s_bits + (smem_neg ? 2 * nwords : 0)); // [Lmax][Lmax][K] negatives of every pair
+    uint8_t *s_list = reinterpret_cast<uint8_t *>(s_tg + Lmax * Lmax * max(K, 1));    // [2 Lmax][Lmax] centres of round u
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
+    for (int q = tid; q < a.exp_table_size; q += blockDim.x) s_exp[q] = a.exp_table[q];
+    if (smem_neg)
+        for (int q = tid; q < 2 * nwords; q += blockDim.x) s_bits[q] = a.neg_bits[q];
+    const int t = lane >> 2, q4 = lane & 3;
+    const bool liveA = q4 < n4, liveB = 4 + q4 < n4;
+    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+    const int my_pos = (q4 + (h16 ? 4 : 0)) * 4 + (h8 ? 2 : 0) + (h4 ? 1 : 0); // the float of the row this lane ends up owning in the neu1e sum
+    const bool pos_live = (q4 + (h16 ? 4 : 0)) < n4;
+    const int E = a.exp_table_size;
+    const float idx_scale = (float)E / SGNS_MAX_EXP / 2.0f;
+    const int win = a.window;
+    const int64_t N = a.n_sent;
+    const double inv_total = 1.0 / (double)((int64_t)a.epochs * a.n_global);
+    const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
+    const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t pitch = (uint32_t)a.stride * 4u;
+    const char *base0 = reinterpret_cast<const char *>(a.syn0) + q4 * 16;
+    const char *base1 = reinterpret_cast<const char *>(a.syn1neg) + q4 * 16;
+    const float my_label = t == 0 ? 1.f : 0.f;
+    const bool reds_on = !(a.dbg & 1);
+    unsigned long long pairs = 0;
+
+    struct item_t { int u, i, c; int32_t tg; uint64_t ra; float4 vA, vB, rA, rB; };
+    item_t A, B;
+    A.vA = A.vB = A.rA = A.rB = B.vA = B.vB = B.rA = B.rB = zero4; // slots that carry no data are never loaded and stay zero
+    A.ra = B.ra = 0;
+
+    for (int ep = a.ep_lo; ep < a.ep_hi; ep++) {
+        int32_t tk_next = -1;
+        if (tid < Lmax && a.s_lo + blockIdx.x < a.s_hi) tk_next = a.wtok[(int64_t)tid * N + a.s_lo + blockIdx.x];
+        for (int64_t s = a.s_lo + blockIdx.x; s < a.s_hi; s += a.n_groups) { // n_groups = blocks = sentences in flight
+            __syncthreads(); // the previous sentence's final flush has read the caches
+            const int32_t tk = tk_next;
+            if (tid < Lmax) {
+                tok[tid] = tk;
+                if (s + a.n_groups < a.s_hi) tk_next = a.wtok[(int64_t)tid * N + s + a.n_groups]; // lands during this sentence's rounds
+            }
+            for (int e = tid; e < Lmax * RP; e += blockDim.x) { delta[e] = 0.f; d1[e] = 0.f; }
+            const int n_tok = __syncthreads_count(tid < Lmax && tk >= 0); // the compacted sentence: tokens first, then padding
+            if (n_tok < 2) continue;
+            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * a.n_global + a.s_off + s) * inv_total);
+            if (alpha < a.min_lr) alpha = a.min_lr;
+            const float g_hi = (my_label - 1.f) * alpha, g_lo = my_label * alpha;
+            const uint64_t S = sgns_sentence_rng(a.seed, ep, s + a.s_off);
+            const int R = 2 * n_tok - 3;
+            if (tid < n_tok) { // the centre's window (word2vec's random shrink), clamped to the sentence
+                const int b = (int32_t)(uint32_t)sgns_position_rng(S, tid) % win;
+                const int hi_c = min(tid + win - b, n_tok - 1);
+                s_lo[tid] = max(tid - win + b, 0);
+                s_hi[tid] = hi_c;
+                s_fr[tid] = tid + hi_c + 1; // the round after its last context: its output-row delta is sent then
+            }
+            for (int e = tid; e < n_tok * 8; e += blockDim.x) { // private copies of the centres' output rows
+                const int i = e >> 3, slot = e & 7;
+                float4 v = zero4;
+                if (slot < n4) v = __ldcg(reinterpret_cast<const float4 *>(a.syn1neg + (int64_t)tok[i] * a.stride) + slot);
+                reinterpret_cast<float4 *>(cur)[i * 8 + slot] = v;
+            }
+            __syncthreads();
+            // ---- draw phase: the K negatives of every pair inside a window; the pairs of every round
+            for (int e = tid; e < n_tok * n_tok * K; e += blockDim.x) {
+                const int kq = e % K, ic = e / K;
+                const int cc = ic % n_tok, ii = ic / n_tok;
+                if (cc == ii || cc < s_lo[ii] || cc > s_hi[ii]) continue;
+                const uint64_t nsk = a.lcg_a[kq] * sgns_pair_rng(S, ii, cc) + a.lcg_c[kq]; // the LCG is affine: state after kq + 1 steps
+                const uint32_t idx = mod48(nsk >> 16, tsize, inv_tsize);
+                int32_t tg = smem_neg ? neg_lookup(s_bits, s_pref, idx) : a.neg_table[idx];
+                if (tg <= 0 || tg >= a.V) tg = (int32_t)mod64(nsk, vm1, inv_vm1) + 1;   // DL4J: target = r % (V - 1) + 1
+                s_tg[(ii * Lmax + cc) * K + kq] = tg == tok[ii] ? -1 : tg;
+            }
+            if (tid >= 1 && tid <= R) { // round u = tid: centre i meets context u - i
+                int n = 0;
+                for (int i = max(0, tid - (n_tok - 1)); i <= min(n_tok - 1, tid); i++) {
+                    const int c = tid - i;
+                    if (c != i && c >= s_lo[i] && c <= s_hi[i] && tok[c] != tok[i]) s_list[tid * Lmax + n++] = (uint8_t)i;
+                }
+                s_cnt[tid] = n;
+            }
+            __syncthreads();
+
+            int ubar = 0; // rounds this warp has opened
+            auto open_round = [&]() {
+                asm volatile("bar.sync 0;" ::: "memory"); // what round u - 1 wrote to the caches is read in round u
+                ubar++;
+                if (warp == W - 1) { // the warp with the fewest pairs sends what is complete
+                    const int c = ubar - n_tok; // context row c saw its last centre in round c + n_tok - 1 at the latest
+                    if (c >= 0 && lane < n4) {
+                        const float4 dl = reinterpret_cast<const float4 *>(delta)[c * 8 + lane];
+                        if (reds_on && (dl.x != 0.f || dl.y != 0.f || dl.z != 0.f || dl.w != 0.f))
+                            red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)tok[c] * a.stride) + lane, dl);
+                    }
+                    unsigned mk = __ballot_sync(FULL, lane < n_tok && s_fr[lane] == ubar);
+                    while (mk) { // centres whose contexts are exhausted
+                        const int i = __ffs(mk) - 1;
+                        mk &= mk - 1;
+                        if (lane < n4 && reds_on)
+                            red_add4(reinterpret_cast<float4 *>(a.syn1neg + (int64_t)tok[i] * a.stride) + lane, reinterpret_cast<const float4 *>(d1)[i * 8 + lane]);
+                    }
+                }
+            };
+            int pu = 1, pp = warp; // the next list entry this warp has not requested yet
+            auto issue = [&](item_t &r) {
+                while (pu <= R && pp >= s_cnt[pu]) { pu++; pp = warp; }
+                r.u = pu;
+                if (pu > R) return;
+                const int i = s_list[pu * Lmax + pp], c = pu - i;
+                pp += W;
+                r.i = i; r.c = c;
+                const int32_t tg = (t >= 1 && t <= K) ? s_tg[(i * Lmax + c) * K + t - 1] : -1;
+                r.tg = tg;
+                const uint64_t va = row_addr(base0, (uint32_t)tok[c], pitch);
+                r.ra = row_addr(base1, (uint32_t)max(tg, 0), pitch);
+                ldcg4_into(r.vA, va, liveA);
+                ldcg4_into(r.vB, va + 64, liveB);
+                ldcg4_into(r.rA, r.ra, tg >= 0 && liveA);
+                ldcg4_into(r.rB, r.ra + 64, tg >= 0 && liveB);
+            };
+            auto compute = [&](const item_t &r) {
+                const float4 *dc = reinterpret_cast<const float4 *>(delta) + r.c * 8;
+                float4 *ci = reinterpret_cast<float4 *>(cur) + r.i * 8;
+                // the context row as this sentence sees it: L2's value + the sentence's pending delta
+                float4 vA = add4(r.vA, dc[q4]), vB = add4(r.vB, dc[4 + q4]);
+                float4 rA = r.rA, rB = r.rB;
+                if (t == 0) { rA = ci[q4]; rB = ci[4 + q4]; }
+                float part = dot4(vA, rA) + dot4(vB, rB);
+                part += __shfl_xor_sync(FULL, part, 1);
+                part += __shfl_xor_sync(FULL, part, 2);
+                float g = sgns_g_lane(part, my_label, alpha, g_hi, g_lo, s_exp, E, idx_scale);
+                if (!(t == 0 || r.tg >= 0)) g = 0.f;
+                const float4 uA = scale4(g, vA), uB = scale4(g, vB); // the target row's update
+                const bool send = t != 0 && g != 0.f && reds_on;
+                red_add4_if(r.ra, uA, send && liveA);
+                red_add4_if(r.ra + 64, uB, send && liveB);
+                if (t == 0) { // the centre's own output row: private copy and its delta
+                    float4 *di = reinterpret_cast<float4 *>(d1) + r.i * 8;
+                    if (liveA) { ci[q4] = add4(rA, uA); di[q4] = add4(di[q4], uA); }
+                    if (liveB) { ci[4 + q4] = add4(rB, uB); di[4 + q4] = add4(di[4 + q4], uB); }
+                }
+                // neu1e = sum over the targets of g_t row_t: transposed reduction over the lanes' target bits
+                const float4 nA = scale4(g, rA), nB = scale4(g, rB);
+                const float m0 = (h16 ? nB.x : nA.x) + __shfl_xor_sync(FULL, h16 ? nA.x : nB.x, 16);
+                const float m1 = (h16 ? nB.y : nA.y) + __shfl_xor_sync(FULL, h16 ? nA.y : nB.y, 16);
+                const float m2 = (h16 ? nB.z : nA.z) + __shfl_xor_sync(FULL, h16 ? nA.z : nB.z, 16);
+                const float m3 = (h16 ? nB.w : nA.w) + __shfl_xor_sync(FULL, h16 ? nA.w : nB.w, 16);
+                const float p0 = (h8 ? m2 : m0) + __shfl_xor_sync(FULL, h8 ? m0 : m2, 8);
+                const float p1 = (h8 ? m3 : m1) + __shfl_xor_sync(FULL, h8 ? m1 : m3, 8);
+                const float val = (h4 ? p1 : p0) + __shfl_xor_sync(FULL, h4 ? p0 : p1, 4);
+                if (pos_live) delta[r.c * RP + my_pos] += val; // syn0[last] += neu1e, pending in the block's cache
+                if (lane == 0) pairs++;
+            };
+
+            issue(A);
+            while (A.u <= R) {
+                issue(B); // the rows of this warp's next pair are in flight while this one is computed
+                while (ubar < A.u) open_round();
+                compute(A);
+                if (B.u > R) break;
+                issue(A);
+                while (ubar < B.u) open_round();
+                compute(B);
+            }
+            while (ubar < R) open_round();
+            __syncthreads();
+            // what the rounds did not send: the context rows whose last centre came in the final rounds, the last centres' rows
+            for (int e = tid; e < n_tok * 8; e += blockDim.x) {
+                const int row = e >> 3, slot = e & 7;
+                if (slot >= n4 || !reds_on) continue;
+                if (row + n_tok > R) {
+                    const float4 dl = reinterpret_cast<const float4 *>(delta)[row * 8 + slot];
+                    if (dl.x != 0.f || dl.y != 0.f || dl.z != 0.f || dl.w != 0.f)
+                        red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)tok[row] * a.stride) + slot, dl);
+                }
+                if (s_fr[row] > R) {
+                    const float4 dd = reinterpret_cast<const float4 *>(d1)[row * 8 + slot];
+                    if (dd.x != 0.f || dd.y != 0.f || dd.z != 0.f || dd.w != 0.f)
+                        red_add4(reinterpret_cast<float4 *>(a.syn1neg + (int64_t)tok[row] * a.stride) + slot, dd);
+                }
+            }
+        }
+    }
+    if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Kernel C': kernel C with the rows of a unit staged in SHARED MEMORY by cp.async instead of registers.
 // EXPERIMENTAL (DGE_SGNS_DEBUG bit 256; never chosen by default; not yet measured on the GPU).  Motivation, from
 // the ncu source page of kernel C on tract x 24 (profiles/r1_stalls_sgns15_tract24.txt): 40.6 % of all stall samples
@@ -2025,6 +2252,241 @@ k_sgns_items_tp(const sgns_args a) {
     if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Kernel J: kernel G's wavefront with the block split into CRITICAL and HELPER warps.  What bounds kernel G
+// (profiles/r2s13_sgns_block_tract24.json): parity caps the sentences in flight at two blocks per SM, a sentence is a
+// chain of 2 n - 3 barrier-separated rounds, and a round costs ~1 200 cycles because the warp that owns a centre runs ~330
+// instructions in order between two barriers although only a third of them lie on the dependency path
+// (pending delta -> K + 1 dot products -> sigmoid -> neu1e -> pending delta); the rest stages the next round (addresses,
+// L2 loads) and sends the reductions.  Here that rest is done by a second set of warps:
+//   * helper warp h serves the four centres of critical warp h.  In round u it sends the negative-row reductions of round
+//     u - 1 (the critical warp leaves each pair's K gradient scales and the context row it used in shared memory), the
+//     context-row delta that became final, and requests the rows of round u + ST - 1 with cp.async (LDGSTS, L2 only) into a
+//     ring of ST stages in shared memory -- no register staging, L2 latency hidden over ST - 1 rounds;
+//   * the critical warp reads its pair's K + 1 rows from the ring, runs the dependency path and nothing else.
+// One block barrier per round, as before; same pair / negative enumeration, same wavefront order, same flush points as
+// kernel G (a negative-row reduction leaves one round later).  Rows of up to 8 slots, K <= 5, sentences of up to 32 tokens.
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 2)
+k_sgns_duo(const sgns_args a) {
+    constexpr int G = 8;
+    constexpr int KM = SGNS_CH;
+    extern __shared__ __align__(16) int32_t smem_j[];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int n4 = a.n4, Lmax = a.Lmax, ST = a.stages;
+    const int nwords = (a.neg_table_size + 31) >> 5;
+    const int K = a.V >= 2 ? a.negative : 0;
+    const bool smem_neg = a.neg_bits != nullptr;
+    const int ROWS = KM + 1;                                  // rows of a pair in the ring: the context row, then the negatives
+    float4 *stage = reinterpret_cast<float4 *>(smem_j);       // [ST][Lmax][ROWS][n4]
+    float4 *delta = stage + (size_t)ST * Lmax * ROWS * n4;    // [Lmax][n4] pending syn0 updates of the sentence's context rows
+    float4 *xv = delta + Lmax * n4;                           // [2][Lmax][n4] the context row a pair used (for the helper's reductions)
+    float *xg = reinterpret_cast<float *>(xv + 2 * Lmax * n4); // [2][Lmax][8] its K gradient scales
+    float *s_exp = xg + 2 * Lmax * 8;
+    int32_t *tok = reinterpret_cast<int32_t *>(s_exp + a.exp_table_size);
+    int32_t *s_lo = tok + Lmax, *s_hi = s_lo + Lmax;
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_hi + Lmax); // [2 Lmax] centres with a pair in round u
+    uint32_t *s_bits = s_mask + 2 * Lmax;
+    uint32_t *s_pref = s_bits + nwords;
+    int32_t *s_tg = reinterpret_cast<int32_t *>(s_bits + (smem_neg ? 2 * nwords : 0)); // [Lmax][Lmax][K] negatives of every pair
+    const int tid = threadIdx.x;
+    const int NW = (blockDim.x >> 5) >> 1;                    // critical warps = helper warps
+    const bool helper = (tid >> 5) >= NW;
+    const int rt = helper ? tid - NW * 32 : tid;              // thread index within the role
+    const int lane = rt % G, i = rt / G;                      // slot of the row; centre position served
+    for (int q = tid; q < a.exp_table_size; q += blockDim.x) s_exp[q] = a.exp_table[q];
+    if (smem_neg)
+        for (int q = tid; q < 2 * nwords; q += blockDim.x) s_bits[q] = a.neg_bits[q];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = tid; q < ST * Lmax * ROWS * n4; q += blockDim.x) stage[q] = zero4; // the ring only ever holds table rows afterwards
+    const int E = a.exp_table_size;
+    const float idx_scale = (float)E / SGNS_MAX_EXP / 2.0f;
+    const int win = a.window;
+    const int64_t N = a.n_sent;
+    const double inv_total = 1.0 / (double)((int64_t)a.epochs * a.n_global);
+    const uint32_t tsize = (uint32_t)a.neg_table_size, vm1 = (uint32_t)(a.V > 1 ? a.V - 1 : 1);
+    const double inv_tsize = 1.0 / (double)tsize, inv_vm1 = 1.0 / (double)vm1;
+    const bool live = lane < n4;
+    const uint32_t pitch = (uint32_t)a.stride * 4u;
+    const char *base0 = reinterpret_cast<const char *>(a.syn0) + (live ? lane : 0) * 16;
+    const char *base1 = reinterpret_cast<const char *>(a.syn1neg) + (live ? lane : 0) * 16;
+    const int L8 = lane & 7;
+    const bool up4 = (lane & 4) != 0, up2 = (lane & 2) != 0, up1 = (lane & 1) != 0;
+    const float my_label = L8 == KM ? 1.f : 0.f;
+    const bool reds_on = !(a.dbg & 1);
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+    unsigned long long pairs = 0;
+
+    for (int ep = a.ep_lo; ep < a.ep_hi; ep++) {
+        int32_t tk_next = -1;
+        if (tid < Lmax && a.s_lo + blockIdx.x < a.s_hi) tk_next = a.wtok[(int64_t)tid * N + a.s_lo + blockIdx.x];
+        for (int64_t s = a.s_lo + blockIdx.x; s < a.s_hi; s += a.n_groups) { // n_groups = blocks = sentences in flight
+            __syncthreads(); // the previous sentence's final flush has read the caches
+            const int32_t tk = tk_next;
+            if (tid < Lmax) {
+                tok[tid] = tk;
+                if (s + a.n_groups < a.s_hi) tk_next = a.wtok[(int64_t)tid * N + s + a.n_groups]; // lands during this sentence's rounds
+            }
+            for (int e = tid; e < Lmax * n4; e += blockDim.x) delta[e] = zero4;
+            const int n_tok = __syncthreads_count(tid < Lmax && tk >= 0); // the compacted sentence: tokens first, then padding
+            if (n_tok < 2) continue;
+            float alpha = a.lr * (float)(1.0 - (double)((int64_t)ep * a.n_global + a.s_off + s) * inv_total);
+            if (alpha < a.min_lr) alpha = a.min_lr;
+            const float g_hi = (my_label - 1.f) * alpha, g_lo = my_label * alpha;
+            const uint64_t S = sgns_sentence_rng(a.seed, ep, s + a.s_off);
+            const int R = 2 * n_tok - 3;
+            const bool valid = i < n_tok;
+            const int32_t w1 = valid ? tok[i] : 0;
+            float4 cur = zero4, d1 = zero4;
+            if (!helper) ldcg4_into(cur, row_addr(base1, (uint32_t)w1, pitch), valid && live); // private copy of syn1neg[w1]
+            if (tid < n_tok) { // the centre's window (word2vec's random shrink), clamped to the sentence
+                const int b = (int32_t)(uint32_t)sgns_position_rng(S, tid) % win;
+                s_lo[tid] = max(tid - win + b, 0);
+                s_hi[tid] = min(tid + win - b, n_tok - 1);
+            }
+            __syncthreads();
+            // ---- draw phase: the K negatives of every pair inside a window; the centres of every round
+            for (int e = tid; e < n_tok * n_tok * K; e += blockDim.x) {
+                const int kq = e % K, ic = e / K;
+                const int cc = ic % n_tok, ii = ic / n_tok;
+                if (cc == ii || cc < s_lo[ii] || cc > s_hi[ii]) continue;
+                const uint64_t nsk = a.lcg_a[kq] * sgns_pair_rng(S, ii, cc) + a.lcg_c[kq]; // the LCG is affine: state after kq + 1 steps
+                const uint32_t idx = mod48(nsk >> 16, tsize, inv_tsize);
+                int32_t tg = smem_neg ? neg_lookup(s_bits, s_pref, idx) : a.neg_table[idx];
+                if (tg <= 0 || tg >= a.V) tg = (int32_t)mod64(nsk, vm1, inv_vm1) + 1;   // DL4J: target = r % (V - 1) + 1
+                s_tg[(ii * Lmax + cc) * K + kq] = tg == tok[ii] ? -1 : tg;
+            }
+            if (tid >= 1 && tid <= R + 1) { // round u = tid: centre ii meets context u - ii
+                uint32_t m = 0;
+                if (tid <= R)
+                    for (int ii = max(0, tid - (n_tok - 1)); ii <= min(n_tok - 1, tid); ii++) {
+                        const int c = tid - ii;
+                        if (c != ii && c >= s_lo[ii] && c <= s_hi[ii] && tok[c] != tok[ii]) m |= 1u << ii;
+                    }
+                s_mask[tid] = m; // round R + 1 is empty
+            }
+            __syncthreads();
+            const int fr = valid ? i + s_hi[i] + 1 : 0; // the round after the centre's last context: its output-row delta is sent then
+
+            if (!helper) {
+                // ================= critical warps: the dependency path of the rounds =================
+                int npairs = 0;
+                uint32_t m = s_mask[1];
+                int su = 1 % ST; // u % ST
+                for (int u = 1; u <= R; u++, su = (su + 1 == ST ? 0 : su + 1)) {
+                    // what does not depend on round u - 1 is read before the barrier
+                    const bool act = valid && ((m >> i) & 1u);
+                    const int c = act ? u - i : 0;
+                    const int32_t mine = (act && L8 < K) ? s_tg[(i * Lmax + c) * K + L8] : -1;
+                    const float4 *st = stage + ((size_t)(su * Lmax + (valid ? i : 0)) * ROWS) * n4 + (live ? lane : 0);
+                    m = s_mask[u + 1];
+                    asm volatile("bar.sync 0;" ::: "memory");
+                    if (u == fr) red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, live && reds_on);
+                    if (!__any_sync(FULL, act)) continue;
+                    float4 v0 = zero4, row[KM];
+#pragma unroll
+                    for (int k = 0; k < KM; k++) row[k] = zero4;
+                    float4 dl = zero4;
+                    if (live) {
+                        v0 = st[0];
+#pragma unroll
+                        for (int k = 0; k < KM; k++) row[k] = st[(k + 1) * n4];
+                        dl = delta[c * n4 + lane];
+                    }
+                    npairs += act;
+                    const float4 v0p = add4(v0, dl); // L2's value + what this sentence has added to the row so far
+                    float d0 = dot4(v0p, row[0]), d1v = dot4(v0p, row[1]), d2 = dot4(v0p, row[2]), d3 = dot4(v0p, row[3]);
+                    float d4 = dot4(v0p, row[4]), d5 = dot4(v0p, cur);
+                    float e0 = (up4 ? d4 : d0) + __shfl_xor_sync(FULL, up4 ? d0 : d4, 4);
+                    float e1 = (up4 ? d5 : d1v) + __shfl_xor_sync(FULL, up4 ? d1v : d5, 4);
+                    float e2 = (up4 ? 0.f : d2) + __shfl_xor_sync(FULL, up4 ? d2 : 0.f, 4);
+                    float e3 = (up4 ? 0.f : d3) + __shfl_xor_sync(FULL, up4 ? d3 : 0.f, 4);
+                    float f0 = (up2 ? e2 : e0) + __shfl_xor_sync(FULL, up2 ? e0 : e2, 2);
+                    float f1 = (up2 ? e3 : e1) + __shfl_xor_sync(FULL, up2 ? e1 : e3, 2);
+                    float tot = (up1 ? f1 : f0) + __shfl_xor_sync(FULL, up1 ? f0 : f1, 1);
+                    float g = sgns_g_lane(tot, my_label, alpha, g_hi, g_lo, s_exp, E, idx_scale);
+                    {
+                        const bool mine_ok = L8 < KM ? mine >= 0 : (L8 == KM && act);
+                        if (!mine_ok) g = 0.f;
+                    }
+                    float gk[KM + 1];
+#pragma unroll
+                    for (int k = 0; k <= KM; k++) gk[k] = __shfl_sync(FULL, g, k, G);
+                    float4 neu = scale4(gk[KM], cur);
+#pragma unroll
+                    for (int k = 0; k < KM; k++) axpy4(neu, gk[k], row[k]);
+                    if (act && live) delta[c * n4 + lane] = add4(dl, neu); // syn0[last] += neu1e, pending in the block's cache
+                    axpy4(d1, gk[KM], v0p);
+                    axpy4(cur, gk[KM], v0p);
+                    // for the helper: the scales of the K negative rows and the context row they multiply
+                    if (valid && L8 < KM) xg[((u & 1) * Lmax + i) * 8 + L8] = g;
+                    if (valid && live) xv[((u & 1) * Lmax + i) * n4 + lane] = v0p;
+                }
+                asm volatile("bar.sync 0;" ::: "memory");
+                if (fr > R) red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, valid && live && reds_on);
+                pairs += (unsigned)npairs;
+            } else {
+                // ================= helper warps: staging and reductions, off the dependency path =================
+                int sq = 1 % ST; // ring slot of the next round to request
+                auto stage_round = [&](int u) { // request the rows of the pairs of round u (called for u = 1, 2, ... in order)
+                    const bool act = valid && u <= R && ((s_mask[u] >> i) & 1u);
+                    const int c = act ? u - i : 0;
+                    const uint32_t dst = stage_s + (uint32_t)(((sq * Lmax + (valid ? i : 0)) * ROWS * n4 + (live ? lane : 0)) * 16);
+                    sq = sq + 1 == ST ? 0 : sq + 1;
+                    cp_async16_if(dst, row_addr(base0, (uint32_t)tok[c], pitch), act && live);
+                    const int32_t *tgp = s_tg + (i * Lmax + c) * K;
+#pragma unroll
+                    for (int k = 0; k < KM; k++) {
+                        const int32_t tg = (act && k < K) ? tgp[k] : -1;
+                        cp_async16_if(dst + (uint32_t)((k + 1) * n4 * 16), row_addr(base1, (uint32_t)max(tg, 0), pitch), tg >= 0 && live);
+                    }
+                    cp_async_commit();
+                };
+                auto send_round = [&](int u) { // the negative-row reductions of round u, from what the critical warp left
+                    const bool act = valid && ((s_mask[u] >> i) & 1u);
+                    if (!__any_sync(FULL, act)) return;
+                    const int c = act ? u - i : 0;
+                    const int32_t *tgp = s_tg + (i * Lmax + c) * K;
+                    const float *gp = xg + ((u & 1) * Lmax + (valid ? i : 0)) * 8;
+                    float4 v = zero4;
+                    if (valid && live) v = xv[((u & 1) * Lmax + i) * n4 + lane];
+#pragma unroll
+                    for (int k = 0; k < KM; k++) {
+                        const int32_t tg = (act && k < K) ? tgp[k] : -1;
+                        const float gv = act ? gp[k] : 0.f;
+                        red_add4_if(row_addr(base1, (uint32_t)max(tg, 0), pitch), scale4(gv, v), tg >= 0 && gv != 0.f && live && reds_on);
+                    }
+                };
+                for (int u = 1; u < ST; u++) stage_round(u);
+                for (int u = 1; u <= R; u++) {
+                    if (ST == 4) cp_async_wait<2>(); else if (ST == 3) cp_async_wait<1>(); else cp_async_wait<0>(); // round u has landed
+                    asm volatile("bar.sync 0;" ::: "memory");
+                    if (u > 1) send_round(u - 1);
+                    const int cf = u - n_tok; // context row cf saw its last centre in round cf + n_tok - 1 at the latest
+                    if (rt < n4 && cf >= 0) {
+                        const float4 dl = delta[cf * n4 + rt];
+                        if (reds_on && (dl.x != 0.f || dl.y != 0.f || dl.z != 0.f || dl.w != 0.f))
+                            red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)tok[cf] * a.stride) + rt, dl);
+                    }
+                    stage_round(u + ST - 1);
+                }
+                cp_async_wait<0>();
+                asm volatile("bar.sync 0;" ::: "memory");
+                send_round(R);
+                // the context rows whose last centre came in the final rounds
+                for (int e = rt; e < n_tok * 8; e += NW * 32) {
+                    const int row = e >> 3, slot = e & 7;
+                    if (slot >= n4 || !reds_on || row + n_tok <= R) continue;
+                    const float4 dl = delta[row * n4 + slot];
+                    if (dl.x != 0.f || dl.y != 0.f || dl.z != 0.f || dl.w != 0.f)
+                        red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)tok[row] * a.stride) + slot, dl);
+                }
+            }
+        }
+    }
+    if (lane == 0 && pairs) atomicAdd(a.pairs, pairs);
+}
+
 // dge_model_stats: one warp per row of each table; acc[0] += |syn0 row|, acc[1] = max |element| (non-negative doubles
 // order like their bit patterns), bad += non-finite elements
 __global__ void k_model_stats(const float *__restrict__ syn0, const float *__restrict__ syn1neg, int32_t V, int32_t dim,
@@ -2062,7 +2524,7 @@ struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq,
 // 16- or 32-lane group one 128-bit slot (2 or 4 for rows wider than 32 slots).
 // Kernel B (items): groups of 8 / 16 / 32 lanes, one slot per lane (2 or 4 beyond 32 slots).
 static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_parallel, bool staged_rows, bool plain_stores, int blk, bool smem_neg,
-                         bool sentence_resident, bool block_sentence, int block_threads, bool pipelined, sgns_variant *out) {
+                         bool sentence_resident, bool block_sentence, int block_threads, bool pipelined, int pair_warps, bool duo, sgns_variant *out) {
     if (n4 > 128) return false;
     sgns_kernel_t seq = nullptr, items = nullptr;
     int Gs = 1, Vs = 1;
@@ -2110,6 +2572,14 @@ static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_p
         if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true, 1> : k_sgns_items_v2<8, false, 1>; }
         else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_items_v2<16, true, 1> : k_sgns_items_v2<16, false, 1>; }
         else { Gi = 32; items = multi ? k_sgns_items_v2<32, true, 1> : k_sgns_items_v2<32, false, 1>; }
+    }
+    else if (n4 <= 8 && sentence_resident && block_sentence && duo && negative <= SGNS_CH) { // kernel J: critical + helper warps
+        code = 12; Gi = 8;
+        items = block_threads <= 192 ? k_sgns_duo<384> : k_sgns_duo<512>;
+    }
+    else if (n4 <= 8 && sentence_resident && block_sentence && pair_warps > 0 && negative <= 7) { // kernel I: a warp per pair, the round's pairs handed out dynamically
+        code = 11; Gi = 32;
+        items = pair_warps <= 8 ? k_sgns_wave<256> : (pair_warps <= 12 ? k_sgns_wave<384> : k_sgns_wave<512>);
     }
     else if (n4 <= 8 && sentence_resident && block_sentence && pipelined && negative <= SGNS_CH && block_threads <= 192) { // kernel H
         code = 10; Gi = 8; items = k_sgns_pipe<192>;
@@ -2466,8 +2936,11 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             const bool blk_fits = ((Lmax + 32 / G_of - 1) / (32 / G_of)) * 32 <= 256;
             const bool force_warp_per_sentence = (dbg & 2048) != 0 && !(dbg & 4);
             const bool blk = blk_fits && n4 <= 8 && !(dbg & 8) && !force_warp_per_sentence;
+            // kernel I (DGE_SGNS_F_PAIR_WARPS): 8 warps per block unless bits 12-15 of the flags name another count (4 .. 16)
+            const int pw_req = (dbg >> 12) & 15;
+            const int pair_warps = ((dbg & 262144) && Lmax <= 32 && p->negative <= 7) ? (pw_req >= 4 ? pw_req : 8) : 0;
             pick_variant(n4, p->negative, narrow, tp, (dbg & 256) != 0, (dbg & 512) != 0, (dbg >> 12) & 15, smem_neg, sent && !forced_other, blk,
-                         ((Lmax + 32 / G_of - 1) / (32 / G_of)) * 32, (dbg & 131072) != 0, &var); // n4 <= 128 was checked
+                         ((Lmax + 32 / G_of - 1) / (32 / G_of)) * 32, (dbg & 131072) != 0, pair_warps, (dbg & 524288) != 0 && Lmax <= 32, &var); // n4 <= 128 was checked
         }
         sgns_kernel_t fn = sequential ? var.seq : var.items;
         const int G = sequential ? var.G_seq : var.G_items;
@@ -2477,7 +2950,9 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             a.lcg_a[k] = la; a.lcg_c[k] = lc;
         }
         const bool pipe_kernel = !sequential && var.items_code == 10;    // kernel H: kernel G with the block's sentences pipelined
-        const bool block_kernel = !sequential && (var.items_code == 9 || pipe_kernel);    // kernel G: a.n_groups counts BLOCKS (sentences in flight)
+        const bool wave_kernel = !sequential && var.items_code == 11;    // kernel I: a warp per pair
+        const bool duo_kernel = !sequential && var.items_code == 12;     // kernel J: critical + helper warps
+        const bool block_kernel = !sequential && (var.items_code == 9 || pipe_kernel || wave_kernel || duo_kernel);    // kernel G: a.n_groups counts BLOCKS (sentences in flight)
         // sentences in flight the hottest word allows (global counts and sentences in a data-parallel run)
         const double hub_p = std::min(1.0, (double)cs[0] / (double)std::max<int64_t>(1, n_global));
         const int64_t hub_sentences = std::max<int64_t>(1, (int64_t)(SGNS_HUB_BOUND / std::max(hub_p, 1e-9)));
@@ -2507,9 +2982,28 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         const bool big_block = !sequential && (var.items_code == 7 || (sent_kernel && !block_kernel && n4 <= 8 && !(dbg & 16))); // one 640-thread block per SM
         int threads = big_block ? 640 : 128;
         if (block_kernel) threads = ((Lmax + 32 / G - 1) / (32 / G)) * 32;   // one lane group per position of the longest sentence
+        if (wave_kernel) { const int pw = (dbg >> 12) & 15; threads = 32 * (pw >= 4 ? pw : 8); }
+        if (duo_kernel) threads *= 2;   // as many helper warps as critical warps
+        // kernel J: stages of the row ring, as many (up to 4) as leave room for two blocks per SM
+        auto duo_smem = [&](int stages) {
+            return 16 * ((size_t)stages * Lmax * (SGNS_CH + 1) * n4 + 3 * (size_t)Lmax * n4) + sizeof(float) * (2 * (size_t)Lmax * 8 + (size_t)p->exp_table_size) +
+                   sizeof(int32_t) * 5 * (size_t)Lmax + (d_negbits ? sizeof(uint32_t) * (size_t)2 * nwords : 0) +
+                   sizeof(int32_t) * (size_t)Lmax * (size_t)Lmax * (size_t)std::max(1, p->negative);
+        };
+        a.stages = 4;
+        if (duo_kernel) {
+            const int req = (dbg >> 12) & 15;   // bits 12-15 of the flags: a fixed stage count (2 .. 4) for A/B runs
+            if (req >= 2 && req <= 4) a.stages = req;
+            else while (a.stages > 2 && 2 * (duo_smem(a.stages) + 1024) > (size_t)227 * 1024) a.stages--;
+        }
         int gpb = threads / G;
         // dynamic shared memory: the sigmoid table, plus (pipelined item kernel) one staged sentence per group
         auto smem_for = [&](int thr) {
+            if (duo_kernel) return duo_smem(a.stages);
+            if (wave_kernel)
+                return sizeof(float) * (3 * (size_t)Lmax * 32 + (size_t)p->exp_table_size) + sizeof(int32_t) * 6 * (size_t)Lmax +
+                       (d_negbits ? sizeof(uint32_t) * (size_t)2 * nwords : 0) + sizeof(int32_t) * (size_t)Lmax * (size_t)Lmax * (size_t)std::max(1, p->negative) +
+                       2 * (size_t)Lmax * (size_t)Lmax;
             if (pipe_kernel)
                 return 3 * ((size_t)Lmax * (size_t)n4 * 16 + sizeof(int32_t) * (size_t)Lmax + sizeof(int32_t) * (size_t)Lmax * (size_t)Lmax * (size_t)std::max(1, p->negative)) +
                        sizeof(float) * (size_t)p->exp_table_size + 24 * sizeof(int32_t) + (d_negbits ? sizeof(uint32_t) * (size_t)2 * nwords : 0);
@@ -2548,9 +3042,10 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             if (dbg & 8) { a.n_groups = 1; blocks = 1; threads = 32; }
         }
         if (block_kernel) { // sentences in flight = blocks: `concurrency`, or what fills the GPU, or the staleness bound (pairs in flight / Lmax)
-            const int64_t full_blocks = (int64_t)ctx->sm_count * per_sm;
+            const int64_t full_blocks = (int64_t)ctx->sm_count * ((wave_kernel || duo_kernel) ? std::min(per_sm, 2) : per_sm);
             int64_t wb = p->concurrency > 0 ? p->concurrency : std::min<int64_t>(full_blocks, hub_sentences);
             wb = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(wb, full_blocks), std::max<int64_t>(1, n_sent)));
+            if ((wave_kernel || duo_kernel) && p->concurrency == 0 && wb > ctx->sm_count) wb -= wb % ctx->sm_count;   // the same number of sentences on every SM
             blocks = (int)wb;
             a.n_groups = blocks;
         }

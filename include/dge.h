@@ -225,6 +225,10 @@ enum { DGE_SGNS_F_NO_UPDATES = 1,     /* timing experiment: compute everything, 
        DGE_SGNS_F_STAGED_ROWS = 256,  /* item kernel with the rows of the next unit staged in shared memory (cp.async) */
        DGE_SGNS_F_PLAIN_STORES = 512, /* atomic-free item kernel: plain 128-bit row stores instead of L2 reductions */
        DGE_SGNS_F_BLOCK_PER_SENTENCE = 4, /* kernel G (a block owns a sentence) even with concurrency = 1 (else the default for narrow rows) */
+       DGE_SGNS_F_PAIR_WARPS = 262144,    /* kernel I: kernel G's wavefront with a warp per pair and the round's pairs handed to the block's warps dynamically;
+                                             bits 12-15 (4 .. 15) = warps per block, default 8 */
+       DGE_SGNS_F_HELPER_WARPS = 524288,  /* kernel J: kernel G's wavefront with helper warps that stage the rows (cp.async ring in shared memory)
+                                             and send the reductions; bits 12-15 (2 .. 4) = stages of the ring */
        DGE_SGNS_F_PIPELINED = 131072,     /* kernel H: kernel G with the sentences of a block pipelined through the wavefront */
        DGE_SGNS_F_ITEM_KERNELS = 65536,   /* the round-1 item kernels B-E with their automatic choice (centres of a sentence in flight at once) */
        DGE_SGNS_F_SMALL_BLOCKS = 16,  /* sentence-resident kernel: 128-thread blocks instead of one 640-thread block per SM */

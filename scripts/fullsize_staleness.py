@@ -3,7 +3,7 @@ Full bench size (tract x 24: 15M flow + 600K spatial walks, D=20, window=24, K=5
 fixture (tests/golden/fullsize_tract24_oracle*.json/.npz): nDCG@k and the agreement of the 10 nearest neighbours with oracle
 run 0 (the other oracle runs agree with it to ~0.88).
 
-    python scripts/fullsize_staleness.py [conc,conc,...] [flags]
+    python scripts/fullsize_staleness.py [conc,conc,...] [flags[,flags...]] [tag]
 """
 import json
 import os
@@ -19,7 +19,8 @@ from embedding_b200 import abi, evaluation as ev, synth  # noqa: E402
 
 def main():
     concs = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "0,256,128,64,32,16").split(",")]
-    flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    flag_sets = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "0").split(",")]
+    tag = sys.argv[3] if len(sys.argv) > 3 else "f%d" % flag_sets[0]
     G = os.path.join(ROOT, "tests", "golden")
     fx = json.load(open(os.path.join(G, "fullsize_tract24_oracle.json")))
     ref = np.load(os.path.join(G, "fullsize_tract24_oracle_knn.npz"))["knn"]
@@ -39,7 +40,7 @@ def main():
         fx["summary"]["5"]["mean"], fx["summary"]["5"]["min"], fx["summary"]["5"]["max"],
         [round(r["knn_overlap_vs_run0"], 4) for r in fx["runs"] if r["objective"] == "ns"][1:]), flush=True)
     out = []
-    for conc in concs:
+    for flags, conc in [(f_, c_) for f_ in flag_sets for c_ in concs]:
         m = abi.Model.train(ctx, [c1, c2], abi.sgns_params(dim=w["dim"], window=w["window"], negative=5, min_count=2, seed=1, concurrency=conc, flags=flags))
         ms = ctx.phase_ms("sgns")
         syn0, ids = m.vectors()
@@ -53,7 +54,7 @@ def main():
         print(json.dumps(r), flush=True)
         m.free()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "fullsize_staleness_f%d.json" % flags), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "fullsize_staleness_%s.json" % tag), "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -2,6 +2,7 @@
     python scripts/prof_path.py tract 500000 [concurrency]
     python scripts/prof_path.py synth 20000 2000000 [dim]
     python scripts/prof_path.py ca 2000000 [concurrency] [dim]      (77 community areas x 24, D = 8)
+A trailing argument flags=N passes dge_sgns_params.flags (DGE_SGNS_F_*: kernel selection for A/B captures).
 """
 import os
 import sys
@@ -12,6 +13,9 @@ from embedding_b200 import abi, host, synth  # noqa: E402
 
 
 def main():
+    flags = 0
+    if sys.argv[-1].startswith("flags="):
+        flags = int(sys.argv.pop()[6:])
     level = sys.argv[1]
     ctx = abi.Context(0)
     if level == "synth":
@@ -38,7 +42,7 @@ def main():
         window = L
     for rep in range(2):
         corpus = G.walk(n_walks, L, seed=1 + rep)
-        m = abi.Model.train(ctx, [corpus], abi.sgns_params(dim=dim, window=window, seed=1, concurrency=conc))
+        m = abi.Model.train(ctx, [corpus], abi.sgns_params(dim=dim, window=window, seed=1, concurrency=conc, flags=flags))
         print("walk ms", ctx.phase_ms("walk"), "steps", corpus.count_tokens(), "sgns ms", ctx.phase_ms("sgns"),
               "pairs", m.pairs, "groups", ctx.phase_ms("sgns_groups"), "kernel", ctx.phase_ms("sgns_kernel"),
               "Mpairs/s", m.pairs / ctx.phase_ms("sgns") / 1e3, "Msteps/s", corpus.count_tokens() / ctx.phase_ms("walk") / 1e3)

@@ -140,6 +140,18 @@ def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negati
         # word of the same sentence)
         e0, e1 = rel_err(concurrency=1, schedule=dge_lib.SCHEDULE_ITEMS, flags=L.F_SENTENCE_RESIDENT | L.F_BLOCK_PER_SENTENCE | L.F_NO_TARGET_PARALLEL)
         assert e0 < 0.05 and e1 < 0.05, ("kernel G", e0, e1)
+        if dim <= 32 and negative <= 7:
+            # kernel I: the same wavefront, a warp per pair, the round's pairs handed to the warps dynamically (8 and 12 warps)
+            for warps in (0, 12 << 12):
+                e0, e1 = rel_err(concurrency=1, schedule=dge_lib.SCHEDULE_ITEMS,
+                                 flags=L.F_SENTENCE_RESIDENT | L.F_BLOCK_PER_SENTENCE | L.F_NO_TARGET_PARALLEL | L.F_PAIR_WARPS | warps)
+                assert e0 < 0.05 and e1 < 0.05, ("kernel I", warps, e0, e1)
+        if dim <= 32 and negative <= 5:
+            # kernel J: the same wavefront, helper warps stage the rows (cp.async ring) and send the reductions (4 and 2 stages)
+            for stages in (0, 2 << 12):
+                e0, e1 = rel_err(concurrency=1, schedule=dge_lib.SCHEDULE_ITEMS,
+                                 flags=L.F_SENTENCE_RESIDENT | L.F_BLOCK_PER_SENTENCE | L.F_NO_TARGET_PARALLEL | L.F_HELPER_WARPS | stages)
+                assert e0 < 0.05 and e1 < 0.05, ("kernel J", stages, e0, e1)
         if dim <= 32 and negative <= 5:
             # kernel H: the same wavefront with the block's sentences pipelined -- one block: two sentences overlap at most
             e0, e1 = rel_err(concurrency=1, schedule=dge_lib.SCHEDULE_ITEMS, flags=L.F_SENTENCE_RESIDENT | L.F_BLOCK_PER_SENTENCE | L.F_NO_TARGET_PARALLEL | L.F_PIPELINED)
