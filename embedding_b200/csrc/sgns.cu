@@ -29,6 +29,17 @@
 // most frequent word) <= SGNS_HUB_BOUND.  Calibrated on the full-size tract x 24 fixture (296 sentences in flight, the top
 // word in 5.8 % of the sentences: 17 concurrent holders, kNN agreement with the oracle 0.886; 370 in flight: 0.72).
 #define SGNS_HUB_BOUND 18.0
+// Kernel F with WRITE-THROUGH words (the most frequent words' rows are re-read for every pair and their updates sent at
+// once, so they are never held pending): the hub bound then applies to the most frequent word that is NOT written
+// through, and what caps the sentences in flight is the vocabulary itself -- beyond ~V / 10 sentences the write-through
+// rows start to oscillate (row norms collapse, profiles/r2s20_fullsize_staleness_*.json: tract x 24, V = 19 224: 1 776 in
+// flight agree with the oracle to 0.89-0.91, 1 924 to 0.75-0.82).  One block per SM, the same number of sentences on every
+// SM (uneven loads cost agreement as well: 1 480 on 2.5 blocks per SM 0.82-0.84, on 74 whole SMs 0.87-0.89).
+#define SGNS_WT_WORDS_PER_SENTENCE 10
+#define SGNS_WT_MAX_WORDS 1024
+// measured per-sentence rates of the two kernels on narrow rows (pairs / s per sentence in flight): kernel G 9.6e6 per
+// block, kernel F 2.06e6 per warp -- kernel F pays once it may hold ~4.7 x the sentences
+#define SGNS_F_OVER_G_SENTENCES 4.7
 #define LCG_MUL 25214903917ULL
 #define LCG_ADD 11ULL
 
@@ -54,6 +65,7 @@ struct sgns_args {
     uint64_t lcg_a[SGNS_MAX_NEG], lcg_c[SGNS_MAX_NEG]; // (k+1)-step jump of the negative-sampling LCG
     int32_t dbg;
     int32_t stages;            // kernel J: stages of the row ring in shared memory (2 .. 4)
+    int32_t hot;               // kernel F: words with index < hot (the most frequent) are write-through
 };
 
 __host__ __device__ static inline uint64_t mix64(uint64_t z) {
@@ -808,6 +820,9 @@ k_sgns_sent(const sgns_args a) {
                 if (c_max < c_min) continue;
                 float4 cur = zero4, d1 = zero4, neu = zero4, v0p = zero4;
                 ldcg4_into(cur, row_addr(base1, (uint32_t)w1, pitch), valid && live); // private copy of syn1neg[w1]
+                // write-through words (index < a.hot: the most frequent ones): their rows are re-read for every pair and
+                // their updates sent at once instead of staying pending for the batch (see the schedule in dge_sgns_train)
+                const bool hot_w1 = w1 < a.hot;
                 // unit u of the batch: group g works on context position c_min + u - g (staggered: no two groups on one row)
                 int uT = 0, jT = 0;
                 uint64_t hc = 0;
@@ -849,6 +864,8 @@ k_sgns_sent(const sgns_args a) {
                     if (!MULTI || t.j == 0) ldcg4_into(r.v0, row_addr(base0, (uint32_t)t.last, pitch), t.act && live);
 #pragma unroll
                     for (int k = 0; k < SGNS_CH; k++) ldcg4_into(r.row[k], row_addr(base1, (uint32_t)r.tg[k], pitch), r.tg[k] >= 0 && live);
+                    // a write-through centre: its output row as L2 has it now (this lane's own earlier reductions included)
+                    if (!MULTI || t.j == 0) ldcg4_into(cur, row_addr(base1, (uint32_t)w1, pitch), t.act && live && hot_w1);
                 };
                 auto compute = [&](const stage_r &r) {
                     if (!__any_sync(FULL, r.act)) return;
@@ -888,13 +905,17 @@ k_sgns_sent(const sgns_args a) {
                     }
                     if (first) {
                         axpy4(neu, gk[SGNS_CH], cur);
-                        axpy4(d1, gk[SGNS_CH], v0);
-                        axpy4(cur, gk[SGNS_CH], v0);
+                        if (hot_w1) red_add4_if(row_addr(base1, (uint32_t)w1, pitch), scale4(gk[SGNS_CH], v0), gk[SGNS_CH] != 0.f && live && reds_on);
+                        else { axpy4(d1, gk[SGNS_CH], v0); axpy4(cur, gk[SGNS_CH], v0); }
                     }
-                    if ((!MULTI || r.j == NCH - 1) && r.act && live) { // the pair is complete: syn0[last] += neu, kept in the warp's cache
-                        float4 dl = my_delta[r.c * n4 + lane];
-                        dl.x += neu.x; dl.y += neu.y; dl.z += neu.z; dl.w += neu.w;
-                        my_delta[r.c * n4 + lane] = dl;
+                    if ((!MULTI || r.j == NCH - 1) && r.act && live) { // the pair is complete: syn0[last] += neu
+                        if (r.last < a.hot) { // write-through word: sent at once, the next pair on this row reads it back from L2
+                            if (reds_on) red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)r.last * a.stride) + lane, neu);
+                        } else { // kept in the warp's cache until the batch is flushed
+                            float4 dl = my_delta[r.c * n4 + lane];
+                            dl.x += neu.x; dl.y += neu.y; dl.z += neu.z; dl.w += neu.w;
+                            my_delta[r.c * n4 + lane] = dl;
+                        }
                     }
                 };
 
@@ -910,7 +931,7 @@ k_sgns_sent(const sgns_args a) {
                     compute(rA);
                     __syncwarp(); // the cache rows written in this unit are read by other groups in later units
                 }
-                red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, valid && live && reds_on);
+                red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, valid && live && reds_on && !hot_w1);
                 // flush the warp's pending context-row updates: one 128-bit reduction per slot that moved
                 for (int q = wl; q < n_tok * n4; q += 32) {
                     const float4 dl = my_delta[q];
@@ -2918,6 +2939,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         //                             concurrency * Lmax items, or (auto) min(full GPU, 8 * V / (negative + 1)) so
         //                             that a row sees at most ~8 concurrent stale updates
         const bool sequential = (p->concurrency == 1 && !(dbg & (2048 | 4))) || p->schedule == DGE_SCHEDULE_SENTENCE;
+        int auto_wt_warps = 0, auto_wt_hot = 0;   // kernel F with write-through words chosen automatically: warps per SM, words
         {   // kernel variant; 4-lane groups need (sentences in flight allowed) >= what fills the GPU with them
             const int64_t allowed = p->concurrency > 0 ? (int64_t)p->concurrency * Lmax : (int64_t)SGNS_STALE_BOUND * V / (p->negative + 1);
             const bool narrow = (dbg & 32) || ((dbg & 65536) && !(dbg & 2) && allowed >= (int64_t)ctx->sm_count * 4 * 32);
@@ -2934,7 +2956,27 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             // kernel G needs one lane group per position of the longest sentence in a block of at most 256 threads
             const int G_of = n4 <= 8 ? 8 : (n4 <= 16 ? 16 : 32);
             const bool blk_fits = ((Lmax + 32 / G_of - 1) / (32 / G_of)) * 32 <= 256;
-            const bool force_warp_per_sentence = (dbg & 2048) != 0 && !(dbg & 4);
+            bool force_warp_per_sentence = (dbg & 2048) != 0 && !(dbg & 4);
+            // ---- automatic choice between kernel G (a block per sentence, hub-bounded) and kernel F with write-through words
+            if (!dbg && p->concurrency == 0 && !sequential && blk_fits && n4 <= 8 && V > 0) {
+                const double n_sents = (double)std::max<int64_t>(1, n_global);
+                const int64_t g_sent = std::min<int64_t>(2 * (int64_t)ctx->sm_count, std::max<int64_t>(1, (int64_t)(SGNS_HUB_BOUND / std::max((double)cs[0] / n_sents, 1e-9))));
+                int warps = (int)std::min<int64_t>(20, ((int64_t)V / SGNS_WT_WORDS_PER_SENTENCE) / ctx->sm_count);
+                int hot = 0;
+                while (warps >= 1) { // the fewest write-through words (a power of two) that satisfy the hub bound at this many sentences
+                    const double n_f = (double)warps * ctx->sm_count;
+                    hot = 0;
+                    while (hot < V && hot <= SGNS_WT_MAX_WORDS && n_f * (double)cs[hot] / n_sents > SGNS_HUB_BOUND) hot = hot ? hot * 2 : 1;
+                    if (hot <= SGNS_WT_MAX_WORDS && hot < V) break;
+                    warps--;
+                }
+                if (warps >= 1 && (double)warps * ctx->sm_count >= SGNS_F_OVER_G_SENTENCES * (double)g_sent &&
+                    (int64_t)warps * ctx->sm_count <= std::max<int64_t>(1, n_sent)) {
+                    force_warp_per_sentence = true;
+                    auto_wt_warps = warps;
+                    auto_wt_hot = hot;
+                }
+            }
             const bool blk = blk_fits && n4 <= 8 && !(dbg & 8) && !force_warp_per_sentence;
             // kernel I (DGE_SGNS_F_PAIR_WARPS): 8 warps per block unless bits 12-15 of the flags name another count (4 .. 16)
             const int pw_req = (dbg >> 12) & 15;
@@ -2981,6 +3023,9 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         a.neg_bits = d_negbits;
         const bool big_block = !sequential && (var.items_code == 7 || (sent_kernel && !block_kernel && n4 <= 8 && !(dbg & 16))); // one 640-thread block per SM
         int threads = big_block ? 640 : 128;
+        // kernel F: bits 12-15 of the flags name the warps of a block (A/B runs: one block per SM with `concurrency` = SMs x warps)
+        if (sent_kernel && !block_kernel && ((dbg >> 12) & 15)) threads = 32 * ((dbg >> 12) & 15);
+        if (sent_kernel && !block_kernel && auto_wt_warps) threads = 32 * auto_wt_warps;   // one block per SM
         if (block_kernel) threads = ((Lmax + 32 / G - 1) / (32 / G)) * 32;   // one lane group per position of the longest sentence
         if (wave_kernel) { const int pw = (dbg >> 12) & 15; threads = 32 * (pw >= 4 ? pw : 8); }
         if (duo_kernel) threads *= 2;   // as many helper warps as critical warps
@@ -2991,6 +3036,11 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
                    sizeof(int32_t) * (size_t)Lmax * (size_t)Lmax * (size_t)std::max(1, p->negative);
         };
         a.stages = 4;
+        // kernel F: write-through words (bits 20-23 of the flags: v -> the 2^(v-1) most frequent words; 0 = none)
+        a.hot = 0;
+        if (!sequential && var.items_code == 8 && ((dbg >> 20) & 15)) a.hot = 1 << (((dbg >> 20) & 15) - 1);
+        if (!sequential && var.items_code == 8 && auto_wt_warps) a.hot = auto_wt_hot;
+        ctx->phase_ms["sgns_write_through"] = (float)a.hot;
         if (duo_kernel) {
             const int req = (dbg >> 12) & 15;   // bits 12-15 of the flags: a fixed stage count (2 .. 4) for A/B runs
             if (req >= 2 && req <= 4) a.stages = req;
@@ -3026,10 +3076,11 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         const int64_t full_groups = (int64_t)ctx->sm_count * per_sm * gpb;
         const int64_t units = sequential ? std::max<int64_t>(1, n_sent) : std::max<int64_t>(1, n_sent * (int64_t)Lmax);
         int64_t want;
-        if (p->concurrency > 0) want = sequential ? (int64_t)p->concurrency : (int64_t)p->concurrency * (sent_kernel ? GPW : Lmax);
+        if (sent_kernel && !block_kernel && auto_wt_warps) want = (int64_t)auto_wt_warps * ctx->sm_count * GPW;
+        else if (p->concurrency > 0) want = sequential ? (int64_t)p->concurrency : (int64_t)p->concurrency * (sent_kernel ? GPW : Lmax);
         else if (sequential) want = full_groups;
         else want = std::min<int64_t>(full_groups, std::max<int64_t>(gpb, (int64_t)SGNS_STALE_BOUND * V / (p->negative + 1)));
-        if (sent_kernel && p->concurrency == 0) want = std::min<int64_t>(want, hub_sentences * GPW);   // kernel F: a warp (GPW groups) per sentence
+        if (sent_kernel && p->concurrency == 0 && !auto_wt_warps) want = std::min<int64_t>(want, hub_sentences * GPW);   // kernel F: a warp (GPW groups) per sentence
         if (!sequential && (dbg & 8)) want = 1; // one warp, one item at a time, strictly in corpus order (arithmetic check against the oracle)
         want = std::max<int64_t>(1, std::min(want, sent_kernel ? std::max<int64_t>(1, n_sent) * GPW : units));
         while (!big_block && !block_kernel && threads > 32 && threads > G && want < (int64_t)ctx->sm_count * gpb) { threads >>= 1; gpb = threads / G; }

@@ -47,7 +47,7 @@ def main():
         layers = ev.layers_from_model(syn0, ids, vl, vr)
         nd = ev.pairwise_ndcg(gt, layers, ks=(5, 20, 50))
         ov = ev.knn_table_overlap(ref, ev.knn_table(layers, w["region_ids"], L, 10))
-        r = dict(concurrency=conc, flags=flags, groups=ctx.phase_ms("sgns_groups"), kernel=int(ctx.phase_ms("sgns_kernel")), sgns_ms=round(ms, 1),
+        r = dict(concurrency=conc, flags=flags, groups=ctx.phase_ms("sgns_groups"), kernel=int(ctx.phase_ms("sgns_kernel")), write_through_words=int(ctx.phase_ms("sgns_write_through")), sgns_ms=round(ms, 1),
                  gpairs_per_s=round(m.pairs / ms / 1e6, 3), ndcg={str(k): round(v, 5) for k, v in nd.items()}, knn_agreement_with_oracle_run0=round(ov, 4),
                  mean_row_norm=round(float(np.linalg.norm(syn0, axis=1).mean()), 3))
         out.append(r)
