@@ -42,7 +42,8 @@ if ROOT not in sys.path:
 WALK_BYTES_PER_STEP = 28.0      # row_ptr pair 8 + prob 8 + alias 4 + col 4 + token 4
 METRIC = "walk_steps_per_sec_through_walks_and_skipgram"
 SG_KERNELS = {0: "k_sgns_seq", 1: "k_sgns_items", 2: "k_sgns_items_v2", 3: "k_sgns_items_g4", 4: "k_sgns_items_tp",
-              5: "k_sgns_items_v3", 6: "k_sgns_items_v2 (plain stores)", 7: "k_sgns_items_v2 (negative table in shared memory)", 8: "k_sgns_sent", 9: "k_sgns_block", 10: "k_sgns_pipe"}
+              5: "k_sgns_items_v3", 6: "k_sgns_items_v2 (plain stores)", 7: "k_sgns_items_v2 (negative table in shared memory)", 8: "k_sgns_sent", 9: "k_sgns_block", 10: "k_sgns_pipe",
+              11: "k_sgns_wave", 12: "k_sgns_duo"}
 
 
 def sgns_bytes_per_pair(dim, negative):
@@ -334,6 +335,7 @@ def run_main_workload(args, w, rank, world, D, abi, ctx, local):
     launches = ctx.kernel_launches() - launches0
     sg_kernel = SG_KERNELS.get(int(ctx.phase_ms("sgns_kernel")), "k_sgns_items_v2")
     groups = ctx.phase_ms("sgns_groups")
+    write_through = int(ctx.phase_ms("sgns_write_through"))
     t_walk = D.max(sum(walk_ms) / 1e3)
     t_sgns = D.max(sum(sg_ms) / 1e3)
     t_step = D.max((sum(walk_ms) + sum(sg_ms)) / 1e3)
@@ -433,7 +435,7 @@ def run_main_workload(args, w, rank, world, D, abi, ctx, local):
                       includes="dge_corpus_from_tokens from pinned host + dge_sgns_train + dge_model_vectors to host"))
     return dict(t_walk=t_walk, t_sgns=t_sgns, t_step=t_step, tot_tokens=tot_tokens, tot_pairs=tot_pairs,
                 per_step_tokens=per_step_tokens, pairs_per_launch=float(np.mean(sg_pairs)),
-                wk_ms=float(np.mean(walk_kernel_ms)), sk_ms=float(np.mean(sg_kernel_ms)), sg_kernel=sg_kernel, groups=groups,
+                wk_ms=float(np.mean(walk_kernel_ms)), sk_ms=float(np.mean(sg_kernel_ms)), sg_kernel=sg_kernel, groups=groups, write_through=write_through,
                 clocks=clk, launches=launches, e2e=e2e, stage_e2e=stage_e2e)
 
 
@@ -660,7 +662,9 @@ def run_gpu_arm(args, w, rank, world, dist):
                                      "denominator, the kernel is bound by L1/L2 request throughput of one 32-byte sector per step"),
                   cpu_baseline=cpu["walk"] if cpu else None),
         sgns=dict(value=R["tot_pairs"] / R["t_sgns"], unit="pairs/s", ms_per_step=R["t_sgns"] / args.steps * 1e3, kernel=R["sg_kernel"],
-                  kernel_ms=R["sk_ms"], groups_in_flight=R["groups"], e2e=se.get("sgns"), roofline=sg_roof,
+                  kernel_ms=R["sk_ms"], groups_in_flight=R["groups"], write_through_words=R["write_through"],
+                  schedule=("a warp per sentence, sentences handed out from a counter, the %d most frequent words written through" % R["write_through"]) if R["sg_kernel"] == "k_sgns_sent" else None,
+                  e2e=se.get("sgns"), roofline=sg_roof,
                   cpu_baseline=cpu["sgns"] if cpu else None))
     if synth is not None and world == 1:
         stages["synth100k"] = synth

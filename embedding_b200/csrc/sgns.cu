@@ -29,14 +29,20 @@
 // most frequent word) <= SGNS_HUB_BOUND.  Calibrated on the full-size tract x 24 fixture (296 sentences in flight, the top
 // word in 5.8 % of the sentences: 17 concurrent holders, kNN agreement with the oracle 0.886; 370 in flight: 0.72).
 #define SGNS_HUB_BOUND 18.0
-// Kernel F with WRITE-THROUGH words (the most frequent words' rows are re-read for every pair and their updates sent at
-// once, so they are never held pending): the hub bound then applies to the most frequent word that is NOT written
-// through, and what caps the sentences in flight is the vocabulary itself -- beyond ~V / 10 sentences the write-through
-// rows start to oscillate (row norms collapse, profiles/r2s20_fullsize_staleness_*.json: tract x 24, V = 19 224: 1 776 in
-// flight agree with the oracle to 0.89-0.91, 1 924 to 0.75-0.82).  One block per SM, the same number of sentences on every
-// SM (uneven loads cost agreement as well: 1 480 on 2.5 blocks per SM 0.82-0.84, on 74 whole SMs 0.87-0.89).
-#define SGNS_WT_WORDS_PER_SENTENCE 10
-#define SGNS_WT_MAX_WORDS 1024
+// Kernel F with WRITE-THROUGH words and a sentence COUNTER -- the default schedule for rows of up to 8 slots.
+//  * Write-through: the rows of the most frequent words are re-read for every pair and their updates sent at once, so they
+//    are never held pending; the hub bound then applies to the most frequent word that is NOT written through.
+//  * Counter: sentences are handed out in corpus order from a device counter, so the warps sweep the corpus front together
+//    whatever their speeds.  With the strided assignment a warp that runs slower (an SM sub-partition with one warp more,
+//    an SM with one block more) falls behind in the corpus and in the learning-rate schedule, and the corpus' last part
+//    (the spatial walks) is no longer trained last: agreement with the oracle 0.82 instead of 0.88 at 10 or 13 warps per SM,
+//    row-norm collapse beyond ~V / 10 sentences in flight (profiles/r2s19, r2s20, r2s22).
+// With both, the full-size tract x 24 fixture is reproduced with a FULL GPU of sentences in flight (20 warps per SM, 2 960
+// sentences, 512-1 024 words written through: kNN agreement 0.887-0.892 against 0.873-0.882 between oracle runs, nDCG@5
+// within 0.0004 of the oracle mean, 4.5 G pairs/s -- profiles/r2s24, r2s25), and the CA fixture (V = 1 848: every word
+// written through) at 1 480-2 960 in flight (agreement 0.76-0.84 against 0.70-0.88 between oracle runs, 3.0 G pairs/s).
+// Sentences in flight are kept <= V (one per vocabulary word; CA agrees better at 1 480 than at 2 960 for the same rate).
+#define SGNS_WT_MAX_WORDS 2048
 // measured per-sentence rates of the two kernels on narrow rows (pairs / s per sentence in flight): kernel G 9.6e6 per
 // block, kernel F 2.06e6 per warp -- kernel F pays once it may hold ~4.7 x the sentences
 #define SGNS_F_OVER_G_SENTENCES 4.7
@@ -66,6 +72,7 @@ struct sgns_args {
     int32_t dbg;
     int32_t stages;            // kernel J: stages of the row ring in shared memory (2 .. 4)
     int32_t hot;               // kernel F: words with index < hot (the most frequent) are write-through
+    unsigned long long *next;  // kernel F: the next (epoch, sentence) of this launch to hand out, or NULL for the strided assignment
 };
 
 __host__ __device__ static inline uint64_t mix64(uint64_t z) {
@@ -746,9 +753,14 @@ __device__ __forceinline__ int32_t neg_lookup(const uint32_t *__restrict__ s_bit
     return (int32_t)(s_pref[w] + __popc(s_bits[w] & ((2u << j) - 2u)));
 }
 
-template <int G, bool MULTI>
-__global__ void __launch_bounds__(640, 1)
+// PF = true (narrow rows, K <= 5, at most 12 warps per block): the rows of unit u + 1 are requested before unit u is computed
+// (two row buffers in registers).  A write-through row that this warp updated in unit u is then missing that update in the
+// copy requested before it: a context row's last update stays in the warp's cache, tagged with its unit, and is added by
+// the reader of the next unit only; a centre adds its own last update from a register.
+template <int G, bool MULTI, bool PF>
+__global__ void __launch_bounds__(PF ? 384 : 640, 1)
 k_sgns_sent(const sgns_args a) {
+    static_assert(!(PF && MULTI), "the prefetching build handles one chunk of negatives per pair");
     static_assert(G == 8 || G == 16 || G == 32, "lane groups of 8, 16 or 32");
     extern __shared__ __align__(16) int32_t smem_f[];
     constexpr unsigned FULL = 0xffffffffu;
@@ -760,7 +772,8 @@ k_sgns_sent(const sgns_args a) {
     float4 *my_delta = reinterpret_cast<float4 *>(smem_f) + (size_t)wib * Lmax * n4;
     float *s_exp = reinterpret_cast<float *>(reinterpret_cast<float4 *>(smem_f) + (size_t)warps_per_block * Lmax * n4);
     int32_t *mytok = reinterpret_cast<int32_t *>(s_exp + a.exp_table_size) + wib * Lmax;
-    uint32_t *s_bits = reinterpret_cast<uint32_t *>(s_exp + a.exp_table_size) + warps_per_block * Lmax;
+    int32_t *my_tag = reinterpret_cast<int32_t *>(s_exp + a.exp_table_size) + (warps_per_block + wib) * Lmax; // PF: unit of a write-through row's cached update
+    uint32_t *s_bits = reinterpret_cast<uint32_t *>(s_exp + a.exp_table_size) + 2 * warps_per_block * Lmax;
     uint32_t *s_pref = s_bits + nwords;
     const bool smem_neg = a.neg_bits != nullptr;
     for (int i = threadIdx.x; i < a.exp_table_size; i += blockDim.x) s_exp[i] = a.exp_table[i];
@@ -792,14 +805,32 @@ k_sgns_sent(const sgns_args a) {
     unsigned long long pairs = 0;
 
     struct stage_t { int32_t last; bool act; uint64_t nsk; int32_t traw; int j; int c; };
-    struct stage_r { int32_t last; bool act; int j; int c; int32_t mine; int32_t tg[SGNS_CH]; float4 row[SGNS_CH]; float4 v0; };
+    struct stage_r { int32_t last; bool act; int j; int c; int32_t mine; int32_t tg[SGNS_CH]; float4 row[SGNS_CH]; float4 v0; float4 cur; };
 
-    for (int ep = a.ep_lo; ep < a.ep_hi; ep++) {
-        for (int64_t s = a.s_lo + warp_id; s < a.s_hi; s += a.n_groups) { // n_groups = warps = sentences in flight
+    // Sentences are handed out in corpus order, either strided (warp w takes w, w + n_groups, ...) or -- a.next != NULL -- from
+    // a counter: then the warps sweep the corpus front together whatever their speeds (a strided warp that runs slower, e.g.
+    // on an SM sub-partition with one warp more, falls behind in the corpus and in the learning-rate schedule, and the
+    // corpus' last part -- the spatial walks -- is no longer trained last: the full-size agreement with the oracle drops
+    // from 0.88 to 0.82 with 10 or 13 warps per SM, profiles/r2s19 / r2s22).
+    const int64_t ns_launch = a.s_hi - a.s_lo;
+    const unsigned long long total_launch = (unsigned long long)(a.ep_hi - a.ep_lo) * (unsigned long long)ns_launch;
+    unsigned long long it = (unsigned long long)warp_id;
+    if (warp_id >= a.n_groups) it = total_launch; // (a block's spare warps)
+    for (;; it += (unsigned long long)a.n_groups) {
+        {
+            if (a.next) {
+                unsigned long long nx = 0;
+                if (wl == 0) nx = atomicAdd(a.next, 1ULL);
+                it = shfl64(nx, 0, 32);
+            }
+            if (it >= total_launch) break;
+            const int ep = a.ep_lo + (int)(it / (unsigned long long)ns_launch);
+            const int64_t s = a.s_lo + (int64_t)(it % (unsigned long long)ns_launch);
             __syncwarp();
             int n_tok = 0;
             for (int j = wl; j < Lmax; j += 32) { const int32_t tk = a.wtok[(int64_t)j * N + s]; mytok[j] = tk; n_tok += tk >= 0; }
             for (int q = wl; q < Lmax * n4; q += 32) my_delta[q] = zero4;
+            if (PF) for (int j = wl; j < Lmax; j += 32) my_tag[j] = -2;
             __syncwarp();
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) n_tok += __shfl_xor_sync(FULL, n_tok, o);
@@ -823,6 +854,7 @@ k_sgns_sent(const sgns_args a) {
                 // write-through words (index < a.hot: the most frequent ones): their rows are re-read for every pair and
                 // their updates sent at once instead of staying pending for the batch (see the schedule in dge_sgns_train)
                 const bool hot_w1 = w1 < a.hot;
+                float4 upd_last = zero4; // PF: what this centre sent to its write-through output row in the previous unit
                 // unit u of the batch: group g works on context position c_min + u - g (staggered: no two groups on one row)
                 int uT = 0, jT = 0;
                 uint64_t hc = 0;
@@ -865,9 +897,11 @@ k_sgns_sent(const sgns_args a) {
 #pragma unroll
                     for (int k = 0; k < SGNS_CH; k++) ldcg4_into(r.row[k], row_addr(base1, (uint32_t)r.tg[k], pitch), r.tg[k] >= 0 && live);
                     // a write-through centre: its output row as L2 has it now (this lane's own earlier reductions included)
-                    if (!MULTI || t.j == 0) ldcg4_into(cur, row_addr(base1, (uint32_t)w1, pitch), t.act && live && hot_w1);
+                    if (!MULTI || t.j == 0) ldcg4_into(PF ? r.cur : cur, row_addr(base1, (uint32_t)w1, pitch), t.act && live && hot_w1);
                 };
-                auto compute = [&](const stage_r &r) {
+                auto compute = [&](const stage_r &r, int u) {
+                    const float4 upd_prev = upd_last;
+                    upd_last = zero4;
                     if (!__any_sync(FULL, r.act)) return;
                     const bool first = !MULTI || r.j == 0;
                     if (first) {
@@ -875,7 +909,14 @@ k_sgns_sent(const sgns_args a) {
                         neu = zero4;
                         // the row as this sentence sees it: L2's value + what this warp has added since its last flush
                         v0p = r.v0;
-                        if (r.act && live) { const float4 dl = my_delta[r.c * n4 + lane]; v0p.x += dl.x; v0p.y += dl.y; v0p.z += dl.z; v0p.w += dl.w; }
+                        if (r.act && live) {
+                            // PF, write-through row: the cached update counts only if it was made in the unit just before (it
+                            // is in every copy requested later)
+                            if (!PF || r.last >= a.hot || my_tag[r.c] == u - 1) {
+                                const float4 dl = my_delta[r.c * n4 + lane]; v0p.x += dl.x; v0p.y += dl.y; v0p.z += dl.z; v0p.w += dl.w;
+                            }
+                        }
+                        if (PF && hot_w1 && r.act) cur = add4(r.cur, upd_prev); // requested before the previous unit's update left
                     }
                     const float4 v0 = v0p;
                     float d0 = dot4(v0, r.row[0]), d1v = dot4(v0, r.row[1]), d2 = dot4(v0, r.row[2]), d3 = dot4(v0, r.row[3]);
@@ -905,12 +946,17 @@ k_sgns_sent(const sgns_args a) {
                     }
                     if (first) {
                         axpy4(neu, gk[SGNS_CH], cur);
-                        if (hot_w1) red_add4_if(row_addr(base1, (uint32_t)w1, pitch), scale4(gk[SGNS_CH], v0), gk[SGNS_CH] != 0.f && live && reds_on);
+                        if (hot_w1) {
+                            const float4 upd = scale4(gk[SGNS_CH], v0);
+                            red_add4_if(row_addr(base1, (uint32_t)w1, pitch), upd, gk[SGNS_CH] != 0.f && live && reds_on);
+                            if (PF && reds_on) upd_last = upd;
+                        }
                         else { axpy4(d1, gk[SGNS_CH], v0); axpy4(cur, gk[SGNS_CH], v0); }
                     }
                     if ((!MULTI || r.j == NCH - 1) && r.act && live) { // the pair is complete: syn0[last] += neu
                         if (r.last < a.hot) { // write-through word: sent at once, the next pair on this row reads it back from L2
                             if (reds_on) red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)r.last * a.stride) + lane, neu);
+                            if (PF && reds_on) { my_delta[r.c * n4 + lane] = neu; if (lane == 0) my_tag[r.c] = u; }
                         } else { // kept in the warp's cache until the batch is flushed
                             float4 dl = my_delta[r.c * n4 + lane];
                             dl.x += neu.x; dl.y += neu.y; dl.z += neu.z; dl.w += neu.w;
@@ -921,14 +967,34 @@ k_sgns_sent(const sgns_args a) {
 
                 const int U = (c_max - c_min + 1 + (gpw_eff - 1)) * NCH;
                 stage_r rA;
-                rA.v0 = zero4;
+                rA.v0 = rA.cur = zero4;
 #pragma unroll
                 for (int k = 0; k < SGNS_CH; k++) rA.row[k] = zero4;
                 stage_t t1 = stageT();
+                if (PF) {
+                    stage_r rB;
+                    rB.v0 = rB.cur = zero4;
+#pragma unroll
+                    for (int k = 0; k < SGNS_CH; k++) rB.row[k] = zero4;
+                    stageR(t1, rA);
+                    t1 = stageT();
+                    for (int u = 0; u < U; u += 2) {
+                        stageR(t1, rB); // the rows of unit u + 1 (nothing is requested past the end: act is false there)
+                        t1 = stageT();
+                        compute(rA, u);
+                        __syncwarp(); // the cache rows written in this unit are read by other groups in later units
+                        if (u + 1 < U) {
+                            stageR(t1, rA);
+                            t1 = stageT();
+                            compute(rB, u + 1);
+                            __syncwarp();
+                        }
+                    }
+                } else
                 for (int u = 0; u < U; u++) {
                     stageR(t1, rA);
                     t1 = stageT();
-                    compute(rA);
+                    compute(rA, u);
                     __syncwarp(); // the cache rows written in this unit are read by other groups in later units
                 }
                 red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, valid && live && reds_on && !hot_w1);
@@ -937,10 +1003,12 @@ k_sgns_sent(const sgns_args a) {
                     const float4 dl = my_delta[q];
                     const int row = q / n4, slot = q - row * n4;
                     if (dl.x != 0.f || dl.y != 0.f || dl.z != 0.f || dl.w != 0.f) {
-                        if (reds_on) red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)mytok[row] * a.stride) + slot, dl);
+                        // (PF: a write-through row's entry is the copy of an update that has been sent already)
+                        if (reds_on && !(PF && mytok[row] < a.hot)) red_add4(reinterpret_cast<float4 *>(a.syn0 + (int64_t)mytok[row] * a.stride) + slot, dl);
                         my_delta[q] = zero4;
                     }
                 }
+                if (PF) for (int j = wl; j < Lmax; j += 32) my_tag[j] = -2; // units are counted per batch
                 __threadfence(); // the next batch re-reads these rows from L2
                 __syncwarp();
             }
@@ -2545,7 +2613,7 @@ struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq,
 // 16- or 32-lane group one 128-bit slot (2 or 4 for rows wider than 32 slots).
 // Kernel B (items): groups of 8 / 16 / 32 lanes, one slot per lane (2 or 4 beyond 32 slots).
 static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_parallel, bool staged_rows, bool plain_stores, int blk, bool smem_neg,
-                         bool sentence_resident, bool block_sentence, int block_threads, bool pipelined, int pair_warps, bool duo, sgns_variant *out) {
+                         bool sentence_resident, bool block_sentence, int block_threads, bool pipelined, int pair_warps, bool duo, bool prefetch_f, sgns_variant *out) {
     if (n4 > 128) return false;
     sgns_kernel_t seq = nullptr, items = nullptr;
     int Gs = 1, Vs = 1;
@@ -2614,9 +2682,9 @@ static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_p
     }
     else if (n4 <= 32 && sentence_resident) { // kernel F: a warp owns a sentence (intra-sentence updates in sequence)
         code = 8;
-        if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_sent<8, true> : k_sgns_sent<8, false>; }
-        else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_sent<16, true> : k_sgns_sent<16, false>; }
-        else { Gi = 32; items = multi ? k_sgns_sent<32, true> : k_sgns_sent<32, false>; }
+        if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_sent<8, true, false> : (prefetch_f ? k_sgns_sent<8, false, true> : k_sgns_sent<8, false, false>); }
+        else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_sent<16, true, false> : k_sgns_sent<16, false, false>; }
+        else { Gi = 32; items = multi ? k_sgns_sent<32, true, false> : k_sgns_sent<32, false, false>; }
     }
     else if (n4 <= 8 && smem_neg) { Gi = 8; code = 7; items = multi ? k_sgns_items_v2<8, true, 2> : k_sgns_items_v2<8, false, 2>; }
     else if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true, 0> : k_sgns_items_v2<8, false, 0>; }
@@ -2958,31 +3026,33 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             const bool blk_fits = ((Lmax + 32 / G_of - 1) / (32 / G_of)) * 32 <= 256;
             bool force_warp_per_sentence = (dbg & 2048) != 0 && !(dbg & 4);
             // ---- automatic choice between kernel G (a block per sentence, hub-bounded) and kernel F with write-through words
-            if (!dbg && p->concurrency == 0 && !sequential && blk_fits && n4 <= 8 && V > 0) {
+            if (!dbg && p->concurrency == 0 && !sequential && !multi && blk_fits && n4 <= 8 && V > 0) {
                 const double n_sents = (double)std::max<int64_t>(1, n_global);
                 const int64_t g_sent = std::min<int64_t>(2 * (int64_t)ctx->sm_count, std::max<int64_t>(1, (int64_t)(SGNS_HUB_BOUND / std::max((double)cs[0] / n_sents, 1e-9))));
-                int warps = (int)std::min<int64_t>(20, ((int64_t)V / SGNS_WT_WORDS_PER_SENTENCE) / ctx->sm_count);
+                int warps = (int)std::min<int64_t>(20, (int64_t)V / ctx->sm_count);
                 int hot = 0;
                 while (warps >= 1) { // the fewest write-through words (a power of two) that satisfy the hub bound at this many sentences
                     const double n_f = (double)warps * ctx->sm_count;
                     hot = 0;
-                    while (hot < V && hot <= SGNS_WT_MAX_WORDS && n_f * (double)cs[hot] / n_sents > SGNS_HUB_BOUND) hot = hot ? hot * 2 : 1;
-                    if (hot <= SGNS_WT_MAX_WORDS && hot < V) break;
+                    while (hot < V && n_f * (double)cs[hot] / n_sents > SGNS_HUB_BOUND) hot = hot ? hot * 2 : 1;
+                    if (hot >= V || hot <= SGNS_WT_MAX_WORDS) break; // every word, or few enough
                     warps--;
                 }
                 if (warps >= 1 && (double)warps * ctx->sm_count >= SGNS_F_OVER_G_SENTENCES * (double)g_sent &&
                     (int64_t)warps * ctx->sm_count <= std::max<int64_t>(1, n_sent)) {
                     force_warp_per_sentence = true;
                     auto_wt_warps = warps;
-                    auto_wt_hot = hot;
+                    auto_wt_hot = std::min(hot, V);
                 }
             }
             const bool blk = blk_fits && n4 <= 8 && !(dbg & 8) && !force_warp_per_sentence;
             // kernel I (DGE_SGNS_F_PAIR_WARPS): 8 warps per block unless bits 12-15 of the flags name another count (4 .. 16)
+            // kernel F with the rows of the next unit requested ahead (DGE_SGNS_F_ROW_PREFETCH; blocks of at most 12 warps)
+            const bool prefetch_f = (dbg & (1 << 24)) != 0 && p->negative <= SGNS_CH && n4 <= 8;
             const int pw_req = (dbg >> 12) & 15;
             const int pair_warps = ((dbg & 262144) && Lmax <= 32 && p->negative <= 7) ? (pw_req >= 4 ? pw_req : 8) : 0;
             pick_variant(n4, p->negative, narrow, tp, (dbg & 256) != 0, (dbg & 512) != 0, (dbg >> 12) & 15, smem_neg, sent && !forced_other, blk,
-                         ((Lmax + 32 / G_of - 1) / (32 / G_of)) * 32, (dbg & 131072) != 0, pair_warps, (dbg & 524288) != 0 && Lmax <= 32, &var); // n4 <= 128 was checked
+                         ((Lmax + 32 / G_of - 1) / (32 / G_of)) * 32, (dbg & 131072) != 0, pair_warps, (dbg & 524288) != 0 && Lmax <= 32, prefetch_f, &var); // n4 <= 128 was checked
         }
         sgns_kernel_t fn = sequential ? var.seq : var.items;
         const int G = sequential ? var.G_seq : var.G_items;
@@ -3026,6 +3096,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         // kernel F: bits 12-15 of the flags name the warps of a block (A/B runs: one block per SM with `concurrency` = SMs x warps)
         if (sent_kernel && !block_kernel && ((dbg >> 12) & 15)) threads = 32 * ((dbg >> 12) & 15);
         if (sent_kernel && !block_kernel && auto_wt_warps) threads = 32 * auto_wt_warps;   // one block per SM
+        if (sent_kernel && !block_kernel && (dbg & (1 << 24)) && p->negative <= SGNS_CH && n4 <= 8 && threads > 384) threads = 384;
         if (block_kernel) threads = ((Lmax + 32 / G - 1) / (32 / G)) * 32;   // one lane group per position of the longest sentence
         if (wave_kernel) { const int pw = (dbg >> 12) & 15; threads = 32 * (pw >= 4 ? pw : 8); }
         if (duo_kernel) threads *= 2;   // as many helper warps as critical warps
@@ -3041,6 +3112,12 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         if (!sequential && var.items_code == 8 && ((dbg >> 20) & 15)) a.hot = 1 << (((dbg >> 20) & 15) - 1);
         if (!sequential && var.items_code == 8 && auto_wt_warps) a.hot = auto_wt_hot;
         ctx->phase_ms["sgns_write_through"] = (float)a.hot;
+        // kernel F: sentences handed out from a counter (DGE_SGNS_F_DYNAMIC, and whenever the write-through schedule is automatic)
+        unsigned long long *d_next = nullptr;
+        if (!sequential && var.items_code == 8 && !(dbg & 8) && ((dbg & (1 << 25)) || auto_wt_warps)) {
+            if (tmp.get(&d_next, 1) != cudaSuccess) { d_next = nullptr; cudaGetLastError(); }
+        }
+        a.next = d_next;
         if (duo_kernel) {
             const int req = (dbg >> 12) & 15;   // bits 12-15 of the flags: a fixed stage count (2 .. 4) for A/B runs
             if (req >= 2 && req <= 4) a.stages = req;
@@ -3062,7 +3139,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
                        (d_negbits ? sizeof(uint32_t) * (size_t)2 * nwords : 0) + sizeof(int32_t) * (size_t)Lmax * (size_t)Lmax * (size_t)std::max(1, p->negative);
             if (sent_kernel)
                 return (size_t)(thr / 32) * (size_t)Lmax * (size_t)n4 * 16 + sizeof(float) * (size_t)p->exp_table_size +
-                       sizeof(int32_t) * (size_t)(thr / 32) * (size_t)Lmax + (d_negbits ? sizeof(uint32_t) * (size_t)2 * nwords : 0);
+                       sizeof(int32_t) * 2 * (size_t)(thr / 32) * (size_t)Lmax + (d_negbits ? sizeof(uint32_t) * (size_t)2 * nwords : 0);
             return sizeof(float) * (size_t)p->exp_table_size + (sequential ? 0 : sizeof(int32_t) * (size_t)(thr / G) * (size_t)Lmax) +
                    (!sequential && var.items_code == 5 ? (size_t)thr * 2 * (SGNS_CH + 1) * 16 : 0) + // kernel C': two row stages per lane
                    (var.items_code == 7 ? (((size_t)p->neg_table_size * 2 + 15) / 16) * 16 : 0);
@@ -3126,6 +3203,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         smem = smem_for(threads);
         if (rounds == 1 && !multi) {
             a.ep_lo = 0; a.ep_hi = p->epochs; a.s_lo = 0; a.s_hi = n_sent;
+            if (d_next) cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), st);
             fn<<<blocks, threads, smem, st>>>(a);
             ctx->launches++;
         } else {
@@ -3135,6 +3213,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
                     a.s_lo = n_sent * r / rounds; a.s_hi = n_sent * (r + 1) / rounds;
                     int launch_err = 0;
                     if (a.s_hi > a.s_lo) {
+                        if (d_next) cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), st);
                         fn<<<blocks, threads, smem, st>>>(a);
                         ctx->launches++;
                         launch_err = cudaGetLastError() != cudaSuccess;

@@ -129,6 +129,13 @@ def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negati
         flag_sets.append(L.F_ONE_WARP | L.F_SENTENCE_RESIDENT | L.F_SMALL_BLOCKS)
         flag_sets.append(L.F_ONE_WARP | L.F_STAGED_ROWS)             # kernel C': rows staged in shared memory by cp.async
         flag_sets.append(L.F_ONE_WARP | L.F_PLAIN_STORES)            # atomic-free build: one item at a time loses no update
+    if dim <= 32 and negative <= 5:
+        # kernel F with write-through words (bits 20-23: the 2^(v-1) most frequent words are re-read for every pair and
+        # updated at once), without and with the row prefetch (cached last update + unit tag): still the oracle's order
+        flag_sets.append(L.F_ONE_WARP | L.F_SENTENCE_RESIDENT | (8 << 20))
+        flag_sets.append(L.F_ONE_WARP | L.F_SENTENCE_RESIDENT | L.F_ROW_PREFETCH)
+        flag_sets.append(L.F_ONE_WARP | L.F_SENTENCE_RESIDENT | L.F_ROW_PREFETCH | (8 << 20))
+        flag_sets.append(L.F_ONE_WARP | L.F_SENTENCE_RESIDENT | L.F_ROW_PREFETCH | (12 << 20))
     for flags in flag_sets:
         e0, e1 = rel_err(flags=flags)
         # plain stores lose an update whenever one row is drawn twice within a unit (both copies start from the same load)
@@ -156,6 +163,13 @@ def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negati
             # kernel H: the same wavefront with the block's sentences pipelined -- one block: two sentences overlap at most
             e0, e1 = rel_err(concurrency=1, schedule=dge_lib.SCHEDULE_ITEMS, flags=L.F_SENTENCE_RESIDENT | L.F_BLOCK_PER_SENTENCE | L.F_NO_TARGET_PARALLEL | L.F_PIPELINED)
             assert e0 < 0.1 and e1 < 0.1, ("kernel H", e0, e1)
+    if dim <= 32 and negative <= 5:
+        # one warp, its four lane groups staggered over the contexts (a legitimate sequential order of the sentence's pairs),
+        # write-through words and row prefetch: the cached-update bookkeeping between the groups must be exact
+        b0, b1 = rel_err(concurrency=1, schedule=dge_lib.SCHEDULE_ITEMS, flags=L.F_SENTENCE_RESIDENT)
+        for extra in (8 << 20, L.F_ROW_PREFETCH | (8 << 20), L.F_ROW_PREFETCH | (12 << 20), L.F_DYNAMIC | (8 << 20)):
+            e0, e1 = rel_err(concurrency=1, schedule=dge_lib.SCHEDULE_ITEMS, flags=L.F_SENTENCE_RESIDENT | extra)
+            assert e0 < 1.25 * b0 + 0.02 and e1 < 1.25 * b1 + 0.02, ("kernel F, one sentence in flight", extra, e0, e1, b0, b1)
     e0, e1 = rel_err(concurrency=2)                 # two sentences in flight
     assert e0 < 0.35 and e1 < 0.35, (e0, e1)
     e0, e1 = rel_err()                              # automatic full-GPU schedule
