@@ -3157,7 +3157,12 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         else if (p->concurrency > 0) want = sequential ? (int64_t)p->concurrency : (int64_t)p->concurrency * (sent_kernel ? GPW : Lmax);
         else if (sequential) want = full_groups;
         else want = std::min<int64_t>(full_groups, std::max<int64_t>(gpb, (int64_t)SGNS_STALE_BOUND * V / (p->negative + 1)));
-        if (sent_kernel && p->concurrency == 0 && !auto_wt_warps) want = std::min<int64_t>(want, hub_sentences * GPW);   // kernel F: a warp (GPW groups) per sentence
+        // kernel F on wider rows (a warp owns a sentence, one pair at a time): the same schedule -- sentence counter, write-through
+        // words chosen for the sentences in flight (at most one per vocabulary word) -- instead of the hub bound on the
+        // sentences in flight; also on the ranks of a data-parallel run (global counts, this rank's sentences in flight)
+        const bool auto_wide = !dbg && p->concurrency == 0 && sent_kernel && !block_kernel && var.items_code == 8 && n4 > 8 && !auto_wt_warps;
+        if (auto_wide) want = std::min<int64_t>(want, std::max<int64_t>(1, (int64_t)V) * GPW);
+        if (sent_kernel && p->concurrency == 0 && !auto_wt_warps && !auto_wide) want = std::min<int64_t>(want, hub_sentences * GPW);   // kernel F: a warp (GPW groups) per sentence
         if (!sequential && (dbg & 8)) want = 1; // one warp, one item at a time, strictly in corpus order (arithmetic check against the oracle)
         want = std::max<int64_t>(1, std::min(want, sent_kernel ? std::max<int64_t>(1, n_sent) * GPW : units));
         while (!big_block && !block_kernel && threads > 32 && threads > G && want < (int64_t)ctx->sm_count * gpb) { threads >>= 1; gpb = threads / G; }
@@ -3178,6 +3183,15 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             a.n_groups = blocks;
         }
         ctx->phase_ms["sgns_groups"] = (float)a.n_groups;
+        if (auto_wide) {
+            const double n_sents = (double)std::max<int64_t>(1, n_global), n_f = (double)a.n_groups;
+            int hot = 0;
+            while (hot < V && hot <= SGNS_WT_MAX_WORDS && n_f * (double)cs[hot] / n_sents > SGNS_HUB_BOUND) hot = hot ? hot * 2 : 1;
+            a.hot = std::min(hot, V);
+            ctx->phase_ms["sgns_write_through"] = (float)a.hot;
+            if (!d_next && tmp.get(&d_next, 1) != cudaSuccess) { d_next = nullptr; cudaGetLastError(); }
+            a.next = d_next;
+        }
         ctx->phase_ms["sgns_kernel"] = (float)(sequential ? 0 : var.items_code);
         // ---- launches.  Single GPU: one launch over all epochs and sentences.  Data-parallel (the ctx has a
         // communicator; or sync_rounds > 0, where the exchange is the identity): each epoch is cut into `rounds` slices
