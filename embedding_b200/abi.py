@@ -19,7 +19,7 @@ TRANSPORT_AUTO, TRANSPORT_PEER, TRANSPORT_NCCL = 0, 1, 2
 # dge_sgns_params.flags (include/dge.h DGE_SGNS_F_*): kernel-selection / measurement hooks for tests and A/B runs
 F_NO_UPDATES, F_NO_NARROW, F_ONE_WARP, F_NARROW, F_TARGET_PARALLEL, F_NO_TARGET_PARALLEL, F_STAGED_ROWS, F_PLAIN_STORES, F_SMEM_NEG_TABLE = \
     1, 2, 8, 32, 64, 128, 256, 512, 1024
-F_BLOCK_PER_SENTENCE, F_SMALL_BLOCKS, F_SENTENCE_RESIDENT, F_ITEM_KERNELS, F_PIPELINED, F_PAIR_WARPS, F_HELPER_WARPS, F_ROW_PREFETCH, F_DYNAMIC = 4, 16, 2048, 65536, 131072, 262144, 524288, 1 << 24, 1 << 25
+F_BLOCK_PER_SENTENCE, F_SMALL_BLOCKS, F_SENTENCE_RESIDENT, F_ITEM_KERNELS, F_PIPELINED, F_PAIR_WARPS, F_HELPER_WARPS, F_ROW_PREFETCH, F_DYNAMIC, F_ROW_PREFETCH_SMEM = 4, 16, 2048, 65536, 131072, 262144, 524288, 1 << 24, 1 << 25, 1 << 26
 COMM_ID_BYTES = 128
 
 class DgeError(RuntimeError):

@@ -501,6 +501,13 @@ __device__ __forceinline__ void ldcg4_into(float4 &r, uint64_t p, bool pred) {
                  : "+f"(r.x), "+f"(r.y), "+f"(r.z), "+f"(r.w)
                  : "l"(p), "r"((int)pred));
 }
+// predicated 16-byte cp.async (LDGSTS, L2 only) and its group bookkeeping
+__device__ __forceinline__ void cp_async16_if(uint32_t smem_addr, uint64_t gptr, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+                 ::"r"(smem_addr), "l"(gptr), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // After this rebuild the kernel runs at ~2/3 of what the memory system itself delivers for its access pattern
 // (random 80-byte-row 128-bit loads + reductions, scripts/red_microbench.cu, profiles/r1s7_red_microbench.txt):
@@ -757,8 +764,10 @@ __device__ __forceinline__ int32_t neg_lookup(const uint32_t *__restrict__ s_bit
 // (two row buffers in registers).  A write-through row that this warp updated in unit u is then missing that update in the
 // copy requested before it: a context row's last update stays in the warp's cache, tagged with its unit, and is added by
 // the reader of the next unit only; a centre adds its own last update from a register.
-template <int G, bool MULTI, bool PF>
-__global__ void __launch_bounds__(PF ? 384 : 640, 1)
+// PF = 2: the same, with the requested rows landing in shared memory (cp.async, two stages of 7 rows per lane) instead of
+// registers, so the block keeps its 20 warps; a lane reads back exactly the slots it copied itself.
+template <int G, bool MULTI, int PF>
+__global__ void __launch_bounds__(PF == 1 ? 384 : 640, 1)
 k_sgns_sent(const sgns_args a) {
     static_assert(!(PF && MULTI), "the prefetching build handles one chunk of negatives per pair");
     static_assert(G == 8 || G == 16 || G == 32, "lane groups of 8, 16 or 32");
@@ -770,13 +779,18 @@ k_sgns_sent(const sgns_args a) {
     const int nwords = (a.neg_table_size + 31) >> 5;
     // shared memory: [delta cache of every warp: Lmax x n4 float4][sigmoid table][tokens of every warp][negative table bits | prefixes]
     float4 *my_delta = reinterpret_cast<float4 *>(smem_f) + (size_t)wib * Lmax * n4;
-    float *s_exp = reinterpret_cast<float *>(reinterpret_cast<float4 *>(smem_f) + (size_t)warps_per_block * Lmax * n4);
+    float4 *stage_all = reinterpret_cast<float4 *>(smem_f) + (size_t)warps_per_block * Lmax * n4; // PF == 2: [warp][2 stages][7 rows][32 lanes]
+    constexpr int SROWS = SGNS_CH + 2;
+    float4 *my_stage = stage_all + (size_t)wib * 2 * SROWS * 32 + (threadIdx.x & 31);
+    float *s_exp = reinterpret_cast<float *>(stage_all + (PF == 2 ? (size_t)warps_per_block * 2 * SROWS * 32 : 0));
     int32_t *mytok = reinterpret_cast<int32_t *>(s_exp + a.exp_table_size) + wib * Lmax;
     int32_t *my_tag = reinterpret_cast<int32_t *>(s_exp + a.exp_table_size) + (warps_per_block + wib) * Lmax; // PF: unit of a write-through row's cached update
     uint32_t *s_bits = reinterpret_cast<uint32_t *>(s_exp + a.exp_table_size) + 2 * warps_per_block * Lmax;
     uint32_t *s_pref = s_bits + nwords;
     const bool smem_neg = a.neg_bits != nullptr;
     for (int i = threadIdx.x; i < a.exp_table_size; i += blockDim.x) s_exp[i] = a.exp_table[i];
+    if (PF == 2) // the stages only ever hold table rows afterwards (a slot that is not copied keeps an older row: finite)
+        for (int i = threadIdx.x; i < warps_per_block * 2 * SROWS * 32; i += blockDim.x) stage_all[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (smem_neg)
         for (int i = threadIdx.x; i < 2 * nwords; i += blockDim.x) s_bits[i] = a.neg_bits[i];
     __syncthreads();
@@ -883,7 +897,8 @@ k_sgns_sent(const sgns_args a) {
                     else uT++;
                     return t;
                 };
-                auto stageR = [&](const stage_t &t, stage_r &r) {
+                const uint32_t my_stage_s = (uint32_t)__cvta_generic_to_shared(my_stage);
+                auto stageR = [&](const stage_t &t, stage_r &r, int sidx) {
                     r.last = t.last; r.act = t.act; r.j = t.j; r.c = t.c;
                     int32_t tt = t.traw;
                     const bool redraw = tt != -2 && (tt <= 0 || tt >= a.V);
@@ -893,16 +908,33 @@ k_sgns_sent(const sgns_args a) {
                     r.mine = (tt != -2 && tt != w1) ? tt : -1;
 #pragma unroll
                     for (int k = 0; k < SGNS_CH; k++) r.tg[k] = __shfl_sync(FULL, r.mine, k, G);
+                    if (PF == 2) {
+                        const uint32_t dst = my_stage_s + (uint32_t)(sidx * SROWS * 32 * 16);
+                        cp_async16_if(dst, row_addr(base0, (uint32_t)t.last, pitch), t.act && live);
+#pragma unroll
+                        for (int k = 0; k < SGNS_CH; k++) cp_async16_if(dst + (uint32_t)((k + 1) * 32 * 16), row_addr(base1, (uint32_t)r.tg[k], pitch), r.tg[k] >= 0 && live);
+                        cp_async16_if(dst + (uint32_t)((SGNS_CH + 1) * 32 * 16), row_addr(base1, (uint32_t)w1, pitch), t.act && live && hot_w1);
+                        cp_async_commit();
+                        return;
+                    }
                     if (!MULTI || t.j == 0) ldcg4_into(r.v0, row_addr(base0, (uint32_t)t.last, pitch), t.act && live);
 #pragma unroll
                     for (int k = 0; k < SGNS_CH; k++) ldcg4_into(r.row[k], row_addr(base1, (uint32_t)r.tg[k], pitch), r.tg[k] >= 0 && live);
                     // a write-through centre: its output row as L2 has it now (this lane's own earlier reductions included)
                     if (!MULTI || t.j == 0) ldcg4_into(PF ? r.cur : cur, row_addr(base1, (uint32_t)w1, pitch), t.act && live && hot_w1);
                 };
-                auto compute = [&](const stage_r &r, int u) {
+                auto compute = [&](stage_r &r, int u, int sidx) {
                     const float4 upd_prev = upd_last;
                     upd_last = zero4;
+                    if (PF == 2) cp_async_wait<1>(); // everything but the newest group (the next unit's rows) has landed
                     if (!__any_sync(FULL, r.act)) return;
+                    if (PF == 2) { // this lane's slots of the unit's rows
+                        const float4 *sp = my_stage + sidx * SROWS * 32;
+                        r.v0 = sp[0];
+#pragma unroll
+                        for (int k = 0; k < SGNS_CH; k++) r.row[k] = sp[(k + 1) * 32];
+                        r.cur = sp[(SGNS_CH + 1) * 32];
+                    }
                     const bool first = !MULTI || r.j == 0;
                     if (first) {
                         npairs += r.act;
@@ -976,25 +1008,26 @@ k_sgns_sent(const sgns_args a) {
                     rB.v0 = rB.cur = zero4;
 #pragma unroll
                     for (int k = 0; k < SGNS_CH; k++) rB.row[k] = zero4;
-                    stageR(t1, rA);
+                    stageR(t1, rA, 0);
                     t1 = stageT();
                     for (int u = 0; u < U; u += 2) {
-                        stageR(t1, rB); // the rows of unit u + 1 (nothing is requested past the end: act is false there)
+                        stageR(t1, rB, 1); // the rows of unit u + 1 (nothing is requested past the end: act is false there)
                         t1 = stageT();
-                        compute(rA, u);
+                        compute(rA, u, 0);
                         __syncwarp(); // the cache rows written in this unit are read by other groups in later units
                         if (u + 1 < U) {
-                            stageR(t1, rA);
+                            stageR(t1, rA, 0);
                             t1 = stageT();
-                            compute(rB, u + 1);
+                            compute(rB, u + 1, 1);
                             __syncwarp();
                         }
                     }
+                    if (PF == 2) cp_async_wait<0>(); // no copy may land in a stage the next batch is already filling
                 } else
                 for (int u = 0; u < U; u++) {
-                    stageR(t1, rA);
+                    stageR(t1, rA, 0);
                     t1 = stageT();
-                    compute(rA, u);
+                    compute(rA, u, 0);
                     __syncwarp(); // the cache rows written in this unit are read by other groups in later units
                 }
                 red_add4_if(row_addr(base1, (uint32_t)w1, pitch), d1, valid && live && reds_on && !hot_w1);
@@ -1725,12 +1758,6 @@ k_sgns_wave(const sgns_args a) {
 // (profiles/r1s6_sgns_builds.txt).  cp.async.cg (LDGSTS, L2 only) keeps the rows of unit u+1 in flight through the
 // whole compute of unit u without holding a register: per group 2 stages x 6 rows x G slots x 16 B.  Every lane
 // reads back exactly the slots it copied itself, so cp.async.wait_group is the only synchronisation needed.
-__device__ __forceinline__ void cp_async16_if(uint32_t smem_addr, uint64_t gptr, bool pred) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
-                 ::"r"(smem_addr), "l"(gptr), "r"((int)pred) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ float4 lds4(uint32_t smem_addr) {
     float4 r;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(smem_addr));
@@ -2613,7 +2640,7 @@ struct sgns_variant { int G_seq, VPL_seq, G_items, VPL_items; sgns_kernel_t seq,
 // 16- or 32-lane group one 128-bit slot (2 or 4 for rows wider than 32 slots).
 // Kernel B (items): groups of 8 / 16 / 32 lanes, one slot per lane (2 or 4 beyond 32 slots).
 static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_parallel, bool staged_rows, bool plain_stores, int blk, bool smem_neg,
-                         bool sentence_resident, bool block_sentence, int block_threads, bool pipelined, int pair_warps, bool duo, bool prefetch_f, sgns_variant *out) {
+                         bool sentence_resident, bool block_sentence, int block_threads, bool pipelined, int pair_warps, bool duo, int prefetch_f, sgns_variant *out) {
     if (n4 > 128) return false;
     sgns_kernel_t seq = nullptr, items = nullptr;
     int Gs = 1, Vs = 1;
@@ -2682,9 +2709,9 @@ static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_p
     }
     else if (n4 <= 32 && sentence_resident) { // kernel F: a warp owns a sentence (intra-sentence updates in sequence)
         code = 8;
-        if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_sent<8, true, false> : (prefetch_f ? k_sgns_sent<8, false, true> : k_sgns_sent<8, false, false>); }
-        else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_sent<16, true, false> : k_sgns_sent<16, false, false>; }
-        else { Gi = 32; items = multi ? k_sgns_sent<32, true, false> : k_sgns_sent<32, false, false>; }
+        if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_sent<8, true, 0> : (prefetch_f == 2 ? k_sgns_sent<8, false, 2> : (prefetch_f == 1 ? k_sgns_sent<8, false, 1> : k_sgns_sent<8, false, 0>)); }
+        else if (n4 <= 16) { Gi = 16; items = multi ? k_sgns_sent<16, true, 0> : k_sgns_sent<16, false, 0>; }
+        else { Gi = 32; items = multi ? k_sgns_sent<32, true, 0> : k_sgns_sent<32, false, 0>; }
     }
     else if (n4 <= 8 && smem_neg) { Gi = 8; code = 7; items = multi ? k_sgns_items_v2<8, true, 2> : k_sgns_items_v2<8, false, 2>; }
     else if (n4 <= 8) { Gi = 8; items = multi ? k_sgns_items_v2<8, true, 0> : k_sgns_items_v2<8, false, 0>; }
@@ -2949,7 +2976,10 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
     float *t0 = nullptr, *t1 = nullptr;
     if (multi) {
         float *arena = nullptr;
-        const int rc = dge_dp_arena(ctx, 2 * nel * sizeof(float), &arena);   // collective
+        // sized for the whole id space (V <= n_ids): the vocabulary of the next call (another walk seed) never makes the arena
+        // grow, and a grown arena means every rank re-opens every peer's mapping (8 GPUs: ~400 ms, profiles/r2s33_bench_n8.json)
+        const size_t nel_cap = (size_t)std::max<int64_t>(V ? V : 1, n_ids) * (size_t)stride;
+        const int rc = dge_dp_arena(ctx, 2 * nel_cap * sizeof(float), &arena);   // collective
         if (rc != DGE_OK) { model_release(m); return rc; }
         t0 = arena; t1 = arena + nel;
     }
@@ -3048,7 +3078,8 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
             const bool blk = blk_fits && n4 <= 8 && !(dbg & 8) && !force_warp_per_sentence;
             // kernel I (DGE_SGNS_F_PAIR_WARPS): 8 warps per block unless bits 12-15 of the flags name another count (4 .. 16)
             // kernel F with the rows of the next unit requested ahead (DGE_SGNS_F_ROW_PREFETCH; blocks of at most 12 warps)
-            const bool prefetch_f = (dbg & (1 << 24)) != 0 && p->negative <= SGNS_CH && n4 <= 8;
+            // ... or into shared memory (DGE_SGNS_F_ROW_PREFETCH_SMEM: cp.async, the block keeps its 20 warps)
+            const int prefetch_f = (p->negative <= SGNS_CH && n4 <= 8) ? ((dbg & (1 << 26)) ? 2 : ((dbg & (1 << 24)) ? 1 : 0)) : 0;
             const int pw_req = (dbg >> 12) & 15;
             const int pair_warps = ((dbg & 262144) && Lmax <= 32 && p->negative <= 7) ? (pw_req >= 4 ? pw_req : 8) : 0;
             pick_variant(n4, p->negative, narrow, tp, (dbg & 256) != 0, (dbg & 512) != 0, (dbg >> 12) & 15, smem_neg, sent && !forced_other, blk,
@@ -3096,7 +3127,7 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         // kernel F: bits 12-15 of the flags name the warps of a block (A/B runs: one block per SM with `concurrency` = SMs x warps)
         if (sent_kernel && !block_kernel && ((dbg >> 12) & 15)) threads = 32 * ((dbg >> 12) & 15);
         if (sent_kernel && !block_kernel && auto_wt_warps) threads = 32 * auto_wt_warps;   // one block per SM
-        if (sent_kernel && !block_kernel && (dbg & (1 << 24)) && p->negative <= SGNS_CH && n4 <= 8 && threads > 384) threads = 384;
+        if (sent_kernel && !block_kernel && (dbg & (1 << 24)) && !(dbg & (1 << 26)) && p->negative <= SGNS_CH && n4 <= 8 && threads > 384) threads = 384;
         if (block_kernel) threads = ((Lmax + 32 / G - 1) / (32 / G)) * 32;   // one lane group per position of the longest sentence
         if (wave_kernel) { const int pw = (dbg >> 12) & 15; threads = 32 * (pw >= 4 ? pw : 8); }
         if (duo_kernel) threads *= 2;   // as many helper warps as critical warps
@@ -3139,7 +3170,8 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
                        (d_negbits ? sizeof(uint32_t) * (size_t)2 * nwords : 0) + sizeof(int32_t) * (size_t)Lmax * (size_t)Lmax * (size_t)std::max(1, p->negative);
             if (sent_kernel)
                 return (size_t)(thr / 32) * (size_t)Lmax * (size_t)n4 * 16 + sizeof(float) * (size_t)p->exp_table_size +
-                       sizeof(int32_t) * 2 * (size_t)(thr / 32) * (size_t)Lmax + (d_negbits ? sizeof(uint32_t) * (size_t)2 * nwords : 0);
+                       sizeof(int32_t) * 2 * (size_t)(thr / 32) * (size_t)Lmax + (d_negbits ? sizeof(uint32_t) * (size_t)2 * nwords : 0) +
+                       (((dbg & (1 << 26)) && p->negative <= SGNS_CH && n4 <= 8) ? (size_t)(thr / 32) * 2 * (SGNS_CH + 2) * 32 * 16 : 0);
             return sizeof(float) * (size_t)p->exp_table_size + (sequential ? 0 : sizeof(int32_t) * (size_t)(thr / G) * (size_t)Lmax) +
                    (!sequential && var.items_code == 5 ? (size_t)thr * 2 * (SGNS_CH + 1) * 16 : 0) + // kernel C': two row stages per lane
                    (var.items_code == 7 ? (((size_t)p->neg_table_size * 2 + 15) / 16) * 16 : 0);

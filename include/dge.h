@@ -232,6 +232,7 @@ enum { DGE_SGNS_F_NO_UPDATES = 1,     /* timing experiment: compute everything, 
        DGE_SGNS_F_HOT_SHIFT = 20,         /* not a flag: bits 20-23 = v > 0 makes the 2^(v-1) most frequent words write-through in kernel F */
        DGE_SGNS_F_ROW_PREFETCH = 1 << 24, /* kernel F, rows of up to 8 slots, K <= 5: the rows of the next unit are requested before the current one is computed */
        DGE_SGNS_F_DYNAMIC = 1 << 25,      /* kernel F: sentences handed out in corpus order from a counter instead of strided by warp */
+       DGE_SGNS_F_ROW_PREFETCH_SMEM = 1 << 26, /* the same with the requested rows landing in shared memory (cp.async) instead of registers */
        DGE_SGNS_F_PIPELINED = 131072,     /* kernel H: kernel G with the sentences of a block pipelined through the wavefront */
        DGE_SGNS_F_ITEM_KERNELS = 65536,   /* the round-1 item kernels B-E with their automatic choice (centres of a sentence in flight at once) */
        DGE_SGNS_F_SMALL_BLOCKS = 16,  /* sentence-resident kernel: 128-thread blocks instead of one 640-thread block per SM */

@@ -136,6 +136,8 @@ def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negati
         flag_sets.append(L.F_ONE_WARP | L.F_SENTENCE_RESIDENT | L.F_ROW_PREFETCH)
         flag_sets.append(L.F_ONE_WARP | L.F_SENTENCE_RESIDENT | L.F_ROW_PREFETCH | (8 << 20))
         flag_sets.append(L.F_ONE_WARP | L.F_SENTENCE_RESIDENT | L.F_ROW_PREFETCH | (12 << 20))
+        flag_sets.append(L.F_ONE_WARP | L.F_SENTENCE_RESIDENT | L.F_ROW_PREFETCH_SMEM)             # ... requested into shared memory (cp.async)
+        flag_sets.append(L.F_ONE_WARP | L.F_SENTENCE_RESIDENT | L.F_ROW_PREFETCH_SMEM | (8 << 20))
     for flags in flag_sets:
         e0, e1 = rel_err(flags=flags)
         # plain stores lose an update whenever one row is drawn twice within a unit (both copies start from the same load)
@@ -167,7 +169,7 @@ def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negati
         # one warp, its four lane groups staggered over the contexts (a legitimate sequential order of the sentence's pairs),
         # write-through words and row prefetch: the cached-update bookkeeping between the groups must be exact
         b0, b1 = rel_err(concurrency=1, schedule=dge_lib.SCHEDULE_ITEMS, flags=L.F_SENTENCE_RESIDENT)
-        for extra in (8 << 20, L.F_ROW_PREFETCH | (8 << 20), L.F_ROW_PREFETCH | (12 << 20), L.F_DYNAMIC | (8 << 20)):
+        for extra in (8 << 20, L.F_ROW_PREFETCH | (8 << 20), L.F_ROW_PREFETCH | (12 << 20), L.F_DYNAMIC | (8 << 20), L.F_ROW_PREFETCH_SMEM | (8 << 20)):
             e0, e1 = rel_err(concurrency=1, schedule=dge_lib.SCHEDULE_ITEMS, flags=L.F_SENTENCE_RESIDENT | extra)
             assert e0 < 1.25 * b0 + 0.02 and e1 < 1.25 * b1 + 0.02, ("kernel F, one sentence in flight", extra, e0, e1, b0, b1)
     e0, e1 = rel_err(concurrency=2)                 # two sentences in flight
