@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "embedding_b200", "libdge.so")
-KERNELS = ["k_walk_alias", "k_walk_cdf", "k_sgns_items_v2ILi8ELb0ELb0E", "k_sgns_items_v2ILi32ELb0ELb0E", "k_sgns_items_tpILi2E",
+KERNELS = ["k_walk_alias", "k_walk_cdf", "k_sgns_sentILi8ELb0ELi0E", "k_sgns_sentILi32ELb0ELi0E", "k_sgns_blockILi8ELb0ELi192E", "k_sgns_items_v2ILi8ELb0ELb0E", "k_sgns_items_v2ILi32ELb0ELb0E", "k_sgns_items_tpILi2E",
            "k_sgns_items_g4ILi1ELb0E", "k_sgns_seqILi1ELi5E", "k_dp_exchange_peerILi1E", "k_alias_small", "k_seq_format"]
 
 

@@ -39,6 +39,22 @@ def test_sgns_params_struct_layout_matches_ctypes(dge_lib):
     assert abs(p.lr - 0.025) < 1e-9 and abs(p.min_lr - 1e-4) < 1e-9 and p.seed == 1
 
 
+def test_flag_constants_match_the_header(dge_lib):
+    """The F_* constants of the ctypes binding are the DGE_SGNS_F_* values of include/dge.h."""
+    src = open(os.path.join(ROOT, "include", "dge.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    header = {}
+    for name, val in re.findall(r"DGE_SGNS_F_([A-Z0-9_]+)\s*=\s*([^,}]+)", src):
+        header[name] = eval(val.strip(), {"__builtins__": {}})
+    assert len(header) >= 20
+    checked = 0
+    for name, val in header.items():
+        if hasattr(dge_lib, "F_" + name):
+            assert getattr(dge_lib, "F_" + name) == val, name
+            checked += 1
+    assert checked >= 12
+
+
 def test_no_silent_cpu_fallback(dge_lib):
     """Without a CUDA device dge_create must fail with DGE_E_NO_DEVICE and say so."""
     h = C.c_void_p()
