@@ -180,6 +180,35 @@ def test_item_kernel_arithmetic_matches_oracle(dge_lib, oracle, ctx, dim, negati
     assert e1 < 0.5 and e0 < 1.5, (e0, e1)
 
 
+def test_automatic_schedule_on_a_mid_size_vocabulary(dge_lib, oracle, ctx):
+    """flags = 0, concurrency = 0 on narrow rows and a vocabulary of thousands of words: kernel F (a warp per sentence), the
+    sentences handed out from the device counter, the most frequent words written through, a whole number of warps per SM in
+    flight and never more sentences than vocabulary words.  The enumeration does not depend on the schedule:
+    exactly the oracle's pairs.  The same corpus with write-through forced off / on by flags trains the same pairs too."""
+    rng = np.random.default_rng(77)
+    n_ids, n_sent, L = 12000, 60000, 12
+    p = 1.0 / (np.arange(n_ids) + 20.0)                      # a Zipf-like word distribution: a few hub words
+    tok = rng.choice(n_ids, size=(n_sent, L), p=p / p.sum()).astype(np.int32)
+    kw = dict(dim=20, window=6, negative=5, min_count=2, seed=9)
+    ref = oracle.sgns_train(tok, n_ids, oracle.sgns_params(threads=8, **kw))
+    c = dge_lib.Corpus.from_tokens(ctx, tok, n_ids)
+    m = dge_lib.Model.train(ctx, [c], dge_lib.sgns_params(**kw))
+    assert m.pairs == ref["pairs"] and m.V == len(ref["id_of_word"])
+    assert int(ctx.phase_ms("sgns_kernel")) == 8                           # k_sgns_sent
+    in_flight, hot = int(ctx.phase_ms("sgns_groups")), int(ctx.phase_ms("sgns_write_through"))
+    assert 0 < hot <= m.V and in_flight <= m.V and in_flight <= n_sent
+    syn0, _ = m.vectors()
+    assert np.isfinite(syn0).all()
+    norm_auto = float(np.linalg.norm(syn0, axis=1).mean())
+    norm_ref = float(np.linalg.norm(ref["syn0"], axis=1).mean())
+    assert 0.5 * norm_ref < norm_auto < 2.0 * norm_ref, (norm_auto, norm_ref)   # neither collapsed nor blown up (5 % of this corpus is in flight at once)
+    L_ = dge_lib
+    for flags in (L_.F_SENTENCE_RESIDENT | L_.F_DYNAMIC, L_.F_SENTENCE_RESIDENT | L_.F_DYNAMIC | (9 << 20)):
+        m2 = dge_lib.Model.train(ctx, [c], dge_lib.sgns_params(concurrency=in_flight, flags=flags, **kw))
+        assert m2.pairs == ref["pairs"]
+        assert int(ctx.phase_ms("sgns_write_through")) == (256 if (flags >> 20) & 15 else 0)
+
+
 def test_vec_file_format(dge_lib, ctx, tmp_path):
     """WordVectorSerializer.writeWordVectors as its consumers read it (embeddingEvaluation_tract.py:139-166,
     skipheader=0): "<layer>-<region> v1 ... vD", one line per vocabulary word."""
