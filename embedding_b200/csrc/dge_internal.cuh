@@ -99,6 +99,7 @@ struct dge_model {
     int64_t pairs = 0;   // (centre, context) updates executed
     int64_t words = 0;   // in-vocabulary tokens of the corpus
     float *syn0 = nullptr, *syn1neg = nullptr; // device [V*stride]
+    float *syn0_alloc = nullptr, *syn1neg_alloc = nullptr; // what was allocated (the tables may start at an offset inside: placement)
     int32_t *id_of_word = nullptr;             // device [V]
 };
 

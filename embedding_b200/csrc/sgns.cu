@@ -17,6 +17,43 @@
 #include "sgns_kernels_items.cuh"
 #include "sgns_kernels_sentence.cuh"
 
+// Placement probe.  The tables of the CA / tract workloads are a few MB and L2-resident, their traffic is concentrated on the
+// rows of the frequent words, and how those rows fall on the L2 slices depends on where the tables start: the same launch
+// took 987 ms at one base address and 1 018 / 1 040 / 1 148 / 1 239 / 1 401 ms at others (scripts/spread_probe.py,
+// profiles/r2s36_spread_probe_before.json).  dge_sgns_train therefore allocates small tables with some slack, runs this
+// probe -- random rows drawn from the unigram^0.75 table, one syn0 row loaded and two syn1neg rows loaded and reduced
+// (with zeros) per step, from a full GPU of warps -- at a few candidate offsets, and trains at the fastest one.
+#define SGNS_PLACE_CANDIDATES 24
+#define SGNS_PLACE_STEP_FLOATS 9216            // 36 KB between candidates
+#define SGNS_PLACE_MAX_BYTES (8u << 20)        // only tables this small are placed
+__global__ void __launch_bounds__(640, 1)
+k_place_probe(float *syn0, float *syn1neg, const int32_t *__restrict__ neg_table, uint32_t tsize, int32_t stride, int32_t n4, int iters, uint32_t seed) {
+    const int lane = threadIdx.x & 7;
+    const bool live = lane < n4;
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    uint64_t x = mix64(0x9E3779B97F4A7C15ULL * (uint64_t)(g + 1) + seed);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc = 0.f;
+    for (int it = 0; it < iters; it++) {
+        x = x * LCG_MUL + LCG_ADD;
+        const uint32_t i0 = (uint32_t)(((x >> 16) & 0xFFFFFFFFULL) * tsize >> 32);
+        const uint32_t i1 = (uint32_t)(((x >> 24) & 0xFFFFFFFFULL) * tsize >> 32);
+        const uint32_t i2 = (uint32_t)(((x >> 32) & 0xFFFFFFFFULL) * tsize >> 32);
+        const int32_t r0 = neg_table[i0], r1 = neg_table[i1], r2 = neg_table[i2];
+        if (live) {
+            float4 *p0 = reinterpret_cast<float4 *>(syn0 + (int64_t)r0 * stride) + lane;
+            float4 *p1 = reinterpret_cast<float4 *>(syn1neg + (int64_t)r1 * stride) + lane;
+            float4 *p2 = reinterpret_cast<float4 *>(syn1neg + (int64_t)r2 * stride) + lane;
+            const float4 a = __ldcg(p0), b = __ldcg(p1), c = __ldcg(p2);
+            acc += a.x + b.x + c.x;
+            red_add4(p1, zero4);
+            red_add4(p2, zero4);
+            if ((it & 7) == 0) red_add4(p0, zero4);
+        }
+    }
+    if (acc == 1234.5678f) syn0[0] = acc; // keeps the loads alive
+}
+
 // dge_model_stats: one warp per row of each table; acc[0] += |syn0 row|, acc[1] = max |element| (non-negative doubles
 // order like their bit patterns), bad += non-finite elements
 __global__ void k_model_stats(const float *__restrict__ syn0, const float *__restrict__ syn1neg, int32_t V, int32_t dim,
@@ -140,7 +177,7 @@ static bool pick_variant(int n4, int negative, bool narrow_groups, bool target_p
 
 static void model_release(dge_model *m) {
     if (!m) return;
-    dge_free(m->ctx, m->syn0); dge_free(m->ctx, m->syn1neg);
+    dge_free(m->ctx, m->syn0_alloc ? m->syn0_alloc : m->syn0); dge_free(m->ctx, m->syn1neg_alloc ? m->syn1neg_alloc : m->syn1neg);
     dge_free(m->ctx, m->id_of_word);
     dge_delete_handle(m);
 }
@@ -397,7 +434,10 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         if (rc != DGE_OK) { model_release(m); return rc; }
         t0 = arena; t1 = arena + nel;
     }
-    bool ok = dge_malloc(ctx, &m->syn0, nel) == cudaSuccess && dge_malloc(ctx, &m->syn1neg, nel) == cudaSuccess;
+    const bool place = !multi && train && nel * sizeof(float) <= SGNS_PLACE_MAX_BYTES && SGNS_PLACE_CANDIDATES > 1;
+    const size_t slack = place ? (size_t)SGNS_PLACE_CANDIDATES * SGNS_PLACE_STEP_FLOATS : 0;
+    bool ok = dge_malloc(ctx, &m->syn0, nel + slack) == cudaSuccess && dge_malloc(ctx, &m->syn1neg, nel + slack) == cudaSuccess;
+    m->syn0_alloc = m->syn0; m->syn1neg_alloc = m->syn1neg;
     if (!multi) { t0 = m->syn0; t1 = m->syn1neg; }
     ok = ok && dge_malloc(ctx, &m->id_of_word, (size_t)V) == cudaSuccess && tmp.get(&d_word_of_id, (size_t)n_ids) == cudaSuccess &&
          tmp.get(&d_table, (size_t)p->neg_table_size) == cudaSuccess && tmp.get(&d_exp, (size_t)p->exp_table_size) == cudaSuccess &&
@@ -405,6 +445,40 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
     local = ok ? DGE_OK : dge_fail(ctx, DGE_E_CUDA, std::string("dge_sgns_train: cudaMalloc failed (") + cudaGetErrorString(cudaGetLastError()) + ")");
     if (multi) local = dge_comm_agree(ctx, local, "dge_sgns_train (tables)");
     if (local != DGE_OK) { model_release(m); return local; }
+    ctx->phase_ms["sgns_placement"] = 0.f; ctx->phase_ms["sgns_placement_best_us"] = 0.f; ctx->phase_ms["sgns_placement_worst_us"] = 0.f;
+    if (place) { // where inside the allocations do the tables train fastest?  (before anything is written to them)
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (cudaMemcpyAsync(d_table, table.data(), sizeof(int32_t) * table.size(), cudaMemcpyHostToDevice, st) == cudaSuccess &&
+            cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) {
+            cudaMemsetAsync(m->syn0_alloc, 0, (nel + slack) * sizeof(float), st);
+            cudaMemsetAsync(m->syn1neg_alloc, 0, (nel + slack) * sizeof(float), st);
+            float best = 1e30f, worst = 0.f;
+            int best_k = 0;
+            k_place_probe<<<ctx->sm_count, 640, 0, st>>>(m->syn0_alloc, m->syn1neg_alloc, d_table, (uint32_t)p->neg_table_size, stride, n4, 32, 0u); // warm-up
+            for (int k = 0; k < SGNS_PLACE_CANDIDATES; k++) {
+                float ms_k = 1e30f;
+                for (int rep = 0; rep < 2; rep++) {
+                    float ms = 0.f;
+                    cudaEventRecord(e0, st);
+                    k_place_probe<<<ctx->sm_count, 640, 0, st>>>(m->syn0_alloc + (size_t)k * SGNS_PLACE_STEP_FLOATS, m->syn1neg_alloc + (size_t)k * SGNS_PLACE_STEP_FLOATS,
+                                                                d_table, (uint32_t)p->neg_table_size, stride, n4, 128, (uint32_t)(17 * rep + 1));
+                    cudaEventRecord(e1, st);
+                    if (cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) ms_k = std::min(ms_k, ms);
+                }
+                ctx->launches += 2;
+                if (ms_k < best) { best = ms_k; best_k = k; }
+                if (ms_k < 1e29f) worst = std::max(worst, ms_k);
+            }
+            if (cudaGetLastError() == cudaSuccess && best < 1e29f) {
+                m->syn0 = m->syn0_alloc + (size_t)best_k * SGNS_PLACE_STEP_FLOATS;
+                m->syn1neg = m->syn1neg_alloc + (size_t)best_k * SGNS_PLACE_STEP_FLOATS;
+                t0 = m->syn0; t1 = m->syn1neg;
+                ctx->phase_ms["sgns_placement"] = (float)best_k; ctx->phase_ms["sgns_placement_best_us"] = best * 1e3f; ctx->phase_ms["sgns_placement_worst_us"] = worst * 1e3f;
+            }
+        } else cudaGetLastError();
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
     cudaMemsetAsync(t0, 0, nel * sizeof(float), st);
     cudaMemsetAsync(t1, 0, nel * sizeof(float), st);
     cudaMemsetAsync(d_pairs, 0, 2 * sizeof(unsigned long long), st);
@@ -417,6 +491,9 @@ int dge_sgns_train(dge_ctx *ctx, const dge_corpus *const *corpora, int32_t n_cor
         k_init_syn0<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t0, V, p->dim, stride, p->seed);
         ctx->launches++;
     }
+    // where the tables landed (bits 8-19 and 20-39 of their addresses): a diagnostic for the run-to-run spread of the kernel time
+    ctx->phase_ms["sgns_syn0_addr_lo"] = (float)(((uintptr_t)t0 >> 8) & 0xFFF); ctx->phase_ms["sgns_syn0_addr_hi"] = (float)(((uintptr_t)t0 >> 20) & 0xFFFFF);
+    ctx->phase_ms["sgns_syn1_addr_lo"] = (float)(((uintptr_t)t1 >> 8) & 0xFFF); ctx->phase_ms["sgns_syn1_addr_hi"] = (float)(((uintptr_t)t1 >> 20) & 0xFFFFF);
     ctx->phase_ms["sgns_rounds"] = 0.f; ctx->phase_ms["sgns_sync"] = 0.f; ctx->phase_ms["sgns_transport"] = 0.f; ctx->phase_ms["sgns_dp_setup"] = 0.f;
     ctx->phase_ms["compact"] = 0.f; ctx->phase_ms["sgns"] = 0.f;
 
